@@ -1,0 +1,62 @@
+"""ctypes binding of the C ABI declared in include/giga_b200.h (libgiga_b200.so).
+
+There is deliberately no fallback: if the CUDA library is missing or cannot be
+loaded the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libgiga_b200.so")
+
+HEAD_QUAL, HEAD_ROT, HEAD_WIDTH, HEAD_TSDF = 1, 2, 4, 8
+HEAD_GRASP = HEAD_QUAL | HEAD_ROT | HEAD_WIDTH
+
+# symbol -> (restype, argtypes); must list every function include/giga_b200.h declares
+_F = C.POINTER(C.c_float)
+SYMBOLS = {
+    "giga_version": (C.c_int, []),
+    "giga_last_error": (C.c_char_p, []),
+    "giga_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "giga_ctx_destroy": (None, [C.c_void_p]),
+    "giga_ctx_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long, C.c_int]),
+    "giga_ctx_commit_params": (C.c_int, [C.c_void_p]),
+    "giga_ctx_heads": (C.c_uint, [C.c_void_p]),
+    "giga_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "giga_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_sample_feature": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "giga_scene_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_ctx_launch_count": (C.c_long, [C.c_void_p]),
+    "giga_debug_copy": (C.c_long, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p]),
+}
+
+
+class GigaError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the giga_b200 CUDA library is not built. Run "
+            "`python -m giga_b200.build` (or __graft_entry__.build()). There is no CPU/PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = "") -> int:
+    if rc < 0:
+        raise GigaError(f"{what}: {lib.giga_last_error().decode()} (code {rc})")
+    return rc

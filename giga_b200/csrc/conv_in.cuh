@@ -1,0 +1,172 @@
+// Fused  Conv3d(1->32, k3, pad 1) + ReLU + the three tri-plane means.
+//
+// Replaces (reference, relative to src/vgn/ConvONets):
+//   encoder/voxels.py:95-108   voxel coords + relu(conv_in(x)) -> an 8.19 MB/scene feature volume
+//   encoder/voxels.py:57-66    3x  normalize_coordinate + coordinate2index + torch_scatter.scatter_mean
+// With a 40^3 grid scattered onto 40^2 cells the index map is the identity per axis and
+// every cell averages exactly the 40 voxels along the perpendicular axis (SURVEY.md 8a-a4,
+// tests/test_oracle_golden.py::test_plane_mean_identity), so the feature volume is never
+// materialised: each thread owns one (iy,iz) voxel column, marches along ix with a 3x3x3
+// register window, and the three axis sums are formed on the fly:
+//   yz[c][iz][iy] = sum_ix f   -> thread-private registers
+//   xy[c][iy][ix] = sum_iz f   -> per-step shared-memory row reduction
+//   xz[c][iz][ix] = sum_iy f   -> per-step reduction over the CTA's TY rows, then one partial
+//                                 per CTA (deterministic order; finished by xz_finish_kernel)
+// Weights (27x32) + bias live in the kernel parameter space (constant bank): every FFMA takes
+// its weight as an immediate constant-bank operand, so the inner loop is pure FFMA.
+#pragma once
+#include "common.cuh"
+
+namespace giga {
+
+struct ConvInParams {
+  float w[27][32];  // [tap = dx*9 + dy*3 + dz][cout]   (cross-correlation, voxels.py:36)
+  float b[32];
+};
+
+constexpr int CI_TY = 4;            // iy rows per CTA
+constexpr int CI_NT = G / CI_TY;    // 10 CTAs per scene
+constexpr int CI_THREADS = CI_TY * G;  // 160
+constexpr int CI_XS_Z = 44;         // padded iz extent (iz+1 in 0..41, +2 pad)
+constexpr int CI_XS_Y = CI_TY + 2;
+constexpr int CI_XS_X = G + 2;
+constexpr int CI_XS = CI_XS_X * CI_XS_Y * CI_XS_Z;        // 11088 floats
+constexpr int CI_RED_STRIDE = 41;
+constexpr int CI_RED = C * CI_TY * CI_RED_STRIDE;          // 5248 floats
+constexpr int CI_XYACC = C * CI_TY * CI_RED_STRIDE;        // 5248 floats
+constexpr int CI_SMEM_BYTES = (CI_XS + CI_RED + CI_XYACC) * 4;  // 86,336 B
+
+// grid (CI_NT, B), block CI_THREADS
+__global__ void __launch_bounds__(CI_THREADS, 2)
+conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
+                      float* __restrict__ pre,       // [3][B][32][40][40]  (xz, xy, yz), NCHW
+                      float* __restrict__ xz_part,   // [B][CI_NT][40 ix][32][40 iz]
+                      int B, const __grid_constant__ ConvInParams P) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                 // [42][TY+2][44]
+  float* red = xs + CI_XS;          // [32*TY][41]
+  float* xyacc = red + CI_RED;      // [32*TY][41]  (col = ix)
+
+  const int tile = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int iyl = tid / G, iz = tid % G;
+  const int iy0 = tile * CI_TY;
+
+  // stage the CTA's whole input footprint (42 x 6 x 44, zero padded halo)
+  const float* xb = x + (size_t)b * G3;
+  for (int e = tid; e < CI_XS; e += CI_THREADS) {
+    const int zp = e % CI_XS_Z;
+    const int yp = (e / CI_XS_Z) % CI_XS_Y;
+    const int xp = e / (CI_XS_Z * CI_XS_Y);
+    const int gx = xp - 1, gy = iy0 + yp - 1, gz = zp - 1;
+    float v = 0.f;
+    if (gx >= 0 && gx < G && gy >= 0 && gy < G && gz >= 0 && gz < G) v = __ldg(xb + (gx * G + gy) * G + gz);
+    xs[e] = v;
+  }
+  __syncthreads();
+
+  float yz[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) yz[c] = 0.f;
+
+  float win[3][9];  // [dx][dy*3+dz]
+  {
+    const float* s0 = xs + (0 * CI_XS_Y + iyl) * CI_XS_Z + iz;
+    const float* s1 = xs + (1 * CI_XS_Y + iyl) * CI_XS_Z + iz;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dz = 0; dz < 3; ++dz) {
+        win[1][dy * 3 + dz] = s0[dy * CI_XS_Z + dz];
+        win[2][dy * 3 + dz] = s1[dy * CI_XS_Z + dz];
+      }
+  }
+
+#pragma unroll 1
+  for (int ix = 0; ix < G; ++ix) {
+    {
+      const float* s2 = xs + ((ix + 2) * CI_XS_Y + iyl) * CI_XS_Z + iz;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        win[0][t] = win[1][t];
+        win[1][t] = win[2][t];
+      }
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) win[2][dy * 3 + dz] = s2[dy * CI_XS_Z + dz];
+    }
+    float f[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) f[c] = P.b[c];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float v = win[dx][t];
+#pragma unroll
+        for (int c = 0; c < C; ++c) f[c] = fmaf(P.w[dx * 9 + t][c], v, f[c]);
+      }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float r = fmaxf(f[c], 0.f);
+      yz[c] += r;
+      red[(c * CI_TY + iyl) * CI_RED_STRIDE + iz] = r;
+    }
+    __syncthreads();
+    // xy[c][iy][ix] = sum over iz (ascending, the reference's scatter order)
+    if (tid < C * CI_TY) {
+      const float* r = red + tid * CI_RED_STRIDE;
+      float s = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < G; ++k) s += r[k];
+      xyacc[tid * CI_RED_STRIDE + ix] = s;
+    }
+    // xz partial[ix][c][iz] = sum over this CTA's TY rows
+    float* part = xz_part + (((size_t)b * CI_NT + tile) * G + ix) * (C * G);
+    for (int o = tid; o < C * G; o += CI_THREADS) {
+      const int c = o / G, z = o % G;
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < CI_TY; ++r) s += red[(c * CI_TY + r) * CI_RED_STRIDE + z];
+      part[o] = s;
+    }
+    __syncthreads();
+  }
+
+  // yz[c][iz][iy]: transpose through smem so each (c,iz) row segment is one 16 B store
+  float* stage = red;  // [32][40][TY] = 5120 floats <= CI_RED
+#pragma unroll
+  for (int c = 0; c < C; ++c) stage[(c * G + iz) * CI_TY + iyl] = yz[c] / 40.0f;
+  __syncthreads();
+  float* pre_yz = pre + ((size_t)(2 * B + b) * C) * G2;
+  for (int o = tid; o < C * G; o += CI_THREADS) {
+    const int c = o / G, z = o % G;
+    st4(pre_yz + (c * G + z) * G + iy0, ld4(stage + o * CI_TY));
+  }
+  float* pre_xy = pre + ((size_t)(1 * B + b) * C) * G2;
+  for (int o = tid; o < C * CI_TY * G; o += CI_THREADS) {
+    const int j = o / G, ix = o % G;  // j = c*TY + iyl
+    const int c = j / CI_TY, r = j % CI_TY;
+    pre_xy[(c * G + iy0 + r) * G + ix] = xyacc[j * CI_RED_STRIDE + ix] / 40.0f;
+  }
+}
+
+// xz[b][c][iz][ix] = (sum_t xz_part[b][t][ix][c][iz]) / 40      grid (32, B), block 256
+__global__ void __launch_bounds__(256)
+xz_finish_kernel(const float* __restrict__ xz_part, float* __restrict__ pre, int B) {
+  __shared__ float tile[G * 41];
+  const int c = blockIdx.x, b = blockIdx.y;
+  for (int e = threadIdx.x; e < G2; e += 256) {
+    const int ix = e / G, z = e % G;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < CI_NT; ++t) s += xz_part[((((size_t)b * CI_NT + t) * G + ix) * C + c) * G + z];
+    tile[z * 41 + ix] = s / 40.0f;
+  }
+  __syncthreads();
+  float* o = pre + ((size_t)(0 * B + b) * C + c) * G2;
+  for (int e = threadIdx.x; e < G2; e += 256) o[e] = tile[(e / G) * 41 + (e % G)];
+}
+
+}  // namespace giga

@@ -1,0 +1,469 @@
+// C ABI of libgiga_b200.so (see include/giga_b200.h): context, parameter packing, kernel launches.
+// Pure CUDA runtime -- no torch, no CPU compute fallback.
+#include "../../include/giga_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_in.cuh"
+#include "decoder.cuh"
+#include "unet.cuh"
+
+using namespace giga;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                               \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(GIGA_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+// U-Net layer tile configurations (HW, CIN0, CIN1, COUT, R, CT, TCO, CC, POOL)
+using K_d0c1 = Conv3x3Cfg<40, 32, 0, 32, 4, 32, 4, 16, false>;
+using K_d0c2 = Conv3x3Cfg<40, 32, 0, 32, 4, 32, 4, 16, true>;
+using K_d1c1 = Conv3x3Cfg<20, 32, 0, 64, 4, 64, 4, 16, false>;
+using K_d1c2 = Conv3x3Cfg<20, 64, 0, 64, 4, 64, 4, 16, true>;
+using K_d2c1 = Conv3x3Cfg<10, 64, 0, 128, 10, 32, 4, 16, false>;
+using K_d2c2 = Conv3x3Cfg<10, 128, 0, 128, 10, 32, 4, 16, false>;
+using K_u0c1 = Conv3x3Cfg<20, 64, 64, 64, 4, 64, 4, 16, false>;
+using K_u0c2 = Conv3x3Cfg<20, 64, 0, 64, 4, 64, 4, 16, false>;
+using K_u1c1 = Conv3x3Cfg<40, 32, 32, 32, 4, 32, 4, 16, false>;
+using K_u1c2 = Conv3x3Cfg<40, 32, 0, 32, 4, 32, 4, 16, false>;
+using K_u0up = ConvTCfg<10, 128, 64, 10, 16, 32>;
+using K_u1up = ConvTCfg<20, 64, 32, 4, 32, 32>;
+
+struct ParamSpec {
+  const char* name;
+  long numel;
+};
+
+// packed encoder blob offsets (floats)
+struct EncLayout {
+  long conv[10];   // d0c1 d0c2 d1c1 d1c2 d2c1 d2c2 u0c1 u0c2 u1c1 u1c2 : [CIN][9][COUT]
+  long bias[10];
+  long up_w[2], up_b[2];
+  long fin_w, fin_b;
+  long total;
+};
+const int kConvCin[10] = {32, 32, 32, 64, 64, 128, 128, 64, 64, 32};
+const int kConvCout[10] = {32, 32, 64, 64, 128, 128, 64, 64, 32, 32};
+const char* kConvName[10] = {"down_convs.0.conv1", "down_convs.0.conv2", "down_convs.1.conv1", "down_convs.1.conv2",
+                             "down_convs.2.conv1", "down_convs.2.conv2", "up_convs.0.conv1",   "up_convs.0.conv2",
+                             "up_convs.1.conv1",   "up_convs.1.conv2"};
+const int kUpCin[2] = {128, 64}, kUpCout[2] = {64, 32};
+const char* kHeadName[4] = {"qual", "rot", "width", "tsdf"};
+
+EncLayout make_enc_layout() {
+  EncLayout L;
+  long o = 0;
+  for (int i = 0; i < 10; ++i) { L.conv[i] = o; o += (long)kConvCin[i] * 9 * kConvCout[i]; L.bias[i] = o; o += kConvCout[i]; }
+  for (int i = 0; i < 2; ++i) { L.up_w[i] = o; o += (long)kUpCin[i] * kUpCout[i] * 4; L.up_b[i] = o; o += kUpCout[i]; }
+  L.fin_w = o; o += 32 * 32;
+  L.fin_b = o; o += 32;
+  L.total = o;
+  return L;
+}
+
+// activation workspace: name -> floats per image (3B images), in forward order
+struct ActSpec { const char* name; int ch, hw; };
+const ActSpec kActs[] = {{"d0c1", 32, 40}, {"d0c2", 32, 40}, {"p0", 32, 20},  {"d1c1", 64, 20}, {"d1c2", 64, 20},
+                         {"p1", 64, 10},   {"d2c1", 128, 10}, {"d2c2", 128, 10}, {"u0", 64, 20},  {"u0c1", 64, 20},
+                         {"u0c2", 64, 20}, {"u1", 32, 40},   {"u1c1", 32, 40}, {"u1c2", 32, 40}};
+constexpr int kNumActs = sizeof(kActs) / sizeof(kActs[0]);
+
+}  // namespace
+
+struct giga_ctx {
+  int device = 0;
+  std::map<std::string, std::vector<float>> raw;  // reference-layout parameters (host copies)
+  bool committed = false;
+  unsigned heads = 0;
+  bool has_encoder = false;
+  ConvInParams conv_in;
+  EncLayout el;
+  float* d_enc = nullptr;    // packed encoder blob
+  float* d_heads = nullptr;  // [4][DW_HEAD]
+  // workspaces (sized for cap_B scenes)
+  int cap_B = 0;
+  int last_B = 0;
+  float* d_pre = nullptr;      // [3][B][32][1600]
+  float* d_xzpart = nullptr;   // [B][10][40][32][40]
+  float* d_act[kNumActs] = {};
+  // host-entry staging (device side)
+  float *h_tsdf = nullptr, *h_planes = nullptr, *h_p = nullptr, *h_pt = nullptr;
+  float *h_qual = nullptr, *h_rot = nullptr, *h_width = nullptr, *h_occ = nullptr;
+  int hcap_B = 0, hcap_Ng = 0, hcap_No = 0;
+  long launches = 0;
+  bool attrs_set = false;
+};
+
+namespace {
+
+int set_device(giga_ctx* ctx) {
+  CU_TRY(cudaSetDevice(ctx->device));
+  return GIGA_OK;
+}
+
+int ensure_attrs(giga_ctx* ctx) {
+  if (ctx->attrs_set) return GIGA_OK;
+  CU_TRY(cudaFuncSetAttribute(conv_in_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CI_SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(decode_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(sample_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
+#define SET_CONV(K) CU_TRY(cudaFuncSetAttribute(conv3x3_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES))
+  SET_CONV(K_d0c1); SET_CONV(K_d0c2); SET_CONV(K_d1c1); SET_CONV(K_d1c2); SET_CONV(K_d2c1);
+  SET_CONV(K_d2c2); SET_CONV(K_u0c1); SET_CONV(K_u0c2); SET_CONV(K_u1c1); SET_CONV(K_u1c2);
+#undef SET_CONV
+  CU_TRY(cudaFuncSetAttribute(convT2x2_kernel<K_u0up>, cudaFuncAttributeMaxDynamicSharedMemorySize, K_u0up::SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(convT2x2_kernel<K_u1up>, cudaFuncAttributeMaxDynamicSharedMemorySize, K_u1up::SMEM_BYTES));
+  ctx->attrs_set = true;
+  return GIGA_OK;
+}
+
+int ensure_workspace(giga_ctx* ctx, int B) {
+  if (B <= ctx->cap_B) return GIGA_OK;
+  CU_TRY(cudaDeviceSynchronize());
+  if (ctx->d_pre) cudaFree(ctx->d_pre);
+  if (ctx->d_xzpart) cudaFree(ctx->d_xzpart);
+  for (auto& p : ctx->d_act) { if (p) cudaFree(p); p = nullptr; }
+  ctx->d_pre = ctx->d_xzpart = nullptr;
+  ctx->cap_B = 0;
+  CU_TRY(cudaMalloc(&ctx->d_pre, sizeof(float) * 3 * (size_t)B * C * G2));
+  CU_TRY(cudaMalloc(&ctx->d_xzpart, sizeof(float) * (size_t)B * CI_NT * G * C * G));
+  for (int i = 0; i < kNumActs; ++i)
+    CU_TRY(cudaMalloc(&ctx->d_act[i], sizeof(float) * 3 * (size_t)B * kActs[i].ch * kActs[i].hw * kActs[i].hw));
+  ctx->cap_B = B;
+  return GIGA_OK;
+}
+
+float* act(giga_ctx* ctx, const char* name) {
+  for (int i = 0; i < kNumActs; ++i)
+    if (!strcmp(kActs[i].name, name)) return ctx->d_act[i];
+  return nullptr;
+}
+
+template <class K>
+void launch_conv(giga_ctx* ctx, int n_img, const float* s0, const float* s1, int layer, float* out, float* pooled,
+                 cudaStream_t st) {
+  dim3 grid(K::NB * K::NCT, n_img);
+  conv3x3_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(s0, s1, ctx->d_enc + ctx->el.conv[layer],
+                                                              ctx->d_enc + ctx->el.bias[layer], out, pooled);
+  ctx->launches++;
+}
+
+template <class K>
+void launch_convT(giga_ctx* ctx, int n_img, const float* src, int up, float* out, cudaStream_t st) {
+  dim3 grid(K::NB * K::NCT, n_img);
+  convT2x2_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(src, ctx->d_enc + ctx->el.up_w[up],
+                                                               ctx->d_enc + ctx->el.up_b[up], out);
+  ctx->launches++;
+}
+
+bool get(const giga_ctx* ctx, const std::string& name, long numel, const float** out) {
+  auto it = ctx->raw.find(name);
+  if (it == ctx->raw.end() || (long)it->second.size() != numel) return false;
+  *out = it->second.data();
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int giga_version(void) { return 100; }
+
+const char* giga_last_error(void) { return g_err.c_str(); }
+
+int giga_ctx_create(giga_ctx** out, int device) {
+  if (!out) return fail(GIGA_EINVAL, "giga_ctx_create: out is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(GIGA_ENODEV, std::string("no CUDA device (") + cudaGetErrorString(e) + "); giga_b200 has no CPU path");
+  if (device < 0 || device >= n) return fail(GIGA_EINVAL, "giga_ctx_create: bad device ordinal");
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(GIGA_ENODEV, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                 std::to_string(prop.minor) + "; this library is built for sm_100a only");
+  giga_ctx* ctx = new giga_ctx();
+  ctx->device = device;
+  ctx->el = make_enc_layout();
+  *out = ctx;
+  return GIGA_OK;
+}
+
+void giga_ctx_destroy(giga_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_pre, ctx->d_xzpart, ctx->h_tsdf, ctx->h_planes, ctx->h_p,
+                   ctx->h_pt,  ctx->h_qual,  ctx->h_rot, ctx->h_width,  ctx->h_occ};
+  for (float* p : ptrs)
+    if (p) cudaFree(p);
+  for (float* p : ctx->d_act)
+    if (p) cudaFree(p);
+  delete ctx;
+}
+
+int giga_ctx_set_param(giga_ctx* ctx, const char* name, const float* data, long numel, int on_device) {
+  if (!ctx || !name || !data || numel <= 0) return fail(GIGA_EINVAL, "giga_ctx_set_param: bad argument");
+  if (int r = set_device(ctx)) return r;
+  std::vector<float>& v = ctx->raw[name];
+  v.resize(numel);
+  if (on_device) {
+    CU_TRY(cudaMemcpy(v.data(), data, sizeof(float) * numel, cudaMemcpyDeviceToHost));
+  } else {
+    memcpy(v.data(), data, sizeof(float) * numel);
+  }
+  ctx->committed = false;
+  return GIGA_OK;
+}
+
+int giga_ctx_commit_params(giga_ctx* ctx) {
+  if (!ctx) return fail(GIGA_EINVAL, "giga_ctx_commit_params: ctx is null");
+  if (int r = set_device(ctx)) return r;
+  const float* w;
+  const float* b;
+  // ---- encoder ----
+  ctx->has_encoder = false;
+  if (ctx->raw.count("encoder.conv_in.weight")) {
+    if (!get(ctx, "encoder.conv_in.weight", 32 * 27, &w) || !get(ctx, "encoder.conv_in.bias", 32, &b))
+      return fail(GIGA_ESTATE, "encoder.conv_in.{weight,bias}: missing or wrong size");
+    for (int c = 0; c < 32; ++c) {
+      for (int t = 0; t < 27; ++t) ctx->conv_in.w[t][c] = w[c * 27 + t];  // [co][0][dx][dy][dz] -> [tap][co]
+      ctx->conv_in.b[c] = b[c];
+    }
+    std::vector<float> blob(ctx->el.total);
+    for (int i = 0; i < 10; ++i) {
+      const int ci = kConvCin[i], co = kConvCout[i];
+      std::string base = std::string("encoder.unet.") + kConvName[i];
+      if (!get(ctx, base + ".weight", (long)co * ci * 9, &w) || !get(ctx, base + ".bias", co, &b))
+        return fail(GIGA_ESTATE, base + ".{weight,bias}: missing or wrong size");
+      float* dst = blob.data() + ctx->el.conv[i];  // [ci][tap][co]  <-  [co][ci][3][3]
+      for (int o = 0; o < co; ++o)
+        for (int c = 0; c < ci; ++c)
+          for (int t = 0; t < 9; ++t) dst[((long)c * 9 + t) * co + o] = w[((long)o * ci + c) * 9 + t];
+      memcpy(blob.data() + ctx->el.bias[i], b, sizeof(float) * co);
+    }
+    for (int i = 0; i < 2; ++i) {
+      std::string base = "encoder.unet.up_convs." + std::to_string(i) + ".upconv";
+      if (!get(ctx, base + ".weight", (long)kUpCin[i] * kUpCout[i] * 4, &w) || !get(ctx, base + ".bias", kUpCout[i], &b))
+        return fail(GIGA_ESTATE, base + ".{weight,bias}: missing or wrong size");
+      memcpy(blob.data() + ctx->el.up_w[i], w, sizeof(float) * kUpCin[i] * kUpCout[i] * 4);  // [ci][co][2][2] as is
+      memcpy(blob.data() + ctx->el.up_b[i], b, sizeof(float) * kUpCout[i]);
+    }
+    if (!get(ctx, "encoder.unet.conv_final.weight", 32 * 32, &w) || !get(ctx, "encoder.unet.conv_final.bias", 32, &b))
+      return fail(GIGA_ESTATE, "encoder.unet.conv_final.{weight,bias}: missing or wrong size");
+    for (int o = 0; o < 32; ++o)
+      for (int c = 0; c < 32; ++c) blob[ctx->el.fin_w + c * 32 + o] = w[o * 32 + c];  // [ci][co]
+    memcpy(blob.data() + ctx->el.fin_b, b, sizeof(float) * 32);
+    if (!ctx->d_enc) CU_TRY(cudaMalloc(&ctx->d_enc, sizeof(float) * ctx->el.total));
+    CU_TRY(cudaMemcpy(ctx->d_enc, blob.data(), sizeof(float) * ctx->el.total, cudaMemcpyHostToDevice));
+    ctx->has_encoder = true;
+  }
+  // ---- decoder heads ----
+  std::vector<float> hb((size_t)4 * DW_HEAD, 0.f);
+  unsigned heads = 0;
+  for (int h = 0; h < 4; ++h) {
+    const std::string pre = std::string("decoder_") + kHeadName[h] + ".";
+    if (!ctx->raw.count(pre + "fc_p.weight")) continue;
+    const int od = (h == 1) ? 4 : 1;
+    float* H = hb.data() + (size_t)h * DW_HEAD;
+    auto need = [&](const std::string& n, long numel, const float** p) { return get(ctx, pre + n, numel, p); };
+    if (!need("fc_p.weight", 96, &w) || !need("fc_p.bias", 32, &b)) return fail(GIGA_ESTATE, pre + "fc_p: missing or wrong size");
+    for (int j = 0; j < 32; ++j) {
+      for (int k = 0; k < 3; ++k) H[DW_FCP + k * 32 + j] = w[j * 3 + k];
+      H[DW_FCP + 96 + j] = b[j];
+    }
+    for (int i = 0; i < 5; ++i) {
+      float* Bk = H + DW_BLOCK0 + i * DW_BLK;
+      const std::string si = std::to_string(i);
+      if (!need("fc_c." + si + ".weight", 32 * 96, &w) || !need("fc_c." + si + ".bias", 32, &b))
+        return fail(GIGA_ESTATE, pre + "fc_c." + si + ": missing or wrong size");
+      for (int j = 0; j < 32; ++j) {
+        for (int k = 0; k < 96; ++k) Bk[DW_BLK_FCC + k * 32 + j] = w[j * 96 + k];
+        Bk[DW_BLK_BC + j] = b[j];
+      }
+      const int woff[2] = {DW_BLK_W0, DW_BLK_W1}, boff[2] = {DW_BLK_B0, DW_BLK_B1};
+      for (int f = 0; f < 2; ++f) {
+        const std::string fn = "blocks." + si + ".fc_" + std::to_string(f);
+        if (!need(fn + ".weight", 32 * 32, &w) || !need(fn + ".bias", 32, &b))
+          return fail(GIGA_ESTATE, pre + fn + ": missing or wrong size");
+        for (int j = 0; j < 32; ++j) {
+          for (int k = 0; k < 32; ++k) Bk[woff[f] + k * 32 + j] = w[j * 32 + k];
+          Bk[boff[f] + j] = b[j];
+        }
+      }
+    }
+    if (!need("fc_out.weight", od * 32, &w) || !need("fc_out.bias", od, &b))
+      return fail(GIGA_ESTATE, pre + "fc_out: missing or wrong size");
+    for (int m = 0; m < od; ++m) {
+      for (int k = 0; k < 32; ++k) H[DW_OUT + k * 4 + m] = w[m * 32 + k];
+      H[DW_OUT + 128 + m] = b[m];
+    }
+    heads |= 1u << h;
+  }
+  if (!ctx->d_heads) CU_TRY(cudaMalloc(&ctx->d_heads, sizeof(float) * 4 * DW_HEAD));
+  CU_TRY(cudaMemcpy(ctx->d_heads, hb.data(), sizeof(float) * 4 * DW_HEAD, cudaMemcpyHostToDevice));
+  ctx->heads = heads;
+  if (!ctx->has_encoder && !heads) return fail(GIGA_ESTATE, "giga_ctx_commit_params: no parameters were set");
+  if (int r = ensure_attrs(ctx)) return r;
+  ctx->committed = true;
+  return GIGA_OK;
+}
+
+unsigned giga_ctx_heads(const giga_ctx* ctx) { return ctx ? ctx->heads : 0; }
+
+int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* stream) {
+  if (!ctx || !tsdf || !planes || B <= 0) return fail(GIGA_EINVAL, "giga_encode: bad argument");
+  if (!ctx->committed || !ctx->has_encoder) return fail(GIGA_ESTATE, "giga_encode: encoder parameters not committed");
+  if (int r = set_device(ctx)) return r;
+  if (int r = ensure_workspace(ctx, B)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_img = 3 * B;
+  conv_in_planes_kernel<<<dim3(CI_NT, B), CI_THREADS, CI_SMEM_BYTES, st>>>(tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+  xz_finish_kernel<<<dim3(C, B), 256, 0, st>>>(ctx->d_xzpart, ctx->d_pre, B);
+  ctx->launches += 2;
+  float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"),
+        *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),
+        *u0 = act(ctx, "u0"), *u0c1 = act(ctx, "u0c1"), *u0c2 = act(ctx, "u0c2"), *u1 = act(ctx, "u1"),
+        *u1c1 = act(ctx, "u1c1"), *u1c2 = act(ctx, "u1c2");
+  launch_conv<K_d0c1>(ctx, n_img, ctx->d_pre, nullptr, 0, d0c1, nullptr, st);
+  launch_conv<K_d0c2>(ctx, n_img, d0c1, nullptr, 1, d0c2, p0, st);
+  launch_conv<K_d1c1>(ctx, n_img, p0, nullptr, 2, d1c1, nullptr, st);
+  launch_conv<K_d1c2>(ctx, n_img, d1c1, nullptr, 3, d1c2, p1, st);
+  launch_conv<K_d2c1>(ctx, n_img, p1, nullptr, 4, d2c1, nullptr, st);
+  launch_conv<K_d2c2>(ctx, n_img, d2c1, nullptr, 5, d2c2, nullptr, st);
+  launch_convT<K_u0up>(ctx, n_img, d2c2, 0, u0, st);
+  launch_conv<K_u0c1>(ctx, n_img, u0, d1c2, 6, u0c1, nullptr, st);   // cat(from_up, from_down), unet.py:109
+  launch_conv<K_u0c2>(ctx, n_img, u0c1, nullptr, 7, u0c2, nullptr, st);
+  launch_convT<K_u1up>(ctx, n_img, u0c2, 1, u1, st);
+  launch_conv<K_u1c1>(ctx, n_img, u1, d0c2, 8, u1c1, nullptr, st);
+  launch_conv<K_u1c2>(ctx, n_img, u1c1, nullptr, 9, u1c2, nullptr, st);
+  conv1x1_nhwc_kernel<<<dim3(G2 / F_PIX, n_img), 256, 0, st>>>(u1c2, ctx->d_enc + ctx->el.fin_w, ctx->d_enc + ctx->el.fin_b, planes);
+  ctx->launches++;
+  ctx->last_B = B;
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+int giga_decode(giga_ctx* ctx, const float* planes, int B, const float* points, int N, unsigned heads, float* qual,
+                float* rot, float* width, float* occ, void* stream) {
+  if (!ctx || !planes || !points || B <= 0 || N <= 0 || !heads) return fail(GIGA_EINVAL, "giga_decode: bad argument");
+  if (!ctx->committed) return fail(GIGA_ESTATE, "giga_decode: parameters not committed");
+  if (heads & ~ctx->heads) return fail(GIGA_ESTATE, "giga_decode: a requested head has no committed parameters");
+  if (((heads & GIGA_HEAD_QUAL) && !qual) || ((heads & GIGA_HEAD_ROT) && !rot) || ((heads & GIGA_HEAD_WIDTH) && !width) ||
+      ((heads & GIGA_HEAD_TSDF) && !occ))
+    return fail(GIGA_EINVAL, "giga_decode: output pointer of a requested head is null");
+  if (int r = set_device(ctx)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N,
+                                                                                       heads, qual, rot, width, occ);
+  ctx->launches++;
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+int giga_sample_feature(giga_ctx* ctx, const float* planes, int B, const float* points, int N, int mode, float* out,
+                        void* stream) {
+  if (!ctx || !planes || !points || !out || B <= 0 || N <= 0 || (mode != 0 && mode != 1))
+    return fail(GIGA_EINVAL, "giga_sample_feature: bad argument");
+  if (int r = set_device(ctx)) return r;
+  if (int r = ensure_attrs(ctx)) return r;
+  sample_feature_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, SF_SMEM_BYTES, (cudaStream_t)stream>>>(planes, points, B, N, mode, out);
+  ctx->launches++;
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+int giga_scene_argmax(giga_ctx* ctx, const float* qual, int B, int N, float* best_val, int* best_idx, void* stream) {
+  if (!ctx || !qual || !best_val || !best_idx || B <= 0 || N <= 0) return fail(GIGA_EINVAL, "giga_scene_argmax: bad argument");
+  if (int r = set_device(ctx)) return r;
+  scene_argmax_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(qual, N, best_val, best_idx);
+  ctx->launches++;
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+int giga_forward_host(giga_ctx* ctx, const float* tsdf, int B, const float* p, int Ng, const float* p_tsdf, int No,
+                      float* qual, float* rot, float* width, float* occ, void* stream) {
+  if (!ctx || !tsdf || B <= 0) return fail(GIGA_EINVAL, "giga_forward_host: bad argument");
+  const bool grasp = p && Ng > 0, geo = p_tsdf && No > 0;
+  if (!grasp && !geo) return fail(GIGA_EINVAL, "giga_forward_host: no query points");
+  if (grasp && (!qual || !rot || !width)) return fail(GIGA_EINVAL, "giga_forward_host: grasp outputs are null");
+  if (geo && !occ) return fail(GIGA_EINVAL, "giga_forward_host: occ output is null");
+  if (int r = set_device(ctx)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B > ctx->hcap_B || Ng > ctx->hcap_Ng || No > ctx->hcap_No) {
+    CU_TRY(cudaDeviceSynchronize());
+    float** ptrs[] = {&ctx->h_tsdf, &ctx->h_planes, &ctx->h_p, &ctx->h_pt, &ctx->h_qual, &ctx->h_rot, &ctx->h_width, &ctx->h_occ};
+    for (float** q : ptrs) { if (*q) cudaFree(*q); *q = nullptr; }
+    const int cB = B > ctx->hcap_B ? B : ctx->hcap_B, cg = Ng > ctx->hcap_Ng ? Ng : ctx->hcap_Ng, co = No > ctx->hcap_No ? No : ctx->hcap_No;
+    const size_t ng = (size_t)cB * (cg > 0 ? cg : 1), no = (size_t)cB * (co > 0 ? co : 1);
+    CU_TRY(cudaMalloc(&ctx->h_tsdf, sizeof(float) * (size_t)cB * G3));
+    CU_TRY(cudaMalloc(&ctx->h_planes, sizeof(float) * 3 * (size_t)cB * G2 * C));
+    CU_TRY(cudaMalloc(&ctx->h_p, sizeof(float) * ng * 3));
+    CU_TRY(cudaMalloc(&ctx->h_pt, sizeof(float) * no * 3));
+    CU_TRY(cudaMalloc(&ctx->h_qual, sizeof(float) * ng));
+    CU_TRY(cudaMalloc(&ctx->h_rot, sizeof(float) * ng * 4));
+    CU_TRY(cudaMalloc(&ctx->h_width, sizeof(float) * ng));
+    CU_TRY(cudaMalloc(&ctx->h_occ, sizeof(float) * no));
+    ctx->hcap_B = cB; ctx->hcap_Ng = cg; ctx->hcap_No = co;
+  }
+  CU_TRY(cudaMemcpyAsync(ctx->h_tsdf, tsdf, sizeof(float) * (size_t)B * G3, cudaMemcpyHostToDevice, st));
+  if (grasp) CU_TRY(cudaMemcpyAsync(ctx->h_p, p, sizeof(float) * (size_t)B * Ng * 3, cudaMemcpyHostToDevice, st));
+  if (geo) CU_TRY(cudaMemcpyAsync(ctx->h_pt, p_tsdf, sizeof(float) * (size_t)B * No * 3, cudaMemcpyHostToDevice, st));
+  if (int r = giga_encode(ctx, ctx->h_tsdf, B, ctx->h_planes, stream)) return r;
+  if (grasp) {
+    const unsigned hm = ctx->heads & (GIGA_HEAD_QUAL | GIGA_HEAD_ROT | GIGA_HEAD_WIDTH);
+    if (int r = giga_decode(ctx, ctx->h_planes, B, ctx->h_p, Ng, hm, ctx->h_qual, ctx->h_rot, ctx->h_width, nullptr, stream)) return r;
+    CU_TRY(cudaMemcpyAsync(qual, ctx->h_qual, sizeof(float) * (size_t)B * Ng, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(rot, ctx->h_rot, sizeof(float) * (size_t)B * Ng * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(width, ctx->h_width, sizeof(float) * (size_t)B * Ng, cudaMemcpyDeviceToHost, st));
+  }
+  if (geo) {
+    if (int r = giga_decode(ctx, ctx->h_planes, B, ctx->h_pt, No, GIGA_HEAD_TSDF, nullptr, nullptr, nullptr, ctx->h_occ, stream)) return r;
+    CU_TRY(cudaMemcpyAsync(occ, ctx->h_occ, sizeof(float) * (size_t)B * No, cudaMemcpyDeviceToHost, st));
+  }
+  CU_TRY(cudaStreamSynchronize(st));
+  return GIGA_OK;
+}
+
+long giga_ctx_launch_count(const giga_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity, void* stream) {
+  if (!ctx || !name || !dst) return fail(GIGA_EINVAL, "giga_debug_copy: bad argument");
+  if (ctx->last_B <= 0) return fail(GIGA_ESTATE, "giga_debug_copy: no giga_encode call yet");
+  if (int r = set_device(ctx)) return r;
+  const float* src = nullptr;
+  long numel = 0;
+  if (!strcmp(name, "pre")) {
+    src = ctx->d_pre;
+    numel = 3L * ctx->last_B * C * G2;
+  } else {
+    for (int i = 0; i < kNumActs; ++i)
+      if (!strcmp(kActs[i].name, name)) {
+        src = ctx->d_act[i];
+        numel = 3L * ctx->last_B * kActs[i].ch * kActs[i].hw * kActs[i].hw;
+      }
+  }
+  if (!src) return fail(GIGA_EINVAL, std::string("giga_debug_copy: unknown buffer '") + name + "'");
+  if (numel > capacity) return fail(GIGA_EINVAL, "giga_debug_copy: destination too small");
+  CU_TRY(cudaMemcpyAsync(dst, src, sizeof(float) * numel, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return numel;
+}
+
+}  // extern "C"

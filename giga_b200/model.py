@@ -1,0 +1,372 @@
+"""Host-side mirror of the reference model interface for the dense-inference hot path.
+
+`ConvolutionalOccupancyNetwork` here has the reference class's public surface
+(/root/reference/src/vgn/ConvONets/conv_onet/models/__init__.py:15-164): the same
+parameter names/shapes (so reference checkpoints load and ours load into the
+reference), the same methods (`forward/encode_inputs/decode/decode_occ/infer_geo/
+query_feature/decode_feature/to`) and attributes (`encoder`, `decoder_qual/rot/width/
+tsdf`, `_device`, `detach_tsdf`).  The sub-modules are parameter containers only: all
+arithmetic happens in libgiga_b200.so (hand-written sm_100a CUDA) through the C ABI in
+include/giga_b200.h.  PyTorch provides device memory, streams and the nn.Module
+plumbing -- nothing on the compute path.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+from torch import distributions as dist
+
+from . import _lib
+from ._lib import HEAD_GRASP, HEAD_QUAL, HEAD_ROT, HEAD_TSDF, HEAD_WIDTH, check, lib
+
+PLANES = ("xz", "xy", "yz")
+GRID = 40
+CDIM = 32
+
+
+# --------------------------------------------------------------------------------------
+# parameter containers (names/shapes/initialisation of the reference modules)
+# --------------------------------------------------------------------------------------
+class _Affine(nn.Module):
+    """weight + bias holder with torch's default (kaiming-uniform a=sqrt(5)) initialisation
+    of nn.Linear / nn.ConvNd / nn.ConvTranspose2d."""
+
+    def __init__(self, *shape, fan_in: int, bias_len: Optional[int] = None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(*shape))
+        self.bias = nn.Parameter(torch.empty(shape[0] if bias_len is None else bias_len))
+        bound = 1.0 / math.sqrt(fan_in)
+        nn.init.uniform_(self.weight, -bound, bound)  # kaiming_uniform_(a=sqrt(5)) == U(+-1/sqrt(fan_in))
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+def _linear(n_in, n_out):
+    return _Affine(n_out, n_in, fan_in=n_in)
+
+
+def _conv3x3(c_in, c_out):
+    m = _Affine(c_out, c_in, 3, 3, fan_in=c_in * 9)
+    nn.init.xavier_normal_(m.weight)  # encoder/unet.py:213-217 (UNet.weight_init, Conv2d only)
+    nn.init.constant_(m.bias, 0)
+    return m
+
+
+class DownConv(nn.Module):  # encoder/unet.py:48-72
+    def __init__(self, c_in, c_out):
+        super().__init__()
+        self.conv1 = _conv3x3(c_in, c_out)
+        self.conv2 = _conv3x3(c_out, c_out)
+
+
+class UpConv(nn.Module):  # encoder/unet.py:75-114 (transpose up-conv, concat merge)
+    def __init__(self, c_in, c_out):
+        super().__init__()
+        # ConvTranspose2d weight is [in, out, 2, 2]; torch computes fan_in from size(1)
+        self.upconv = _Affine(c_in, c_out, 2, 2, fan_in=c_out * 4, bias_len=c_out)
+        self.conv1 = _conv3x3(2 * c_out, c_out)
+        self.conv2 = _conv3x3(c_out, c_out)
+
+
+class UNet(nn.Module):  # encoder/unet.py:117-239: UNet(32, in_channels=32, depth=3, start_filts=32, concat)
+    def __init__(self):
+        super().__init__()
+        self.down_convs = nn.ModuleList([DownConv(32, 32), DownConv(32, 64), DownConv(64, 128)])
+        self.up_convs = nn.ModuleList([UpConv(128, 64), UpConv(64, 32)])
+        self.conv_final = _Affine(32, 32, 1, 1, fan_in=32)
+        nn.init.xavier_normal_(self.conv_final.weight)
+        nn.init.constant_(self.conv_final.bias, 0)
+
+
+class LocalVoxelEncoder(nn.Module):  # encoder/voxels.py:10-121
+    def __init__(self):
+        super().__init__()
+        self.conv_in = _Affine(32, 1, 3, 3, 3, fan_in=27)
+        self.unet = UNet()
+        self.c_dim = CDIM
+        self.reso_plane = GRID
+        self.plane_type = list(PLANES)
+        self.padding = 0
+
+
+class ResnetBlockFC(nn.Module):  # layers.py:6-47
+    def __init__(self, size):
+        super().__init__()
+        self.fc_0 = _linear(size, size)
+        self.fc_1 = _linear(size, size)
+        nn.init.zeros_(self.fc_1.weight)
+
+
+class LocalDecoder(nn.Module):  # conv_onet/models/decoder.py:61-206 (concat_feat=True -> c_dim 96)
+    def __init__(self, out_dim: int):
+        super().__init__()
+        self.c_dim = 3 * CDIM
+        self.n_blocks = 5
+        self.hidden_size = 32
+        self.out_dim = out_dim
+        self.fc_c = nn.ModuleList([_linear(96, 32) for _ in range(5)])
+        self.fc_p = _linear(3, 32)
+        self.blocks = nn.ModuleList([ResnetBlockFC(32) for _ in range(5)])
+        self.fc_out = _linear(32, out_dim)
+
+
+class PlaneFeatures(dict):
+    """The dict `encode_inputs` returns ({'xz','xy','yz'} -> (B,32,40,40) views) plus the packed
+    channels-last buffer [3][B][40][40][32] the views alias (what the decoder kernels read)."""
+
+    packed: Optional[torch.Tensor] = None
+
+
+# --------------------------------------------------------------------------------------
+# engine: one giga_ctx per (module, device)
+# --------------------------------------------------------------------------------------
+class _Engine:
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise _lib.GigaError("giga_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        self.device = device
+        h = C.c_void_p()
+        check(lib.giga_ctx_create(C.byref(h), device.index if device.index is not None else torch.cuda.current_device()),
+              "giga_ctx_create")
+        self.h = h
+        self.param_key = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib.giga_ctx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def sync_params(self, module: nn.Module):
+        params = list(module.state_dict(keep_vars=True).items())
+        key = tuple((k, v.data_ptr(), v._version) for k, v in params)
+        if key == self.param_key:
+            return
+        for k, v in params:
+            t = v.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            check(lib.giga_ctx_set_param(self.h, k.encode(), C.c_void_p(t.data_ptr()), t.numel(), int(t.is_cuda)),
+                  f"giga_ctx_set_param({k})")
+        check(lib.giga_ctx_commit_params(self.h), "giga_ctx_commit_params")
+        self.param_key = key
+
+    @property
+    def launches(self) -> int:
+        return int(lib.giga_ctx_launch_count(self.h))
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _prep(t: torch.Tensor, device) -> torch.Tensor:
+    if t.device != device:
+        raise _lib.GigaError(f"input on {t.device}, model on {device}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _GigaBase(nn.Module):
+    """Shared host logic of the two reference wrappers."""
+
+    _device = None
+
+    # -- engine plumbing ---------------------------------------------------------------
+    def _engine(self) -> _Engine:
+        dev = next(self.parameters()).device
+        eng = self.__dict__.get("_eng")
+        if eng is None or eng.device != dev:
+            eng = _Engine(dev)
+            self.__dict__["_eng"] = eng
+        eng.sync_params(self)
+        return eng
+
+    def to(self, device):
+        """models/__init__.py:126-134"""
+        model = super().to(device)
+        model._device = device
+        return model
+
+    @property
+    def gpu_launches(self) -> int:
+        eng = self.__dict__.get("_eng")
+        return eng.launches if eng else 0
+
+    # -- encoder -----------------------------------------------------------------------
+    def encode_inputs(self, inputs: torch.Tensor) -> PlaneFeatures:
+        """models/__init__.py:74-87 -> LocalVoxelEncoder.forward (encoder/voxels.py:89-121)."""
+        eng = self._engine()
+        x = _prep(inputs, eng.device)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (GRID, GRID, GRID):
+            raise _lib.GigaError(f"inputs must be (B,{GRID},{GRID},{GRID}), got {tuple(inputs.shape)}")
+        B = x.shape[0]
+        packed = torch.empty((3, B, GRID, GRID, CDIM), device=eng.device, dtype=torch.float32)
+        check(lib.giga_encode(eng.h, C.c_void_p(x.data_ptr()), B, C.c_void_p(packed.data_ptr()), _stream(eng.device)),
+              "giga_encode")
+        c = PlaneFeatures((k, packed[i].permute(0, 3, 1, 2)) for i, k in enumerate(PLANES))
+        c.packed = packed
+        return c
+
+    @staticmethod
+    def _packed(c: Dict[str, torch.Tensor]) -> torch.Tensor:
+        packed = getattr(c, "packed", None)
+        if packed is not None and all(c[k].data_ptr() == packed[i].data_ptr() for i, k in enumerate(PLANES)):
+            return packed
+        # foreign plane tensors (e.g. produced elsewhere): re-pack to channels-last (layout only)
+        return torch.stack([c[k].float().permute(0, 2, 3, 1) for k in PLANES]).contiguous()
+
+    # -- decoder -----------------------------------------------------------------------
+    def _decode_heads(self, p: torch.Tensor, c, heads: int):
+        eng = self._engine()
+        planes = self._packed(c)
+        pts = _prep(p, eng.device)
+        if pts.dim() != 3 or pts.shape[2] != 3 or pts.shape[0] != planes.shape[1]:
+            raise _lib.GigaError(f"points must be (B,N,3) with B={planes.shape[1]}, got {tuple(p.shape)}")
+        B, N = pts.shape[0], pts.shape[1]
+        mk = lambda *s: torch.empty(s, device=eng.device, dtype=torch.float32)
+        qual = mk(B, N) if heads & HEAD_QUAL else None
+        rot = mk(B, N, 4) if heads & HEAD_ROT else None
+        width = mk(B, N) if heads & HEAD_WIDTH else None
+        occ = mk(B, N) if heads & HEAD_TSDF else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        check(lib.giga_decode(eng.h, ptr(planes), B, ptr(pts), N, heads, ptr(qual), ptr(rot), ptr(width), ptr(occ),
+                              _stream(eng.device)), "giga_decode")
+        return qual, rot, width, occ
+
+    def decode_occ(self, p, c, **kwargs):
+        """models/__init__.py:100-109"""
+        logits = self._decode_heads(p, c, HEAD_TSDF)[3]
+        return dist.Bernoulli(logits=logits)
+
+    def infer_geo(self, inputs, p_tsdf, **kwargs):
+        """models/__init__.py:69-72"""
+        c = self.encode_inputs(inputs)
+        return self._decode_heads(p_tsdf, c, HEAD_TSDF)[3]
+
+    def sample_feature(self, p, c, mode: str = "concat") -> torch.Tensor:
+        eng = self._engine()
+        planes = self._packed(c)
+        pts = _prep(p, eng.device)
+        B, N = pts.shape[0], pts.shape[1]
+        out = torch.empty((B, N, 96 if mode == "concat" else 32), device=eng.device, dtype=torch.float32)
+        check(lib.giga_sample_feature(eng.h, C.c_void_p(planes.data_ptr()), B, C.c_void_p(pts.data_ptr()), N,
+                                      0 if mode == "concat" else 1, C.c_void_p(out.data_ptr()), _stream(eng.device)),
+              "giga_sample_feature")
+        return out
+
+    def scene_argmax(self, qual: torch.Tensor, out_val: Optional[torch.Tensor] = None, out_idx: Optional[torch.Tensor] = None):
+        """Per-scene (max quality, first arg-max) -- the final grasp-score reduction; `out_*` may be
+        slices of an all-gather buffer."""
+        eng = self._engine()
+        q = _prep(qual, eng.device)
+        B, N = q.shape
+        if out_val is None:
+            out_val = torch.empty(B, device=eng.device, dtype=torch.float32)
+        if out_idx is None:
+            out_idx = torch.empty(B, device=eng.device, dtype=torch.int32)
+        assert out_val.is_contiguous() and out_idx.is_contiguous() and out_idx.dtype == torch.int32
+        check(lib.giga_scene_argmax(eng.h, C.c_void_p(q.data_ptr()), B, N, C.c_void_p(out_val.data_ptr()),
+                                    C.c_void_p(out_idx.data_ptr()), _stream(eng.device)), "giga_scene_argmax")
+        return out_val, out_idx
+
+    def debug_activation(self, name: str, B: int) -> torch.Tensor:
+        """Copy an intermediate activation of the last encode (tests only)."""
+        eng = self._engine()
+        shapes = {"pre": (32, 40), "d0c1": (32, 40), "d0c2": (32, 40), "p0": (32, 20), "d1c1": (64, 20), "d1c2": (64, 20),
+                  "p1": (64, 10), "d2c1": (128, 10), "d2c2": (128, 10), "u0": (64, 20), "u0c1": (64, 20), "u0c2": (64, 20),
+                  "u1": (32, 40), "u1c1": (32, 40), "u1c2": (32, 40)}
+        ch, hw = shapes[name]
+        out = torch.empty((3, B, ch, hw, hw), device=eng.device, dtype=torch.float32)
+        n = lib.giga_debug_copy(eng.h, name.encode(), C.c_void_p(out.data_ptr()), out.numel(), _stream(eng.device))
+        check(int(n), "giga_debug_copy")
+        assert n == out.numel()
+        return out
+
+    def forward_host(self, tsdf: torch.Tensor, p: Optional[torch.Tensor], p_tsdf: Optional[torch.Tensor] = None, out=None):
+        """End-to-end call with HOST tensors (pinned for full PCIe bandwidth): H2D, encode, decode,
+        D2H inside one C-ABI call (giga_forward_host).  Mirrors `predict()`
+        (detection_implicit.py:99-113).  Returns host tensors (qual, rot, width[, occ])."""
+        eng = self._engine()
+        for t in (tsdf, p, p_tsdf):
+            if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise _lib.GigaError("forward_host takes contiguous fp32 host tensors")
+        B = tsdf.shape[0]
+        Ng = p.shape[1] if p is not None else 0
+        No = p_tsdf.shape[1] if p_tsdf is not None else 0
+        if out is None:
+            pin = dict(dtype=torch.float32, pin_memory=True)
+            out = (torch.empty((B, Ng), **pin), torch.empty((B, Ng, 4), **pin), torch.empty((B, Ng), **pin),
+                   torch.empty((B, No), **pin))
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
+        check(lib.giga_forward_host(eng.h, ptr(tsdf), B, ptr(p), Ng, ptr(p_tsdf), No, ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                                    ptr(out[3]), _stream(eng.device)), "giga_forward_host")
+        return out if No else out[:3]
+
+
+class ConvolutionalOccupancyNetwork(_GigaBase):
+    """Drop-in for conv_onet/models/__init__.py:15-164 (giga, giga_aff, giga_detach)."""
+
+    def __init__(self, with_tsdf: bool = True, device=None, detach_tsdf: bool = False):
+        super().__init__()
+        self.decoder_qual = LocalDecoder(1)
+        self.decoder_rot = LocalDecoder(4)
+        self.decoder_width = LocalDecoder(1)
+        if with_tsdf:
+            self.decoder_tsdf = LocalDecoder(1)
+        self.encoder = LocalVoxelEncoder()
+        self._device = device
+        self.detach_tsdf = detach_tsdf
+        if device is not None:
+            self.to(device)
+
+    def forward(self, inputs, p, p_tsdf=None, sample=True, **kwargs):
+        """models/__init__.py:42-67"""
+        c = self.encode_inputs(inputs)
+        qual, rot, width = self.decode(p, c)
+        if p_tsdf is not None:
+            tsdf = self._decode_heads(p_tsdf, c, HEAD_TSDF)[3]
+            return qual, rot, width, tsdf
+        return qual, rot, width
+
+    def decode(self, p, c, **kwargs):
+        """models/__init__.py:111-124 (sigmoid / normalise fused into the kernel epilogue)."""
+        qual, rot, width, _ = self._decode_heads(p, c, HEAD_GRASP)
+        return qual, rot, width
+
+    def query_feature(self, p, c):
+        """models/__init__.py:89-90 -> LocalDecoder.query_feature (decoder.py:178-191): summed 32-d feature."""
+        return self.sample_feature(p, c, mode="sum")
+
+    def decode_feature(self, p, feature):
+        """models/__init__.py:92-98.  In the reference this feeds the 32-d *summed* feature into fc_c
+        layers that expect 96 inputs (concat_feat=True), i.e. it raises for every shipped GIGA config
+        and is commented out of forward (:57-58); mirrored as an explicit error."""
+        raise RuntimeError("decode_feature: size mismatch, fc_c expects 96-d features (concat_feat=True); "
+                           "same failure as the reference for GIGA configs")
+
+    def grad_refine(self, x, pos, bound_value=0.0125, lr=1e-6, num_step=1):
+        """models/__init__.py:136-164 needs d(qual)/d(pos); not called by any shipped script."""
+        raise NotImplementedError("grad_refine needs the position gradient of the fused decoder (not built yet)")
+
+
+class ConvolutionalOccupancyNetworkGeometry(_GigaBase):
+    """Drop-in for conv_onet/models/__init__.py:166-226 (giga_geo: encoder + decoder_tsdf only)."""
+
+    def __init__(self, device=None):
+        super().__init__()
+        self.decoder_tsdf = LocalDecoder(1)
+        self.encoder = LocalVoxelEncoder()
+        self._device = device
+        if device is not None:
+            self.to(device)
+
+    def forward(self, inputs, p, p_tsdf, sample=True, **kwargs):
+        """models/__init__.py:179-195"""
+        return self.infer_geo(inputs, p_tsdf)

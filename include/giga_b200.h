@@ -1,0 +1,117 @@
+/*
+ * giga_b200.h -- C ABI of the B200-native (sm_100a) GIGA dense-inference hot path.
+ *
+ * The reference (UT-Austin-RPL/GIGA) has no native FFI on this path: its boundary is
+ * the Python nn.Module `ConvolutionalOccupancyNetwork` plus the library ops underneath
+ * it.  Every entry point below therefore names the reference *Python* interface (or
+ * library op) it replaces, file:line relative to /root/reference/src/vgn.  The Python
+ * host layer in giga_b200/ (ctypes) mirrors the reference classes
+ * on top of exactly these symbols.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns 0 on success, a negative GIGA_E* code on failure, and
+ *     leaves a message retrievable with giga_last_error() (thread local);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all
+ *     device work of a call is enqueued on it, nothing synchronises unless stated;
+ *   - device tensors are dense fp32, layouts stated per argument.  There is NO CPU
+ *     fallback: without a CUDA device every compute entry point fails with GIGA_ENODEV.
+ *
+ * Tensor layouts in HBM
+ *   tsdf    [B][40][40][40]            x[b][ix][iy][iz]          (voxels.py:89)
+ *   planes  [3][B][40][40][32]         plane k in (xz, xy, yz), channels-last:
+ *                                      planes[k][b][row][col][c]; row/col per
+ *                                      common.py:314 (xz: row=z col=x, xy: row=y col=x,
+ *                                      yz: row=z col=y).  encode_inputs() exposes
+ *                                      plane k as a (B,32,40,40) permuted view.
+ *   points  [B][N][3]                  p[b][n][xyz] in the unit cube (clamped outside)
+ *   qual    [B][N]   rot [B][N][4]   width [B][N]   occ [B][N]
+ */
+#ifndef GIGA_B200_H_
+#define GIGA_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIGA_GRID 40        /* TSDF / plane resolution (networks.py:95, detection_implicit.py:28) */
+#define GIGA_CDIM 32        /* plane feature channels (networks.py:113) */
+#define GIGA_HIDDEN 32      /* decoder hidden size (networks.py:109) */
+
+#define GIGA_HEAD_QUAL  1u  /* decoder_qual  -> sigmoid            (models/__init__.py:119-120) */
+#define GIGA_HEAD_ROT   2u  /* decoder_rot   -> L2 normalise        (models/__init__.py:121-122) */
+#define GIGA_HEAD_WIDTH 4u  /* decoder_width -> raw                 (models/__init__.py:123)     */
+#define GIGA_HEAD_TSDF  8u  /* decoder_tsdf  -> raw occupancy logit (models/__init__.py:64,71)   */
+
+#define GIGA_OK        0
+#define GIGA_EINVAL   -1    /* bad argument (shape, null pointer, unknown name) */
+#define GIGA_ENODEV   -2    /* no CUDA device / wrong architecture */
+#define GIGA_ECUDA    -3    /* CUDA runtime error (message has the detail) */
+#define GIGA_ESTATE   -4    /* parameters missing or not committed */
+
+typedef struct giga_ctx giga_ctx;   /* opaque: packed parameters + device workspaces of one model on one GPU */
+
+/* library --------------------------------------------------------------------------- */
+int         giga_version(void);
+const char *giga_last_error(void);
+
+/* context: replaces `get_network(name).to(device)` (networks.py:10-18,33) as the owner of
+ * device state.  `device` is a CUDA ordinal. */
+int  giga_ctx_create(giga_ctx **out, int device);
+void giga_ctx_destroy(giga_ctx *ctx);
+
+/* Parameters: replaces `net.load_state_dict(...)` (networks.py:34).  `name` is the
+ * reference state_dict key (e.g. "encoder.unet.down_convs.0.conv1.weight",
+ * "decoder_qual.fc_c.3.bias"; full list SURVEY.md 8b), `data` is the tensor in the
+ * reference's own layout, `numel` its element count (checked), `on_device` says whether
+ * `data` is a device pointer.  giga_ctx_commit_params() re-packs everything into the
+ * kernel layouts (synchronous) and must be called after any parameter change. */
+int giga_ctx_set_param(giga_ctx *ctx, const char *name, const float *data, long numel, int on_device);
+int giga_ctx_commit_params(giga_ctx *ctx);
+/* bit mask of GIGA_HEAD_* whose parameters are committed (giga_aff lacks TSDF; giga_geo has only TSDF) */
+unsigned giga_ctx_heads(const giga_ctx *ctx);
+
+/* encoder: replaces `LocalVoxelEncoder.forward` = `net.encode_inputs(inputs)`
+ * (encoder/voxels.py:89-121; models/__init__.py:74-87): Conv3d(1,32,3,p=1)+ReLU, the
+ * three scatter_mean plane projections (voxels.py:57-66, common.py:238-261,303-318) and
+ * the shared UNet (encoder/unet.py:225-239) on each plane. */
+int giga_encode(giga_ctx *ctx, const float *tsdf, int B, float *planes, void *stream);
+
+/* decoder: replaces `LocalDecoder.forward` for every head in `heads` evaluated at the
+ * SAME points (decoder.py:133-176 incl. sample_plane_feature :117-122, layers.py:39-47)
+ * plus the head epilogues of `decode` (models/__init__.py:111-124).  Output pointers of
+ * heads not in `heads` may be NULL. */
+int giga_decode(giga_ctx *ctx, const float *planes, int B, const float *points, int N, unsigned heads,
+                float *qual, float *rot, float *width, float *occ, void *stream);
+
+/* feature sampling only: mode 0 = concatenated 96-d feature (decoder.py:141-147),
+ * mode 1 = summed 32-d `query_feature` (decoder.py:178-191).  out [B][N][96|32]. */
+int giga_sample_feature(giga_ctx *ctx, const float *planes, int B, const float *points, int N, int mode,
+                        float *out, void *stream);
+
+/* final grasp-score reduction: per scene max / first arg-max of qual over its N points
+ * (what `VGNImplicit.select` ultimately keeps, detection_implicit.py:146-174).  Writes
+ * best_val[b], best_idx[b]; the multi-GPU path points these into the all-gather buffer. */
+int giga_scene_argmax(giga_ctx *ctx, const float *qual, int B, int N, float *best_val, int *best_idx, void *stream);
+
+/* end-to-end host entry: replaces `predict()` (detection_implicit.py:99-113) /
+ * `net(x, pos, p_tsdf=pos_occ)` (scripts/train_giga.py:204) with HOST buffers: H2D of
+ * tsdf/points, encode, decode of the grasp heads at `p` (Ng pts) and of the TSDF head at
+ * `p_tsdf` (No pts, may be NULL/0), D2H of the results; returns after the stream has
+ * drained.  Host buffers should be pinned for full copy bandwidth. */
+int giga_forward_host(giga_ctx *ctx, const float *tsdf, int B, const float *p, int Ng, const float *p_tsdf, int No,
+                      float *qual, float *rot, float *width, float *occ, void *stream);
+
+/* introspection ------------------------------------------------------------------- */
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+long giga_ctx_launch_count(const giga_ctx *ctx);
+/* copy an intermediate activation of the LAST giga_encode call into dst (device, fp32).
+ * names: "pre" [3][B][32][40][40] (planes before the U-Net, NCHW), "d0c1","d0c2","p0",
+ * "d1c1","d1c2","p1","d2c1","d2c2","u0","u0c1","u0c2","u1","u1c1","u1c2" (NCHW over the
+ * 3B stacked planes).  Returns the element count, or a negative error. */
+long giga_debug_copy(giga_ctx *ctx, const char *name, float *dst, long capacity, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIGA_B200_H_ */

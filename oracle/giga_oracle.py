@@ -70,24 +70,33 @@ def scatter_mean(src: Tensor, index: Tensor, out: Tensor) -> Tensor:
 # --------------------------------------------------------------------------
 # encoder/unet.py
 # --------------------------------------------------------------------------
-def unet_forward(sd: Mapping[str, Tensor], x: Tensor, prefix: str = "encoder.unet.") -> Tensor:
+def unet_forward(sd: Mapping[str, Tensor], x: Tensor, prefix: str = "encoder.unet.", capture: Optional[dict] = None) -> Tensor:
     """encoder/unet.py:225-239 with DownConv :66-72 and UpConv :101-114, built as
-    UNet(32, in_channels=32, depth=3, start_filts=32, merge_mode='concat')."""
+    UNet(32, in_channels=32, depth=3, start_filts=32, merge_mode='concat').
+    `capture` (tests) receives every intermediate activation under the names the CUDA
+    library uses (d0c1, d0c2, p0, ..., u1c2)."""
     g = lambda n: sd[prefix + n]
+    cap = (lambda k, v: capture.__setitem__(k, v)) if capture is not None else (lambda k, v: None)
     enc = []
     depth = 3
     for i in range(depth):
         x = F.relu(F.conv2d(x, g(f"down_convs.{i}.conv1.weight"), g(f"down_convs.{i}.conv1.bias"), padding=1))
+        cap(f"d{i}c1", x)
         x = F.relu(F.conv2d(x, g(f"down_convs.{i}.conv2.weight"), g(f"down_convs.{i}.conv2.bias"), padding=1))
+        cap(f"d{i}c2", x)
         enc.append(x)
         if i < depth - 1:
             x = F.max_pool2d(x, kernel_size=2, stride=2)
+            cap(f"p{i}", x)
     for i in range(depth - 1):
         skip = enc[-(i + 2)]
         up = F.conv_transpose2d(x, g(f"up_convs.{i}.upconv.weight"), g(f"up_convs.{i}.upconv.bias"), stride=2)
+        cap(f"u{i}", up)
         x = torch.cat((up, skip), 1)
         x = F.relu(F.conv2d(x, g(f"up_convs.{i}.conv1.weight"), g(f"up_convs.{i}.conv1.bias"), padding=1))
+        cap(f"u{i}c1", x)
         x = F.relu(F.conv2d(x, g(f"up_convs.{i}.conv2.weight"), g(f"up_convs.{i}.conv2.bias"), padding=1))
+        cap(f"u{i}c2", x)
     return F.conv2d(x, g("conv_final.weight"), g("conv_final.bias"))
 
 
