@@ -32,6 +32,8 @@ SYMBOLS = {
     "giga_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_ctx_launch_count": (C.c_long, [C.c_void_p]),
+    "giga_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "giga_ctx_timing_report": (C.c_long, [C.c_void_p, C.c_char_p, C.c_long]),
     "giga_debug_copy": (C.c_long, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p]),
 }
 
@@ -44,7 +46,7 @@ def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: the giga_b200 CUDA library is not built. Run "
-            "`python -m giga_b200.build` (or __graft_entry__.build()). There is no CPU/PyTorch fallback.")
+            "`python giga_b200/build.py` (or __graft_entry__.build()). There is no CPU/PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

@@ -1,6 +1,6 @@
 """Build libgiga_b200.so (hand-written CUDA for sm_100a) in-tree with nvcc.
 
-    python -m giga_b200.build [--force] [--verbose]
+    python giga_b200/build.py [--force] [--verbose]      (a script: importing the package needs the .so)
 
 nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels with
 the repo snapshot to the GPU box.

@@ -108,6 +108,11 @@ struct giga_ctx {
   int hcap_B = 0, hcap_Ng = 0, hcap_No = 0;
   long launches = 0;
   bool attrs_set = false;
+  // optional per-kernel CUDA-event timing (bench.py roofline): events recorded on the launch stream
+  bool timing = false;
+  struct Timed { const char* name; cudaEvent_t a, b; };
+  std::vector<Timed> timed;
+  std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace {
@@ -116,6 +121,30 @@ int set_device(giga_ctx* ctx) {
   CU_TRY(cudaSetDevice(ctx->device));
   return GIGA_OK;
 }
+
+cudaEvent_t take_event(giga_ctx* ctx) {
+  if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// Brackets one kernel launch with events when timing is on; always counts the launch.
+struct LaunchScope {
+  giga_ctx* ctx; cudaStream_t st; cudaEvent_t b = nullptr;
+  LaunchScope(giga_ctx* c, const char* name, cudaStream_t s) : ctx(c), st(s) {
+    if (ctx->timing) {
+      cudaEvent_t a = take_event(ctx);
+      b = take_event(ctx);
+      cudaEventRecord(a, st);
+      ctx->timed.push_back({name, a, b});
+    }
+  }
+  ~LaunchScope() {
+    if (b) cudaEventRecord(b, st);
+    ctx->launches++;
+  }
+};
 
 int ensure_attrs(giga_ctx* ctx) {
   if (ctx->attrs_set) return GIGA_OK;
@@ -155,20 +184,20 @@ float* act(giga_ctx* ctx, const char* name) {
 }
 
 template <class K>
-void launch_conv(giga_ctx* ctx, int n_img, const float* s0, const float* s1, int layer, float* out, float* pooled,
-                 cudaStream_t st) {
+void launch_conv(giga_ctx* ctx, const char* name, int n_img, const float* s0, const float* s1, int layer, float* out,
+                 float* pooled, cudaStream_t st) {
   dim3 grid(K::NB * K::NCT, n_img);
+  LaunchScope ls(ctx, name, st);
   conv3x3_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(s0, s1, ctx->d_enc + ctx->el.conv[layer],
                                                               ctx->d_enc + ctx->el.bias[layer], out, pooled);
-  ctx->launches++;
 }
 
 template <class K>
-void launch_convT(giga_ctx* ctx, int n_img, const float* src, int up, float* out, cudaStream_t st) {
+void launch_convT(giga_ctx* ctx, const char* name, int n_img, const float* src, int up, float* out, cudaStream_t st) {
   dim3 grid(K::NB * K::NCT, n_img);
+  LaunchScope ls(ctx, name, st);
   convT2x2_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(src, ctx->d_enc + ctx->el.up_w[up],
                                                                ctx->d_enc + ctx->el.up_b[up], out);
-  ctx->launches++;
 }
 
 bool get(const giga_ctx* ctx, const std::string& name, long numel, const float** out) {
@@ -215,6 +244,8 @@ void giga_ctx_destroy(giga_ctx* ctx) {
     if (p) cudaFree(p);
   for (float* p : ctx->d_act)
     if (p) cudaFree(p);
+  for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -334,27 +365,34 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
   if (int r = ensure_workspace(ctx, B)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_img = 3 * B;
-  conv_in_planes_kernel<<<dim3(CI_NT, B), CI_THREADS, CI_SMEM_BYTES, st>>>(tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
-  xz_finish_kernel<<<dim3(C, B), 256, 0, st>>>(ctx->d_xzpart, ctx->d_pre, B);
-  ctx->launches += 2;
+  {
+    LaunchScope ls(ctx, "conv_in_planes", st);
+    conv_in_planes_kernel<<<dim3(CI_NT, B), CI_THREADS, CI_SMEM_BYTES, st>>>(tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+  }
+  {
+    LaunchScope ls(ctx, "xz_finish", st);
+    xz_finish_kernel<<<dim3(C, B), 256, 0, st>>>(ctx->d_xzpart, ctx->d_pre, B);
+  }
   float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"),
         *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),
         *u0 = act(ctx, "u0"), *u0c1 = act(ctx, "u0c1"), *u0c2 = act(ctx, "u0c2"), *u1 = act(ctx, "u1"),
         *u1c1 = act(ctx, "u1c1"), *u1c2 = act(ctx, "u1c2");
-  launch_conv<K_d0c1>(ctx, n_img, ctx->d_pre, nullptr, 0, d0c1, nullptr, st);
-  launch_conv<K_d0c2>(ctx, n_img, d0c1, nullptr, 1, d0c2, p0, st);
-  launch_conv<K_d1c1>(ctx, n_img, p0, nullptr, 2, d1c1, nullptr, st);
-  launch_conv<K_d1c2>(ctx, n_img, d1c1, nullptr, 3, d1c2, p1, st);
-  launch_conv<K_d2c1>(ctx, n_img, p1, nullptr, 4, d2c1, nullptr, st);
-  launch_conv<K_d2c2>(ctx, n_img, d2c1, nullptr, 5, d2c2, nullptr, st);
-  launch_convT<K_u0up>(ctx, n_img, d2c2, 0, u0, st);
-  launch_conv<K_u0c1>(ctx, n_img, u0, d1c2, 6, u0c1, nullptr, st);   // cat(from_up, from_down), unet.py:109
-  launch_conv<K_u0c2>(ctx, n_img, u0c1, nullptr, 7, u0c2, nullptr, st);
-  launch_convT<K_u1up>(ctx, n_img, u0c2, 1, u1, st);
-  launch_conv<K_u1c1>(ctx, n_img, u1, d0c2, 8, u1c1, nullptr, st);
-  launch_conv<K_u1c2>(ctx, n_img, u1c1, nullptr, 9, u1c2, nullptr, st);
-  conv1x1_nhwc_kernel<<<dim3(G2 / F_PIX, n_img), 256, 0, st>>>(u1c2, ctx->d_enc + ctx->el.fin_w, ctx->d_enc + ctx->el.fin_b, planes);
-  ctx->launches++;
+  launch_conv<K_d0c1>(ctx, "conv3x3:d0c1", n_img, ctx->d_pre, nullptr, 0, d0c1, nullptr, st);
+  launch_conv<K_d0c2>(ctx, "conv3x3:d0c2", n_img, d0c1, nullptr, 1, d0c2, p0, st);
+  launch_conv<K_d1c1>(ctx, "conv3x3:d1c1", n_img, p0, nullptr, 2, d1c1, nullptr, st);
+  launch_conv<K_d1c2>(ctx, "conv3x3:d1c2", n_img, d1c1, nullptr, 3, d1c2, p1, st);
+  launch_conv<K_d2c1>(ctx, "conv3x3:d2c1", n_img, p1, nullptr, 4, d2c1, nullptr, st);
+  launch_conv<K_d2c2>(ctx, "conv3x3:d2c2", n_img, d2c1, nullptr, 5, d2c2, nullptr, st);
+  launch_convT<K_u0up>(ctx, "convT:u0", n_img, d2c2, 0, u0, st);
+  launch_conv<K_u0c1>(ctx, "conv3x3:u0c1", n_img, u0, d1c2, 6, u0c1, nullptr, st);   // cat(from_up, from_down), unet.py:109
+  launch_conv<K_u0c2>(ctx, "conv3x3:u0c2", n_img, u0c1, nullptr, 7, u0c2, nullptr, st);
+  launch_convT<K_u1up>(ctx, "convT:u1", n_img, u0c2, 1, u1, st);
+  launch_conv<K_u1c1>(ctx, "conv3x3:u1c1", n_img, u1, d0c2, 8, u1c1, nullptr, st);
+  launch_conv<K_u1c2>(ctx, "conv3x3:u1c2", n_img, u1c1, nullptr, 9, u1c2, nullptr, st);
+  {
+    LaunchScope ls(ctx, "conv1x1_final", st);
+    conv1x1_nhwc_kernel<<<dim3(G2 / F_PIX, n_img), 256, 0, st>>>(u1c2, ctx->d_enc + ctx->el.fin_w, ctx->d_enc + ctx->el.fin_b, planes);
+  }
   ctx->last_B = B;
   CU_TRY(cudaGetLastError());
   return GIGA_OK;
@@ -370,9 +408,11 @@ int giga_decode(giga_ctx* ctx, const float* planes, int B, const float* points, 
     return fail(GIGA_EINVAL, "giga_decode: output pointer of a requested head is null");
   if (int r = set_device(ctx)) return r;
   cudaStream_t st = (cudaStream_t)stream;
-  decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N,
-                                                                                       heads, qual, rot, width, occ);
-  ctx->launches++;
+  {
+    LaunchScope ls(ctx, heads == GIGA_HEAD_TSDF ? "decode_points:tsdf" : "decode_points:grasp", st);
+    decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N,
+                                                                                         heads, qual, rot, width, occ);
+  }
   CU_TRY(cudaGetLastError());
   return GIGA_OK;
 }
@@ -383,8 +423,10 @@ int giga_sample_feature(giga_ctx* ctx, const float* planes, int B, const float* 
     return fail(GIGA_EINVAL, "giga_sample_feature: bad argument");
   if (int r = set_device(ctx)) return r;
   if (int r = ensure_attrs(ctx)) return r;
-  sample_feature_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, SF_SMEM_BYTES, (cudaStream_t)stream>>>(planes, points, B, N, mode, out);
-  ctx->launches++;
+  {
+    LaunchScope ls(ctx, "sample_feature", (cudaStream_t)stream);
+    sample_feature_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, SF_SMEM_BYTES, (cudaStream_t)stream>>>(planes, points, B, N, mode, out);
+  }
   CU_TRY(cudaGetLastError());
   return GIGA_OK;
 }
@@ -392,8 +434,10 @@ int giga_sample_feature(giga_ctx* ctx, const float* planes, int B, const float* 
 int giga_scene_argmax(giga_ctx* ctx, const float* qual, int B, int N, float* best_val, int* best_idx, void* stream) {
   if (!ctx || !qual || !best_val || !best_idx || B <= 0 || N <= 0) return fail(GIGA_EINVAL, "giga_scene_argmax: bad argument");
   if (int r = set_device(ctx)) return r;
-  scene_argmax_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(qual, N, best_val, best_idx);
-  ctx->launches++;
+  {
+    LaunchScope ls(ctx, "scene_argmax", (cudaStream_t)stream);
+    scene_argmax_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(qual, N, best_val, best_idx);
+  }
   CU_TRY(cudaGetLastError());
   return GIGA_OK;
 }
@@ -443,6 +487,40 @@ int giga_forward_host(giga_ctx* ctx, const float* tsdf, int B, const float* p, i
 }
 
 long giga_ctx_launch_count(const giga_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int giga_ctx_set_timing(giga_ctx* ctx, int enabled) {
+  if (!ctx) return fail(GIGA_EINVAL, "giga_ctx_set_timing: ctx is null");
+  ctx->timing = enabled != 0;
+  return GIGA_OK;
+}
+
+long giga_ctx_timing_report(giga_ctx* ctx, char* buf, long cap) {
+  if (!ctx || !buf || cap <= 0) return fail(GIGA_EINVAL, "giga_ctx_timing_report: bad argument");
+  if (int r = set_device(ctx)) return r;
+  std::map<std::string, std::pair<long, double>> agg;
+  std::vector<std::string> order;
+  for (auto& t : ctx->timed) {
+    CU_TRY(cudaEventSynchronize(t.b));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, t.a, t.b));
+    if (!agg.count(t.name)) order.push_back(t.name);
+    auto& e = agg[t.name];
+    e.first++;
+    e.second += ms;
+    ctx->ev_pool.push_back(t.a);
+    ctx->ev_pool.push_back(t.b);
+  }
+  ctx->timed.clear();
+  std::string out;
+  for (auto& n : order) {
+    char line[160];
+    snprintf(line, sizeof line, "%s %ld %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+    out += line;
+  }
+  if ((long)out.size() + 1 > cap) return fail(GIGA_EINVAL, "giga_ctx_timing_report: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (long)out.size();
+}
 
 long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity, void* stream) {
   if (!ctx || !name || !dst) return fail(GIGA_EINVAL, "giga_debug_copy: bad argument");

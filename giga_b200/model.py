@@ -160,6 +160,19 @@ class _Engine:
     def launches(self) -> int:
         return int(lib.giga_ctx_launch_count(self.h))
 
+    def set_timing(self, on: bool):
+        check(lib.giga_ctx_set_timing(self.h, int(on)), "giga_ctx_set_timing")
+
+    def timing_report(self):
+        """-> {kernel name: (launches, total_ms)} since the last report (CUDA events on the launch stream)."""
+        buf = C.create_string_buffer(1 << 16)
+        check(int(lib.giga_ctx_timing_report(self.h, buf, len(buf))), "giga_ctx_timing_report")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out[name] = (int(n), float(ms))
+        return out
+
 
 def _stream(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -105,6 +105,12 @@ int giga_forward_host(giga_ctx *ctx, const float *tsdf, int B, const float *p, i
 /* introspection ------------------------------------------------------------------- */
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 long giga_ctx_launch_count(const giga_ctx *ctx);
+/* per-kernel device timing for the roofline report: when enabled every kernel launch is bracketed
+ * by CUDA events recorded on the launch stream.  giga_ctx_timing_report() waits for the recorded
+ * events, writes one text line "name launches total_ms" per distinct kernel into buf (in first-launch
+ * order), clears the record and returns the string length. */
+int  giga_ctx_set_timing(giga_ctx *ctx, int enabled);
+long giga_ctx_timing_report(giga_ctx *ctx, char *buf, long cap);
 /* copy an intermediate activation of the LAST giga_encode call into dst (device, fp32).
  * names: "pre" [3][B][32][40][40] (planes before the U-Net, NCHW), "d0c1","d0c2","p0",
  * "d1c1","d1c2","p1","d2c1","d2c2","u0","u0c1","u0c2","u1","u1c1","u1c2" (NCHW over the

@@ -1,0 +1,222 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+fixtures of the unmodified reference.  Tolerance: 1e-4 absolute fp32 on every model output
+(BASELINE.json north_star), arg-max of the grasp quality bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import giga_oracle as O
+from tests.util import make_net
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+def _close(got, ref, tol=TOL, name=""):
+    got = got.detach().float().cpu()
+    ref = torch.as_tensor(ref)
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    assert torch.isfinite(got).all(), name
+    err = (got - ref).abs().max().item()
+    assert err <= tol, f"{name}: max abs err {err:.3e} > {tol}"
+
+
+@pytest.fixture(scope="module")
+def net(oracle_sd):
+    return make_net("giga", oracle_sd)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_outputs_match_reference_golden(net, golden, tag):
+    B, N, seed = (int(v) for v in golden[f"{tag}_cfg"])
+    x, p, pt = O.seeded_inputs(B, N, seed=seed)
+    with torch.no_grad():
+        c = net.encode_inputs(x.to(DEV))
+        for k in O.PLANES:
+            g = c[k] if B == 1 else c[k][:, ::4, ::3, ::3]
+            _close(g, golden[f"{tag}_plane_{k}"], name=f"plane_{k}")
+        pre = net.debug_activation("pre", B)
+        for i, k in enumerate(O.PLANES):
+            g = pre[i] if B == 1 else pre[i][:, ::4, ::3, ::3]
+            _close(g, golden[f"{tag}_pre_{k}"], tol=1e-5, name=f"pre_{k}")
+        _close(net.sample_feature(p.to(DEV), c, "concat"), golden[f"{tag}_feat96"], name="feat96")
+        _close(net.query_feature(p.to(DEV), c), golden[f"{tag}_qfeat32"], name="qfeat32")
+        qual, rot, width, occ = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+        _close(qual, golden[f"{tag}_qual"], name="qual")
+        _close(rot, golden[f"{tag}_rot"], name="rot")
+        _close(width, golden[f"{tag}_width"], name="width")
+        _close(occ, golden[f"{tag}_tsdf"], name="tsdf")
+        _close(net.infer_geo(x.to(DEV), pt.to(DEV)), golden[f"{tag}_geo"], name="infer_geo")
+        _close(net.decode_occ(pt.to(DEV), c).probs, golden[f"{tag}_occ_probs"], name="occ_probs")
+        assert (qual.argmax(1).cpu().numpy() == golden[f"{tag}_qual"].argmax(1)).all()
+        q3, r3, w3 = net(x.to(DEV), p.to(DEV))
+        assert torch.equal(q3, qual) and torch.equal(r3, rot) and torch.equal(w3, width)
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (1, 129), (3, 128), (2, 1000)])
+def test_every_stage_matches_oracle(net, oracle_sd, B, N):
+    sd = oracle_sd
+    x, p, pt = O.seeded_inputs(B, N, seed=11 + B + N)
+    with torch.no_grad():
+        pre = O.plane_features_pre_unet(sd, x)
+        pre_stack = torch.stack([pre[k] for k in O.PLANES])
+        cap = {}
+        ref_planes = O.unet_forward(sd, pre_stack.reshape(3 * B, 32, 40, 40), capture=cap).reshape(3, B, 32, 40, 40)
+        c = net.encode_inputs(x.to(DEV))
+        _close(net.debug_activation("pre", B), pre_stack, tol=1e-5, name="pre")
+        for k, v in cap.items():
+            got = net.debug_activation(k, B)
+            ref = v.reshape(got.shape)
+            _close(got, ref, tol=1e-5 * max(1.0, ref.abs().max().item()), name=k)
+        _close(torch.stack([c[k] for k in O.PLANES]), ref_planes, name="planes")
+        planes_ref = {k: ref_planes[i] for i, k in enumerate(O.PLANES)}
+        _close(net.sample_feature(p.to(DEV), c, "concat"), O.sample_concat_feature(p, planes_ref), name="feat96")
+        ref = O.forward(sd, x, p, pt)
+        out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+        for nme, a, b in zip(("qual", "rot", "width", "occ"), out, ref):
+            _close(a, b, name=nme)
+        assert torch.equal(out[0].argmax(1).cpu(), ref[0].argmax(1))
+        rn = out[1].norm(dim=2)
+        assert (rn - 1).abs().max().item() < 1e-5
+        assert (out[0] > 0).all() and (out[0] < 1).all()
+
+
+def test_clamp_edge_points(net, oracle_sd):
+    """points on +-0.5, outside the cube, on voxel centres and on the 1/40 planner lattice."""
+    x, _, _ = O.seeded_inputs(1, 8, seed=2)
+    lin = torch.linspace(-0.5, 0.5 - 1.0 / 40, 40)
+    lattice = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1).reshape(1, -1, 3)[:, ::37]
+    special = torch.tensor([[0.5, 0.5, 0.5], [-0.5, -0.5, -0.5], [0.7, -0.9, 0.2], [5.0, 5.0, -5.0], [0.4999999, -0.4999999, 0.0],
+                            [0.5000001, 0.5, -0.5000001], [1e-9, -1e-9, 0.0], [19.0 / 39 - 0.5, 20.0 / 39 - 0.5, 0.5 - 1e-6]])[None]
+    p = torch.cat([special, lattice], 1).contiguous()
+    with torch.no_grad():
+        planes = O.encode_inputs(oracle_sd, x)
+        c = net.encode_inputs(x.to(DEV))
+        _close(net.sample_feature(p.to(DEV), c, "concat"), O.sample_concat_feature(p, planes), name="feat96-edge")
+        ref = O.decode(oracle_sd, p, planes)
+        out = net.decode(p.to(DEV), c)
+        for nme, a, b in zip(("qual", "rot", "width"), out, ref):
+            _close(a, b, name=nme)
+
+
+@pytest.mark.parametrize("name", ["giga_aff", "giga_geo", "giga_detach"])
+def test_model_variants(oracle_sd, name):
+    net = make_net(name, oracle_sd)
+    x, p, pt = O.seeded_inputs(2, 77, seed=5)
+    xd, pd, ptd = x.to(DEV), p.to(DEV), pt.to(DEV)
+    with torch.no_grad():
+        ref = O.forward(oracle_sd, x, p, pt)
+        if name == "giga_geo":
+            _close(net(xd, pd, ptd), ref[3], name="geo.forward")
+            _close(net.infer_geo(xd, ptd), ref[3], name="geo.infer_geo")
+            assert not hasattr(net, "decoder_qual")
+        elif name == "giga_aff":
+            out = net(xd, pd)
+            for a, b in zip(out, ref[:3]):
+                _close(a, b, name="aff")
+            assert not hasattr(net, "decoder_tsdf")
+            with pytest.raises(Exception):
+                net(xd, pd, p_tsdf=ptd)
+        else:
+            out = net(xd, pd, p_tsdf=ptd)
+            assert net.detach_tsdf
+            for a, b in zip(out, ref):
+                _close(a, b, name="detach")
+
+
+def test_forward_host_equals_device_path(net):
+    x, p, pt = O.seeded_inputs(3, 300, seed=9)
+    with torch.no_grad():
+        dev = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+        host = net.forward_host(x.pin_memory(), p.pin_memory(), pt.pin_memory())
+        for a, b in zip(dev, host):
+            assert not b.is_cuda and torch.equal(a.cpu(), b)
+        host2 = net.forward_host(x, p, None)  # pageable host memory, grasp heads only
+        assert len(host2) == 3 and torch.equal(host2[0], host[0])
+
+
+def test_scene_argmax(net):
+    g = torch.Generator().manual_seed(0)
+    q = torch.rand(5, 4097, generator=g)
+    q[1, 77] = q[1, 4000] = 2.0  # tie -> first index
+    q[2, 0] = 3.0
+    q[3, 4096] = 3.0
+    v, i = net.scene_argmax(q.to(DEV))
+    assert torch.equal(i.cpu().long(), q.argmax(1)) and i[1].item() == 77
+    assert torch.equal(v.cpu(), q.max(1).values)
+
+
+def test_baseline_size_properties(net, oracle_sd):
+    """BASELINE config[1] size (B=32, 2048 grasp + 2048 occupancy points): full oracle comparison
+    plus size-independent properties (sharding / permutation invariance are bit-exact)."""
+    B, N = 32, 2048
+    x, p, pt = O.seeded_inputs(B, N, seed=21)
+    xd, pd, ptd = x.to(DEV), p.to(DEV), pt.to(DEV)
+    with torch.no_grad():
+        out = net(xd, pd, p_tsdf=ptd)
+        ref = O.forward(oracle_sd, x, p, pt)
+        for nme, a, b in zip(("qual", "rot", "width", "occ"), out, ref):
+            _close(a, b, name=nme)
+        assert torch.equal(out[0].argmax(1).cpu(), ref[0].argmax(1))
+        # scenes are independent: two shards of 16 == one batch of 32, bit for bit
+        lo = net(xd[:16], pd[:16], p_tsdf=ptd[:16])
+        hi = net(xd[16:], pd[16:], p_tsdf=ptd[16:])
+        for a, l, h in zip(out, lo, hi):
+            assert torch.equal(a, torch.cat([l, h]))
+        # points are independent: permuting the queries permutes the outputs, bit for bit
+        perm = torch.randperm(N, generator=torch.Generator().manual_seed(3)).to(DEV)
+        outp = net(xd, pd[:, perm], p_tsdf=ptd[:, perm])
+        for a, b in zip(out, outp):
+            assert torch.equal(a[:, perm], b)
+        # run-to-run determinism
+        again = net(xd, pd, p_tsdf=ptd)
+        for a, b in zip(out, again):
+            assert torch.equal(a, b)
+
+
+def test_checkpoint_roundtrip_and_param_updates(tmp_path, oracle_sd):
+    import giga_b200
+    from pathlib import Path
+
+    net = make_net("giga", oracle_sd)
+    path = Path(tmp_path) / "vgn_giga_01.pt"
+    torch.save(net.state_dict(), path)
+    net2 = giga_b200.load_network(path, torch.device(DEV))          # name parsed from the file name
+    net3 = giga_b200.load_network(path, torch.device(DEV), model_type="giga")
+    x, p, pt = O.seeded_inputs(1, 64, seed=4)
+    with torch.no_grad():
+        a = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+        for other in (net2, net3):
+            b = other(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+            for u, v in zip(a, b):
+                assert torch.equal(u, v)
+        # in-place parameter update (what optimizer.step does) must be picked up
+        net2.decoder_width.fc_out.bias.add_(1.5)
+        c = net2(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+        assert torch.allclose(c[2], a[2] + 1.5, atol=1e-6) and torch.equal(c[0], a[0])
+    # default initialisation mirrors the reference: fc_1.weight == 0, U-Net conv biases == 0
+    fresh = giga_b200.get_network("giga")
+    assert fresh.decoder_qual.blocks[0].fc_1.weight.abs().max().item() == 0
+    assert fresh.encoder.unet.down_convs[0].conv1.bias.abs().max().item() == 0
+
+
+def test_cabi_error_behaviour(net):
+    from giga_b200._lib import lib
+    eng = net._engine()
+    rc = lib.giga_encode(eng.h, C.c_void_p(0), 1, C.c_void_p(0), C.c_void_p(0))
+    assert rc == -1 and b"giga_encode" in lib.giga_last_error()
+    x = torch.zeros(1, 40, 40, 40, device=DEV)
+    planes = torch.zeros(3, 1, 40, 40, 32, device=DEV)
+    assert lib.giga_encode(eng.h, C.c_void_p(x.data_ptr()), 0, C.c_void_p(planes.data_ptr()), C.c_void_p(0)) == -1
+    pts = torch.zeros(1, 4, 3, device=DEV)
+    assert lib.giga_decode(eng.h, C.c_void_p(planes.data_ptr()), 1, C.c_void_p(pts.data_ptr()), 4, 1,
+                           C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)) == -1
+    with pytest.raises(Exception):
+        net.encode_inputs(torch.zeros(1, 40, 40, 39, device=DEV))
+    with pytest.raises(Exception):
+        net.encode_inputs(torch.zeros(1, 40, 40, 40))  # CPU tensor: no CPU path
+    assert net.gpu_launches > 0
