@@ -117,10 +117,23 @@ def run_cpu_oracle(B, N, steps, warmup, budget_s=25.0):
 
     from oracle import giga_oracle as O
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     sd = O.seeded_state_dict(seed=1)
     x, p, pt = O.seeded_inputs(B, N, seed=0, edge_cases=False)
+    # the reference just uses torch's default intra-op pool; on many-core hosts that oversubscribes the
+    # small convs, so give the CPU arm its best case: probe a few pool sizes on a 4-scene sample
+    cand = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, cores = None, ncpu
+    with torch.no_grad():
+        for c in cand:
+            torch.set_num_threads(c)
+            O.forward(sd, x[:4], p[:4], pt[:4])
+            t0 = time.perf_counter()
+            O.forward(sd, x[:4], p[:4], pt[:4])
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, cores = dt, c
+    torch.set_num_threads(cores)
     with torch.no_grad():
         for _ in range(warmup):
             O.forward(sd, x, p, pt)
@@ -194,7 +207,7 @@ def main():
         k = i % POOL
         c = net.encode_inputs(xs[k])
         qual, rot, width = net.decode(ps[k], c)
-        occ = net.decode_occ(pts[k], c).logits
+        occ = net.decoder_tsdf(pts[k], c)   # as forward() does (models/__init__.py:64)
         net.scene_argmax(qual, gather_val[rank], gather_idx[rank])
         if world > 1:
             dist.all_gather_into_tensor(gather_val, gather_val[rank].clone())

@@ -11,7 +11,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libgiga_b200.so")
 
-HEAD_QUAL, HEAD_ROT, HEAD_WIDTH, HEAD_TSDF = 1, 2, 4, 8
+HEAD_QUAL, HEAD_ROT, HEAD_WIDTH, HEAD_TSDF, HEAD_RAW = 1, 2, 4, 8, 16
 HEAD_GRASP = HEAD_QUAL | HEAD_ROT | HEAD_WIDTH
 
 # symbol -> (restype, argtypes); must list every function include/giga_b200.h declares

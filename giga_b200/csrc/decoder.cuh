@@ -216,11 +216,12 @@ decode_points_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
     }
     if (valid) {
       const size_t idx = (size_t)b * N + n;
+      const bool raw = (heads & 16u) != 0;                          // GIGA_HEAD_RAW
       if (head == 0) {
-        qual[idx] = 1.f / (1.f + expf(-o[0]));                      // torch.sigmoid
+        qual[idx] = raw ? o[0] : 1.f / (1.f + expf(-o[0]));         // torch.sigmoid
       } else if (head == 1) {
         const float nrm = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
-        const float d = fmaxf(nrm, 1e-12f);                         // F.normalize(dim=2, eps=1e-12)
+        const float d = raw ? 1.f : fmaxf(nrm, 1e-12f);             // F.normalize(dim=2, eps=1e-12)
         st4(rot + idx * 4, make_float4(o[0] / d, o[1] / d, o[2] / d, o[3] / d));
       } else if (head == 2) {
         width[idx] = o[0];

@@ -400,16 +400,17 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
 
 int giga_decode(giga_ctx* ctx, const float* planes, int B, const float* points, int N, unsigned heads, float* qual,
                 float* rot, float* width, float* occ, void* stream) {
-  if (!ctx || !planes || !points || B <= 0 || N <= 0 || !heads) return fail(GIGA_EINVAL, "giga_decode: bad argument");
+  if (!ctx || !planes || !points || B <= 0 || N <= 0 || !(heads & 15u) || (heads & ~31u))
+    return fail(GIGA_EINVAL, "giga_decode: bad argument");
   if (!ctx->committed) return fail(GIGA_ESTATE, "giga_decode: parameters not committed");
-  if (heads & ~ctx->heads) return fail(GIGA_ESTATE, "giga_decode: a requested head has no committed parameters");
+  if ((heads & 15u) & ~ctx->heads) return fail(GIGA_ESTATE, "giga_decode: a requested head has no committed parameters");
   if (((heads & GIGA_HEAD_QUAL) && !qual) || ((heads & GIGA_HEAD_ROT) && !rot) || ((heads & GIGA_HEAD_WIDTH) && !width) ||
       ((heads & GIGA_HEAD_TSDF) && !occ))
     return fail(GIGA_EINVAL, "giga_decode: output pointer of a requested head is null");
   if (int r = set_device(ctx)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   {
-    LaunchScope ls(ctx, heads == GIGA_HEAD_TSDF ? "decode_points:tsdf" : "decode_points:grasp", st);
+    LaunchScope ls(ctx, (heads & 15u) == GIGA_HEAD_TSDF ? "decode_points:tsdf" : "decode_points:grasp", st);
     decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N,
                                                                                          heads, qual, rot, width, occ);
   }

@@ -21,7 +21,9 @@ import torch.nn as nn
 from torch import distributions as dist
 
 from . import _lib
-from ._lib import HEAD_GRASP, HEAD_QUAL, HEAD_ROT, HEAD_TSDF, HEAD_WIDTH, check, lib
+import weakref
+
+from ._lib import HEAD_GRASP, HEAD_QUAL, HEAD_RAW, HEAD_ROT, HEAD_TSDF, HEAD_WIDTH, check, lib
 
 PLANES = ("xz", "xy", "yz")
 GRID = 40
@@ -111,6 +113,16 @@ class LocalDecoder(nn.Module):  # conv_onet/models/decoder.py:61-206 (concat_fea
         self.fc_p = _linear(3, 32)
         self.blocks = nn.ModuleList([ResnetBlockFC(32) for _ in range(5)])
         self.fc_out = _linear(32, out_dim)
+        self.__dict__["_owner"] = None   # weakref to the model whose engine evaluates this head
+        self.__dict__["_head_bit"] = 0
+
+    def forward(self, p, c_plane, **kwargs):
+        """decoder.py:133-176 -- the bare head output (no sigmoid / normalise): (B,N) or (B,N,4)."""
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise _lib.GigaError("LocalDecoder is a parameter container; call it through its ConvolutionalOccupancyNetwork")
+        out = owner._decode_heads(p, c_plane, self._head_bit | HEAD_RAW)
+        return out[{HEAD_QUAL: 0, HEAD_ROT: 1, HEAD_WIDTH: 2, HEAD_TSDF: 3}[self._head_bit]]
 
 
 class PlaneFeatures(dict):
@@ -244,6 +256,8 @@ class _GigaBase(nn.Module):
             raise _lib.GigaError(f"points must be (B,N,3) with B={planes.shape[1]}, got {tuple(p.shape)}")
         B, N = pts.shape[0], pts.shape[1]
         mk = lambda *s: torch.empty(s, device=eng.device, dtype=torch.float32)
+        if heads & 15 & ~int(lib.giga_ctx_heads(eng.h)):
+            raise _lib.GigaError("this model has no parameters for a requested decoder head")
         qual = mk(B, N) if heads & HEAD_QUAL else None
         rot = mk(B, N, 4) if heads & HEAD_ROT else None
         width = mk(B, N) if heads & HEAD_WIDTH else None
@@ -252,6 +266,14 @@ class _GigaBase(nn.Module):
         check(lib.giga_decode(eng.h, ptr(planes), B, ptr(pts), N, heads, ptr(qual), ptr(rot), ptr(width), ptr(occ),
                               _stream(eng.device)), "giga_decode")
         return qual, rot, width, occ
+
+    def _bind_heads(self):
+        for name, bit in (("decoder_qual", HEAD_QUAL), ("decoder_rot", HEAD_ROT), ("decoder_width", HEAD_WIDTH),
+                          ("decoder_tsdf", HEAD_TSDF)):
+            dec = self._modules.get(name)
+            if dec is not None:
+                dec.__dict__["_owner"] = weakref.ref(self)
+                dec.__dict__["_head_bit"] = bit
 
     def decode_occ(self, p, c, **kwargs):
         """models/__init__.py:100-109"""
@@ -336,6 +358,7 @@ class ConvolutionalOccupancyNetwork(_GigaBase):
         self.encoder = LocalVoxelEncoder()
         self._device = device
         self.detach_tsdf = detach_tsdf
+        self._bind_heads()
         if device is not None:
             self.to(device)
 
@@ -344,7 +367,7 @@ class ConvolutionalOccupancyNetwork(_GigaBase):
         c = self.encode_inputs(inputs)
         qual, rot, width = self.decode(p, c)
         if p_tsdf is not None:
-            tsdf = self._decode_heads(p_tsdf, c, HEAD_TSDF)[3]
+            tsdf = self.decoder_tsdf(p_tsdf, c, **kwargs)
             return qual, rot, width, tsdf
         return qual, rot, width
 
@@ -377,6 +400,7 @@ class ConvolutionalOccupancyNetworkGeometry(_GigaBase):
         self.decoder_tsdf = LocalDecoder(1)
         self.encoder = LocalVoxelEncoder()
         self._device = device
+        self._bind_heads()
         if device is not None:
             self.to(device)
 

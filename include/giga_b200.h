@@ -42,6 +42,8 @@ extern "C" {
 #define GIGA_HEAD_ROT   2u  /* decoder_rot   -> L2 normalise        (models/__init__.py:121-122) */
 #define GIGA_HEAD_WIDTH 4u  /* decoder_width -> raw                 (models/__init__.py:123)     */
 #define GIGA_HEAD_TSDF  8u  /* decoder_tsdf  -> raw occupancy logit (models/__init__.py:64,71)   */
+#define GIGA_HEAD_RAW  16u  /* modifier: skip the sigmoid / normalise epilogues, i.e. the bare
+                               `LocalDecoder.forward` output (decoder.py:173-176) */
 
 #define GIGA_OK        0
 #define GIGA_EINVAL   -1    /* bad argument (shape, null pointer, unknown name) */

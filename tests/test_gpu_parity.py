@@ -220,3 +220,28 @@ def test_cabi_error_behaviour(net):
     with pytest.raises(Exception):
         net.encode_inputs(torch.zeros(1, 40, 40, 40))  # CPU tensor: no CPU path
     assert net.gpu_launches > 0
+
+
+def test_heads_are_callable_like_the_reference(net, oracle_sd):
+    """`net.decoder_tsdf(p, c)` etc. are used directly by the reference (models/__init__.py:64,71):
+    the bare head output, without sigmoid / normalise."""
+    x, p, _ = O.seeded_inputs(2, 150, seed=13)
+    with torch.no_grad():
+        planes = O.encode_inputs(oracle_sd, x)
+        c = net.encode_inputs(x.to(DEV))
+        for head, mod in (("qual", net.decoder_qual), ("rot", net.decoder_rot), ("width", net.decoder_width), ("tsdf", net.decoder_tsdf)):
+            _close(mod(p.to(DEV), c), O.local_decoder(oracle_sd, head, p, planes), name=f"decoder_{head}")
+        # foreign plane tensors (detached copies, as detach_tsdf does; NCHW-contiguous copies) are re-packed
+        c2 = {k: v.detach().clone().contiguous() for k, v in c.items()}
+        _close(net.decoder_tsdf(p.to(DEV), c2), O.local_decoder(oracle_sd, "tsdf", p, planes), name="repacked")
+
+
+def test_scene_scorer_single_process(net, oracle_sd):
+    from giga_b200 import sharding
+
+    x, p, _ = O.seeded_inputs(4, 500, seed=17)
+    v, i = sharding.sharded_best_grasp(sharding.GigaScorer(net), x.to(DEV), p.to(DEV))
+    with torch.no_grad():
+        rq = O.forward(oracle_sd, x, p)[0]
+    assert torch.equal(i.cpu().long(), rq.argmax(1))
+    _close(v, rq.max(1).values, name="best quality")

@@ -1,0 +1,242 @@
+// tcgen05 bring-up probe (not product): validates, on a real B200, the exact operand layouts,
+// descriptors and TMEM access pattern the tensor-core kernels rely on.
+//   build:  nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o build/tc_probe tools/tc_probe.cu
+//   run:    ./build/tc_probe          (prints one PASS/FAIL line per test)
+// All mbarrier waits are bounded (a wrong descriptor can never hang the GPU).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+               "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// bounded wait: returns false on timeout
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int max_iter = 2000000) {
+  uint32_t ok = 0;
+  for (int i = 0; i < max_iter && !ok; ++i) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity));
+  }
+  return ok != 0;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// smem matrix descriptor (sm_100 UMMA): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;  // SWIZZLE_NONE
+}
+// instruction descriptor kind::tf32: D=f32 (1<<4), A=tf32 (2<<7), B=tf32 (2<<10), K-major both, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Args {
+  const float* A;   // [128][K] row-major (m, k)
+  const float* Alo; // optional low parts (3xTF32) or null
+  const float* B;   // [N][K]  row-major (n, k)
+  const float* Blo;
+  float* D;         // [128][N]
+  int K, N;
+  int a_lbo_pad;    // extra bytes added to A's K-direction stride (bank-conflict padding test)
+  int swap_lbo_sbo; // 1: swap the two stride fields (to detect a wrong reading of the ISA)
+  int a_shift_rows; // rows by which the A start address is advanced (flattened-shift trick); D row m then uses A row m+shift
+  int* status;
+};
+
+// canonical no-swizzle K-major operand: element (r, k) at  (k/4)*kstride + r*16 + (k%4)*4  bytes
+__global__ void __launch_bounds__(128) probe_kernel(Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int K = a.K, N = a.N;
+  const int ROWS_A = 128 + 16;  // room for shifted starts
+  const uint32_t a_kstride = ROWS_A * 16 + a.a_lbo_pad;
+  const uint32_t b_kstride = N * 16;
+  const bool split = a.Alo != nullptr;
+  uint8_t* sA = smem;
+  uint8_t* sAlo = sA + (split ? (K / 4) * a_kstride : 0);
+  uint8_t* sB = sAlo + (K / 4) * a_kstride;
+  uint8_t* sBlo = sB + (split ? (K / 4) * b_kstride : 0);
+  for (int e = tid; e < ROWS_A * K; e += 128) {
+    const int r = e / K, k = e % K;
+    *(float*)(sA + (k / 4) * a_kstride + r * 16 + (k % 4) * 4) = a.A[r * K + k];
+    if (split) *(float*)(sAlo + (k / 4) * a_kstride + r * 16 + (k % 4) * 4) = a.Alo[r * K + k];
+  }
+  for (int e = tid; e < N * K; e += 128) {
+    const int n = e / K, k = e % K;
+    *(float*)(sB + (k / 4) * b_kstride + n * 16 + (k % 4) * 4) = a.B[n * K + k];
+    if (split) *(float*)(sBlo + (k / 4) * b_kstride + n * 16 + (k % 4) * 4) = a.Blo[n * K + k];
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) mbar_init(&bar, 1);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the async proxy (MMA)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, N);
+    const int nsplit = a.Alo ? 3 : 1;
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 8; ++ks) {
+      for (int s = 0; s < nsplit; ++s) {
+        const uint8_t* pa = (s == 1 ? sAlo : sA) + ks * 2 * a_kstride + a.a_shift_rows * 16;
+        const uint8_t* pb = (s == 2 ? sBlo : sB) + ks * 2 * b_kstride;
+        uint32_t albo = a_kstride, asbo = 128, blbo = b_kstride, bsbo = 128;
+        if (a.swap_lbo_sbo) { uint32_t t = albo; albo = asbo; asbo = t; t = blbo; blbo = bsbo; bsbo = t; }
+        mma_tf32(tmem_base, make_desc(smem_u32(pa), albo, asbo), make_desc(smem_u32(pb), blbo, bsbo), idesc, acc);
+        acc = 1;
+      }
+    }
+    mma_commit(&bar);
+  }
+  const bool ok = mbar_wait(&bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!ok) {
+    if (tid == 0) *a.status = 1;  // timeout
+  } else {
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+      for (int i = 0; i < 32; ++i) a.D[tid * N + c0 + i] = v[i];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+static float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xffffe000u; memcpy(&x, &u, 4); return x; }
+static float rna_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x1000u; u &= 0xffffe000u; memcpy(&x, &u, 4); return x; }
+
+struct Result { double max_err, max_ref; int status; };
+
+static Result run(int K, int N, const std::vector<float>& A, const std::vector<float>* Alo, const std::vector<float>& B,
+                  const std::vector<float>* Blo, int pad, int swap, int shift, const std::vector<double>& ref) {
+  float *dA, *dAlo = nullptr, *dB, *dBlo = nullptr, *dD; int* dS;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  if (Alo) { CK(cudaMalloc(&dAlo, A.size() * 4)); CK(cudaMemcpy(dAlo, Alo->data(), A.size() * 4, cudaMemcpyHostToDevice)); }
+  if (Blo) { CK(cudaMalloc(&dBlo, B.size() * 4)); CK(cudaMemcpy(dBlo, Blo->data(), B.size() * 4, cudaMemcpyHostToDevice)); }
+  CK(cudaMalloc(&dD, 128 * N * 4)); CK(cudaMemset(dD, 0xff, 128 * N * 4));
+  CK(cudaMalloc(&dS, 4)); CK(cudaMemset(dS, 0, 4));
+  Args a{dA, dAlo, dB, dBlo, dD, K, N, pad, swap, shift, dS};
+  const int smem = (Alo ? 2 : 1) * ((K / 4) * ((128 + 16) * 16 + pad) + (K / 4) * N * 16) + 1024;
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_kernel<<<1, 128, smem>>>(a);
+  cudaError_t e = cudaDeviceSynchronize();
+  Result r{0, 0, 0};
+  if (e != cudaSuccess) { printf("  kernel error: %s\n", cudaGetErrorString(e)); r.status = 2; return r; }
+  std::vector<float> D(128 * N);
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&r.status, dS, 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 128 * N; ++i) {
+    double d = fabs((double)D[i] - ref[i]);
+    if (!(d <= r.max_err)) r.max_err = d;  // NaN-propagating max
+    r.max_ref = fmax(r.max_ref, fabs(ref[i]));
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS); if (dAlo) cudaFree(dAlo); if (dBlo) cudaFree(dBlo);
+  return r;
+}
+
+int main() {
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+  printf("device %s sm_%d%d\n", p.name, p.major, p.minor);
+  const int RA = 144;
+  // ---- T1..T4: exact integer operands: any layout/descriptor mistake shows as a large error
+  for (int variant = 0; variant < 6; ++variant) {
+    int K = 32, N = 32, pad = 0, swap = 0, shift = 0;
+    const char* name = "";
+    switch (variant) {
+      case 0: name = "T1 K=32 N=32 LBO=K-dir SBO=M-dir"; break;
+      case 1: name = "T2 same, LBO/SBO swapped (expected FAIL)"; swap = 1; break;
+      case 2: name = "T3 K=96 N=160 (fc_c shape)"; K = 96; N = 160; break;
+      case 3: name = "T4 K=32 N=32, A k-stride padded +16 B"; pad = 16; break;
+      case 4: name = "T5 K=32 N=64, A start shifted by 3 rows"; N = 64; shift = 3; break;
+      case 5: name = "T6 K=64 N=128, shift 11, pad 16"; K = 64; N = 128; shift = 11; pad = 16; break;
+    }
+    std::vector<float> A(RA * K), B(N * K);
+    for (int m = 0; m < RA; ++m) for (int k = 0; k < K; ++k) A[m * K + k] = (float)((m * 7 + k * 3) % 13 - 6);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) B[n * K + k] = (float)((n * 5 + k * 2) % 11 - 5);
+    std::vector<double> ref(128 * N);
+    for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) {
+      double s = 0; for (int k = 0; k < K; ++k) s += (double)A[(m + shift) * K + k] * B[n * K + k];
+      ref[m * N + n] = s;
+    }
+    Result r = run(K, N, A, nullptr, B, nullptr, pad, swap, shift, ref);
+    printf("%-48s status=%d max_err=%.3e (max|ref| %.1f) -> %s\n", name, r.status, r.max_err, r.max_ref,
+           (r.status == 0 && r.max_err == 0.0) ? "PASS" : "FAIL");
+  }
+  // ---- T7: how does the MMA convert fp32 operand bits to tf32: truncate or round-to-nearest?
+  {
+    const int K = 8, N = 8;
+    std::vector<float> A(RA * K, 0.f), B(N * K, 0.f);
+    const float x = 1.0f + 3.0f * ldexpf(1.f, -12);  // needs rounding decision at the tf32 boundary (bit 13)
+    for (int m = 0; m < RA; ++m) A[m * K] = x;
+    for (int n = 0; n < N; ++n) B[n * K] = 1.0f;
+    std::vector<double> ref_t(128 * N, (double)trunc_tf32(x)), ref_r(128 * N, (double)rna_tf32(x));
+    Result rt = run(K, N, A, nullptr, B, nullptr, 0, 0, 0, ref_t);
+    Result rr = run(K, N, A, nullptr, B, nullptr, 0, 0, 0, ref_r);
+    printf("T7 fp32->tf32 operand conversion: err vs truncation %.3e, vs round-nearest %.3e -> %s\n", rt.max_err, rr.max_err,
+           rt.max_err == 0 ? "TRUNCATES" : (rr.max_err == 0 ? "ROUNDS" : "UNKNOWN"));
+  }
+  // ---- T8/T9: accuracy of 1xTF32 vs 3xTF32 (hi/lo split) on random fp32 data, K=96 N=64
+  {
+    const int K = 96, N = 64;
+    std::vector<float> A(RA * K), B(N * K), Ahi(RA * K), Alo(RA * K), Bhi(N * K), Blo(N * K);
+    srand(1);
+    auto rnd = []() { return (float)((rand() / (double)RAND_MAX) * 2.0 - 1.0); };
+    for (auto& v : A) v = rnd() * 4.f;
+    for (auto& v : B) v = rnd() * 0.3f;
+    for (size_t i = 0; i < A.size(); ++i) { Ahi[i] = trunc_tf32(A[i]); Alo[i] = A[i] - Ahi[i]; }
+    for (size_t i = 0; i < B.size(); ++i) { Bhi[i] = trunc_tf32(B[i]); Blo[i] = B[i] - Bhi[i]; }
+    std::vector<double> ref(128 * N);
+    for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) {
+      double s = 0; for (int k = 0; k < K; ++k) s += (double)A[m * K + k] * B[n * K + k];
+      ref[m * N + n] = s;
+    }
+    Result r1 = run(K, N, A, nullptr, B, nullptr, 0, 0, 0, ref);
+    Result r3 = run(K, N, Ahi, &Alo, Bhi, &Blo, 0, 0, 0, ref);
+    printf("T8 1xTF32 random K=96: max_err=%.3e (max|ref| %.2f)\n", r1.max_err, r1.max_ref);
+    printf("T9 3xTF32 random K=96: max_err=%.3e (max|ref| %.2f) -> %s\n", r3.max_err, r3.max_ref, r3.max_err < 2e-5 ? "PASS" : "FAIL");
+  }
+  return 0;
+}
