@@ -187,7 +187,7 @@ int main() {
     const char* name = "";
     switch (variant) {
       case 0: name = "T1 K=32 N=32 LBO=K-dir SBO=M-dir"; break;
-      case 1: name = "T2 same, LBO/SBO swapped (expected FAIL)"; swap = 1; break;
+      case 1: continue;  // (LBO/SBO swapped faults with an illegal smem access on hardware -- confirmed, removed)
       case 2: name = "T3 K=96 N=160 (fc_c shape)"; K = 96; N = 160; break;
       case 3: name = "T4 K=32 N=32, A k-stride padded +16 B"; pad = 16; break;
       case 4: name = "T5 K=32 N=64, A start shifted by 3 rows"; N = 64; shift = 3; break;
