@@ -1,0 +1,284 @@
+// Tensor-core implicit decoder (tcgen05 / TMEM, 3xTF32 operand splitting -> fp32-level accuracy).
+//
+// Same function as decode_points_kernel (decoder.cuh) -- tri-plane gather + LocalDecoder heads
+// (conv_onet/models/decoder.py:117-176, layers.py:39-47, models/__init__.py:119-123) -- but every
+// dense contraction runs on the 5th-gen tensor cores:
+//   fc_c  : [128 pts x 96 feat] . [96 x 160]   (all five blocks' fc_c at once, one plane (K=32) at a time)
+//   fc_0/1: [128 pts x 32]      . [32 x 32]    x 10 per head (the ResnetBlockFC chain)
+// A CTA owns 128 query points of one scene; thread t <-> point t <-> TMEM lane t.
+//   * gather: warp-cooperative (lane = channel, 12 coalesced 128 B texel reads per point); the
+//     96 features of the warp's 32 points stay in REGISTERS (F[3][32] per lane) and are re-split
+//     into the shared-memory A operand (hi/lo tf32 pair) for every head -- gathered once per tile;
+//   * MMAs are issued by thread 0; accumulators live in TMEM: columns [0,160) = fc_c outputs of the
+//     five blocks, [160,192) = the current 32x32 layer;
+//   * epilogues (bias, residual, ReLU, hi/lo split, write next A operand) run thread-per-point
+//     straight out of TMEM (tcgen05.ld 32x32b.x32), fc_p (K=3) and fc_out (N<=4) stay on CUDA cores;
+//   * 3xTF32: x*y ~= xh*yh + xl*yh + xh*yl with xh = rn_tf32(x), xl = x - xh (exact); measured
+//     error vs fp64 ~1e-6 relative (profiles/r01_tc_probe.txt), i.e. fp32-class.
+#pragma once
+#include "common.cuh"
+#include "decoder.cuh"
+#include "tc.cuh"
+
+namespace giga {
+
+// ---- packed per-head parameter blob for the tensor-core path (floats) ----
+constexpr int TW_FCP = 0;                         // Wt[3][32] + b[32]                      (128)
+constexpr int TW_FCC = 128;                       // [plane 3][hi,lo][ (k/4)*640 + n*4 + k%4 ], n = blk*32+j  (3*2*5120)
+constexpr int TW_FCC_SLICE = 5120;                //   one (plane, hi|lo) operand: N=160 x K=32
+constexpr int TW_BC = TW_FCC + 6 * TW_FCC_SLICE;  // 30848: fc_c biases [5][32]
+constexpr int TW_BLK = TW_BC + 160;               // 31008: per block W0hi W0lo W1hi W1lo (1024 each, (k/4)*128 + n*4 + k%4), b0[32], b1[32]
+constexpr int TW_BLK_SIZE = 4 * 1024 + 64;        // 4160
+constexpr int TW_OUT = TW_BLK + 5 * TW_BLK_SIZE;  // 51808: Wt[32][4] + b[4]
+constexpr int TW_HEAD = TW_OUT + 132;             // 51940 floats per head
+
+constexpr int TD_PTS = 128;
+constexpr int TD_KS_A = TD_PTS * 16 + 16;         // A k-chunk stride (bytes), +16 keeps the gather stores conflict free
+constexpr int TD_A_BYTES = 8 * TD_KS_A;           // one A operand (K=32): 16512 B
+constexpr int TD_W_BYTES = 2 * TW_FCC_SLICE * 4;  // staged weights: fc_c plane slice hi+lo = 40960 B (chain stage uses 16.9 KB of it)
+constexpr int TD_OFF_ALO = TD_A_BYTES;
+constexpr int TD_OFF_W = 2 * TD_A_BYTES;          // 33024
+constexpr int TD_OFF_TINFO = TD_OFF_W + TD_W_BYTES;          // 73984
+constexpr int TD_OFF_BAR = TD_OFF_TINFO + TD_PTS * 24 * 4;   // 86272
+constexpr int TD_SMEM_BYTES = TD_OFF_BAR + 16;               // 86288
+constexpr int TD_TMEM_COLS = 256;
+constexpr uint32_t TD_KS_WC = 160 * 16;           // fc_c B operand k-chunk stride (N=160)
+constexpr uint32_t TD_KS_W = 32 * 16;             // 32x32 B operand k-chunk stride
+
+__device__ __forceinline__ float tf32_rn(float v) {  // round-to-nearest tf32 (top 19 bits)
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+
+// issue the K=32 contraction  D[128 x N] (+)= (Ahi+Alo)[128x32] . (Bhi+Blo)[N x 32]^T  as 4 k-steps x 3 MMAs
+__device__ __forceinline__ void issue_k32_x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                             uint32_t b_kstride, uint32_t idesc, bool accumulate_first) {
+  uint32_t acc = accumulate_first ? 1u : 0u;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t ah = tc::make_desc(a_hi + ks * 2 * TD_KS_A, TD_KS_A, 128);
+    const uint64_t al = tc::make_desc(a_lo + ks * 2 * TD_KS_A, TD_KS_A, 128);
+    const uint64_t bh = tc::make_desc(b_hi + ks * 2 * b_kstride, b_kstride, 128);
+    const uint64_t bl = tc::make_desc(b_lo + ks * 2 * b_kstride, b_kstride, 128);
+    tc::mma_tf32(d_tmem, ah, bh, idesc, acc);
+    tc::mma_tf32(d_tmem, al, bh, idesc, 1u);
+    tc::mma_tf32(d_tmem, ah, bl, idesc, 1u);
+    acc = 1u;
+  }
+}
+
+// thread t writes row t of the A operand (hi and lo) from 32 fp32 values
+__device__ __forceinline__ void store_a_row(uint8_t* a_hi, uint8_t* a_lo, int row, const float* v) {
+#pragma unroll
+  for (int kc = 0; kc < 8; ++kc) {
+    float4 h, l;
+    h.x = tf32_rn(v[4 * kc + 0]); l.x = v[4 * kc + 0] - h.x;
+    h.y = tf32_rn(v[4 * kc + 1]); l.y = v[4 * kc + 1] - h.y;
+    h.z = tf32_rn(v[4 * kc + 2]); l.z = v[4 * kc + 2] - h.z;
+    h.w = tf32_rn(v[4 * kc + 3]); l.w = v[4 * kc + 3] - h.w;
+    *reinterpret_cast<float4*>(a_hi + kc * TD_KS_A + row * 16) = h;
+    *reinterpret_cast<float4*>(a_lo + kc * TD_KS_A + row * 16) = l;
+  }
+}
+
+// grid (ceil(N/128), B), block 128, dynamic smem TD_SMEM_BYTES, 2 CTAs/SM (2 x 256 TMEM columns)
+__global__ void __launch_bounds__(TD_PTS, 2)
+decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
+                        const float* __restrict__ pts,     // [B][N][3]
+                        const float* __restrict__ tw,      // [4][TW_HEAD]
+                        int B, int N, unsigned heads,
+                        float* __restrict__ qual, float* __restrict__ rot, float* __restrict__ width,
+                        float* __restrict__ occ) {
+  extern __shared__ __align__(128) uint8_t smem_tc[];
+  uint8_t* smem = smem_tc;
+  uint8_t* sAhi = smem;
+  uint8_t* sAlo = smem + TD_OFF_ALO;
+  uint8_t* sW = smem + TD_OFF_W;
+  float* tinfo = reinterpret_cast<float*>(smem + TD_OFF_TINFO);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TD_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TD_OFF_BAR + 8);
+
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * TD_PTS;
+  const int n = n0 + tid;
+  const bool valid = n < N;
+  const int nc = valid ? n : N - 1;
+
+  if (warp == 0) tc::tmem_alloc(tmem_slot, TD_TMEM_COLS);
+  if (tid == 0) tc::mbar_init(bar, 1);
+
+  // ---- gather: the warp's 32 points, lane = channel; features stay in registers ----
+  float F[3][32];
+  {
+    float* tw_ = tinfo + warp * 32 * 24;
+    {
+      const int nq = min(n0 + warp * 32 + lane, N - 1);
+      TexInfo t;
+      point_taps(pts + ((size_t)b * N + nq) * 3, t);
+      int* ti = reinterpret_cast<int*>(tw_) + lane * 24;
+      float* tf = tw_ + lane * 24 + 12;
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ti[pl * 4 + q] = t.off[pl][q];
+          tf[pl * 4 + q] = t.w[pl][q];
+        }
+    }
+    __syncwarp();
+    const float* pb[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) pb[pl] = planes + ((size_t)pl * B + b) * (G2 * C) + lane;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int4* oi = reinterpret_cast<const int4*>(tw_ + q * 24);
+      const float4* wf = reinterpret_cast<const float4*>(tw_ + q * 24 + 12);
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        const int4 o = oi[pl];
+        const float4 w = wf[pl];
+        const float v0 = __ldg(pb[pl] + o.x), v1 = __ldg(pb[pl] + o.y), v2 = __ldg(pb[pl] + o.z), v3 = __ldg(pb[pl] + o.w);
+        F[pl][q] = v0 * w.x + v1 * w.y + v2 * w.z + v3 * w.w;
+      }
+    }
+  }
+
+  const float* pp = pts + ((size_t)b * N + nc) * 3;
+  const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+
+  tc::fence_before_sync();
+  __syncthreads();   // TMEM address + mbarrier init visible
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t a_hi = tc::smem_u32(sAhi), a_lo = tc::smem_u32(sAlo), w_s = tc::smem_u32(sW);
+  constexpr uint32_t IDESC_160 = tc::make_idesc_tf32(128, 160);
+  constexpr uint32_t IDESC_32 = tc::make_idesc_tf32(128, 32);
+  uint32_t phase = 0;
+
+#pragma unroll 1
+  for (int head = 0; head < 4; ++head) {
+    if (!(heads & (1u << head))) continue;
+    const float* W = tw + (size_t)head * TW_HEAD;
+
+    // ---- fc_c for all five blocks: C[128 x 160] = F[128 x 96] . Wc^T, one plane (K = 32) per round ----
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      // stage the (head, plane) weight slice hi|lo, already in operand layout
+      const float4* src = reinterpret_cast<const float4*>(W + TW_FCC + pl * 2 * TW_FCC_SLICE);
+      float4* dst = reinterpret_cast<float4*>(sW);
+#pragma unroll 4
+      for (int e = tid; e < 2 * TW_FCC_SLICE / 4; e += TD_PTS) dst[e] = __ldg(src + e);
+      // A operand from the register-resident features: element (row = warp*32+q, k = lane)
+      uint8_t* ah = sAhi + (lane >> 2) * TD_KS_A + (lane & 3) * 4 + (warp * 32) * 16;
+      uint8_t* al = sAlo + (lane >> 2) * TD_KS_A + (lane & 3) * 4 + (warp * 32) * 16;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float v = F[pl][q];
+        const float h = tf32_rn(v);
+        *reinterpret_cast<float*>(ah + q * 16) = h;
+        *reinterpret_cast<float*>(al + q * 16) = v - h;
+      }
+      tc::fence_smem_to_async();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        issue_k32_x3(tmem, a_hi, a_lo, w_s, w_s + TW_FCC_SLICE * 4, TD_KS_WC, IDESC_160, pl > 0);
+        tc::mma_commit(bar);
+      }
+      tc::mbar_wait(bar, phase);   // MMAs done: A / W buffers reusable, C columns readable
+      phase ^= 1u;
+      tc::fence_after_sync();
+    }
+
+    // ---- fc_p on CUDA cores ----
+    float h[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      h[j] = __ldg(W + TW_FCP + 96 + j) + __ldg(W + TW_FCP + j) * px + __ldg(W + TW_FCP + 32 + j) * py +
+             __ldg(W + TW_FCP + 64 + j) * pz;
+
+#pragma unroll 1
+    for (int blk = 0; blk < 5; ++blk) {
+      // stage W0hi W0lo W1hi W1lo b0 b1 (4160 floats); the previous MMAs reading sW have completed
+      {
+        const float4* src = reinterpret_cast<const float4*>(W + TW_BLK + blk * TW_BLK_SIZE);
+        float4* dst = reinterpret_cast<float4*>(sW);
+        for (int e = tid; e < TW_BLK_SIZE / 4; e += TD_PTS) dst[e] = __ldg(src + e);
+      }
+      float v[32];
+      tc::tmem_ld32(tmem_row + blk * 32, v);           // fc_c[blk] output for this point
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        h[j] += v[j] + __ldg(W + TW_BC + blk * 32 + j);  // net = net + fc_c[blk](c)
+        v[j] = fmaxf(h[j], 0.f);
+      }
+      store_a_row(sAhi, sAlo, tid, v);
+      tc::fence_smem_to_async();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        issue_k32_x3(tmem + 160, a_hi, a_lo, w_s, w_s + 4096, TD_KS_W, IDESC_32, false);   // fc_0
+        tc::mma_commit(bar);
+      }
+      tc::mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc::fence_after_sync();
+      const float* bs = reinterpret_cast<const float*>(sW) + 4096;   // b0[32], b1[32]
+      tc::tmem_ld32(tmem_row + 160, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bs[j], 0.f);
+      store_a_row(sAhi, sAlo, tid, v);
+      tc::fence_smem_to_async();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        issue_k32_x3(tmem + 160, a_hi, a_lo, w_s + 8192, w_s + 12288, TD_KS_W, IDESC_32, false);   // fc_1
+        tc::mma_commit(bar);
+      }
+      tc::mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc::fence_after_sync();
+      tc::tmem_ld32(tmem_row + 160, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] += v[j] + bs[32 + j];     // x + fc_1(relu(fc_0(relu(x))))
+      tc::fence_before_sync();
+      __syncthreads();   // everyone has read b0/b1 and T before sW / T are overwritten by the next round
+    }
+
+    // ---- fc_out(relu(net)) + head epilogue on CUDA cores ----
+    float o[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) o[m] = __ldg(W + TW_OUT + 128 + m);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float r = fmaxf(h[k], 0.f);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(W + TW_OUT + k * 4));
+      o[0] = fmaf(w.x, r, o[0]); o[1] = fmaf(w.y, r, o[1]);
+      o[2] = fmaf(w.z, r, o[2]); o[3] = fmaf(w.w, r, o[3]);
+    }
+    if (valid) {
+      const size_t idx = (size_t)b * N + n;
+      const bool raw = (heads & 16u) != 0;
+      if (head == 0) {
+        qual[idx] = raw ? o[0] : 1.f / (1.f + expf(-o[0]));
+      } else if (head == 1) {
+        const float nrm = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
+        const float d = raw ? 1.f : fmaxf(nrm, 1e-12f);
+        st4(rot + idx * 4, make_float4(o[0] / d, o[1] / d, o[2] / d, o[3] / d));
+      } else if (head == 2) {
+        width[idx] = o[0];
+      } else {
+        occ[idx] = o[0];
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, TD_TMEM_COLS);
+}
+
+}  // namespace giga

@@ -3,6 +3,7 @@
 #include "../../include/giga_b200.h"
 
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <map>
 #include <string>
@@ -11,6 +12,7 @@
 #include "common.cuh"
 #include "conv_in.cuh"
 #include "decoder.cuh"
+#include "decoder_tc.cuh"
 #include "unet.cuh"
 
 using namespace giga;
@@ -95,7 +97,9 @@ struct giga_ctx {
   ConvInParams conv_in;
   EncLayout el;
   float* d_enc = nullptr;    // packed encoder blob
-  float* d_heads = nullptr;  // [4][DW_HEAD]
+  float* d_heads = nullptr;  // [4][DW_HEAD]   fp32 FMA-pipe decoder
+  float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo tf32 splits)
+  int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   // workspaces (sized for cap_B scenes)
   int cap_B = 0;
   int last_B = 0;
@@ -150,6 +154,7 @@ int ensure_attrs(giga_ctx* ctx) {
   if (ctx->attrs_set) return GIGA_OK;
   CU_TRY(cudaFuncSetAttribute(conv_in_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CI_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(decode_points_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(sample_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
 #define SET_CONV(K) CU_TRY(cudaFuncSetAttribute(conv3x3_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES))
   SET_CONV(K_d0c1); SET_CONV(K_d0c2); SET_CONV(K_d1c1); SET_CONV(K_d1c2); SET_CONV(K_d2c1);
@@ -200,6 +205,14 @@ void launch_convT(giga_ctx* ctx, const char* name, int n_img, const float* src, 
                                                                ctx->d_enc + ctx->el.up_b[up], out);
 }
 
+float tf32_rn_host(float v) {  // same rounding as decoder_tc.cuh::tf32_rn
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&v, &u, 4);
+  return v;
+}
+
 bool get(const giga_ctx* ctx, const std::string& name, long numel, const float** out) {
   auto it = ctx->raw.find(name);
   if (it == ctx->raw.end() || (long)it->second.size() != numel) return false;
@@ -238,7 +251,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_pre, ctx->d_xzpart, ctx->h_tsdf, ctx->h_planes, ctx->h_p,
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->h_tsdf, ctx->h_planes, ctx->h_p,
                    ctx->h_pt,  ctx->h_qual,  ctx->h_rot, ctx->h_width,  ctx->h_occ};
   for (float* p : ptrs)
     if (p) cudaFree(p);
@@ -307,6 +320,7 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
   }
   // ---- decoder heads ----
   std::vector<float> hb((size_t)4 * DW_HEAD, 0.f);
+  std::vector<float> tb((size_t)4 * TW_HEAD, 0.f);
   unsigned heads = 0;
   for (int h = 0; h < 4; ++h) {
     const std::string pre = std::string("decoder_") + kHeadName[h] + ".";
@@ -345,8 +359,43 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       for (int k = 0; k < 32; ++k) H[DW_OUT + k * 4 + m] = w[m * 32 + k];
       H[DW_OUT + 128 + m] = b[m];
     }
+    // tensor-core blob: the same parameters pre-split into tf32 hi/lo pairs in UMMA operand layout
+    float* T = tb.data() + (size_t)h * TW_HEAD;
+    memcpy(T + TW_FCP, H + DW_FCP, sizeof(float) * 128);
+    for (int i = 0; i < 5; ++i) {
+      const std::string si = std::to_string(i);
+      need("fc_c." + si + ".weight", 32 * 96, &w);
+      need("fc_c." + si + ".bias", 32, &b);
+      for (int j = 0; j < 32; ++j) {
+        for (int k96 = 0; k96 < 96; ++k96) {
+          const int pl = k96 / 32, k = k96 % 32, n = i * 32 + j;
+          const float v = w[j * 96 + k96], hi = tf32_rn_host(v);
+          float* S = T + TW_FCC + pl * 2 * TW_FCC_SLICE;
+          S[(k / 4) * 640 + n * 4 + (k % 4)] = hi;
+          S[TW_FCC_SLICE + (k / 4) * 640 + n * 4 + (k % 4)] = v - hi;
+        }
+        T[TW_BC + i * 32 + j] = b[j];
+      }
+      float* Bk = T + TW_BLK + i * TW_BLK_SIZE;
+      for (int f = 0; f < 2; ++f) {
+        const std::string fn = "blocks." + si + ".fc_" + std::to_string(f);
+        need(fn + ".weight", 32 * 32, &w);
+        need(fn + ".bias", 32, &b);
+        for (int j = 0; j < 32; ++j) {
+          for (int k = 0; k < 32; ++k) {
+            const float v = w[j * 32 + k], hi = tf32_rn_host(v);
+            Bk[f * 2048 + (k / 4) * 128 + j * 4 + (k % 4)] = hi;
+            Bk[f * 2048 + 1024 + (k / 4) * 128 + j * 4 + (k % 4)] = v - hi;
+          }
+          Bk[4096 + f * 32 + j] = b[j];
+        }
+      }
+    }
+    memcpy(T + TW_OUT, H + DW_OUT, sizeof(float) * 132);
     heads |= 1u << h;
   }
+  if (!ctx->d_heads_tc) CU_TRY(cudaMalloc(&ctx->d_heads_tc, sizeof(float) * 4 * TW_HEAD));
+  CU_TRY(cudaMemcpy(ctx->d_heads_tc, tb.data(), sizeof(float) * 4 * TW_HEAD, cudaMemcpyHostToDevice));
   if (!ctx->d_heads) CU_TRY(cudaMalloc(&ctx->d_heads, sizeof(float) * 4 * DW_HEAD));
   CU_TRY(cudaMemcpy(ctx->d_heads, hb.data(), sizeof(float) * 4 * DW_HEAD, cudaMemcpyHostToDevice));
   ctx->heads = heads;
@@ -411,8 +460,12 @@ int giga_decode(giga_ctx* ctx, const float* planes, int B, const float* points, 
   cudaStream_t st = (cudaStream_t)stream;
   {
     LaunchScope ls(ctx, (heads & 15u) == GIGA_HEAD_TSDF ? "decode_points:tsdf" : "decode_points:grasp", st);
-    decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N,
-                                                                                         heads, qual, rot, width, occ);
+    if (ctx->decoder_impl == 1)
+      decode_points_tc_kernel<<<dim3(ceil_div(N, TD_PTS), B), TD_PTS, TD_SMEM_BYTES, st>>>(planes, points, ctx->d_heads_tc, B,
+                                                                                           N, heads, qual, rot, width, occ);
+    else
+      decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N,
+                                                                                           heads, qual, rot, width, occ);
   }
   CU_TRY(cudaGetLastError());
   return GIGA_OK;
@@ -488,6 +541,16 @@ int giga_forward_host(giga_ctx* ctx, const float* tsdf, int B, const float* p, i
 }
 
 long giga_ctx_launch_count(const giga_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
+  if (!ctx || !key) return fail(GIGA_EINVAL, "giga_ctx_set_option: bad argument");
+  if (!strcmp(key, "decoder_impl")) {
+    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "decoder_impl must be 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
+    ctx->decoder_impl = value;
+    return GIGA_OK;
+  }
+  return fail(GIGA_EINVAL, std::string("giga_ctx_set_option: unknown key '") + key + "'");
+}
 
 int giga_ctx_set_timing(giga_ctx* ctx, int enabled) {
   if (!ctx) return fail(GIGA_EINVAL, "giga_ctx_set_timing: ctx is null");

@@ -172,6 +172,9 @@ class _Engine:
     def launches(self) -> int:
         return int(lib.giga_ctx_launch_count(self.h))
 
+    def set_option(self, key: str, value: int):
+        check(lib.giga_ctx_set_option(self.h, key.encode(), int(value)), f"giga_ctx_set_option({key})")
+
     def set_timing(self, on: bool):
         check(lib.giga_ctx_set_timing(self.h, int(on)), "giga_ctx_set_timing")
 

@@ -44,9 +44,12 @@ def main(B=2, N=300):
         planes_ref = {k: ref_planes[i] for i, k in enumerate(O.PLANES)}
         cmp("feat96", net.sample_feature(p.to(dev), c, "concat"), O.sample_concat_feature(p, planes_ref))
         cmp("qfeat32", net.query_feature(p.to(dev), c), O.query_feature(p, planes_ref))
-        qual, rot, width, occ = net(x.to(dev), p.to(dev), p_tsdf=pt.to(dev))
         rq, rr, rw, ro = O.forward(sd, x, p, pt)
-        cmp("qual", qual, rq); cmp("rot", rot, rr); cmp("width", width, rw); cmp("occ", occ, ro)
+        for impl, tag in ((0, "ffma"), (1, "tc")):
+            net._engine().set_option("decoder_impl", impl)
+            qual, rot, width, occ = net(x.to(dev), p.to(dev), p_tsdf=pt.to(dev))
+            torch.cuda.synchronize()
+            cmp(tag + ".qual", qual, rq); cmp(tag + ".rot", rot, rr); cmp(tag + ".width", width, rw); cmp(tag + ".occ", occ, ro)
         hq = net.forward_host(x.pin_memory(), p.pin_memory(), pt.pin_memory())
         cmp("host.qual", hq[0], rq); cmp("host.rot", hq[1], rr); cmp("host.width", hq[2], rw); cmp("host.occ", hq[3], ro)
         bv, bi = net.scene_argmax(qual)

@@ -245,3 +245,19 @@ def test_scene_scorer_single_process(net, oracle_sd):
         rq = O.forward(oracle_sd, x, p)[0]
     assert torch.equal(i.cpu().long(), rq.argmax(1))
     _close(v, rq.max(1).values, name="best quality")
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_decoder_implementations(oracle_sd, impl):
+    """decoder_impl 0 = fp32 FMA pipe, 1 = tcgen05 3xTF32 (default): both within 1e-4 of the oracle,
+    arg-max exact, on ragged N and with clamp edge points."""
+    net = make_net("giga", oracle_sd)
+    net._engine().set_option("decoder_impl", impl)
+    for B, N, seed in ((1, 1, 1), (2, 333, 2), (3, 2048, 3)):
+        x, p, pt = O.seeded_inputs(B, N, seed=30 + seed)
+        with torch.no_grad():
+            ref = O.forward(oracle_sd, x, p, pt)
+            out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+        for nme, a, b in zip(("qual", "rot", "width", "occ"), out, ref):
+            _close(a, b, name=f"impl{impl}.{nme}")
+        assert torch.equal(out[0].argmax(1).cpu(), ref[0].argmax(1))
