@@ -9,8 +9,8 @@
 //   * gather: warp-cooperative (lane = channel, 12 coalesced 128 B texel reads per point); the
 //     96 features of the warp's 32 points stay in REGISTERS (F[3][32] per lane) and are re-split
 //     into the shared-memory A operand (hi/lo tf32 pair) for every head -- gathered once per tile;
-//   * MMAs are issued by thread 0; accumulators live in TMEM: columns [0,160) = fc_c outputs of the
-//     five blocks, [160,192) = the current 32x32 layer;
+//   * MMAs are issued by one elected lane of warp 0; accumulators live in TMEM: columns [0,160) = fc_c outputs of the
+//     five blocks, [160,256) = three partial accumulators (hi*hi, lo*hi, hi*lo) of the current 32x32 layer;
 //   * epilogues (bias, residual, ReLU, hi/lo split, write next A operand) run thread-per-point
 //     straight out of TMEM (tcgen05.ld 32x32b.x32), fc_p (K=3) and fc_out (N<=4) stay on CUDA cores;
 //   * 3xTF32: x*y ~= xh*yh + xl*yh + xh*yl with xh = rn_tf32(x), xl = x - xh (exact); measured
@@ -47,6 +47,34 @@ constexpr uint32_t TD_KS_W = 32 * 16;             // 32x32 B operand k-chunk str
 
 __device__ __forceinline__ float tf32_rn(float v) {  // round-to-nearest tf32 (top 19 bits)
   return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+
+// 32x32 layer: the three 3xTF32 products go to three INDEPENDENT accumulators (d, d+32, d+64) so that only
+// 4 dependent MMAs (the k-steps) chain on each -- dependent MMAs into one TMEM tile cost ~100 cycles each.
+__device__ __forceinline__ void issue_k32_split3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                 uint32_t b_kstride, uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t ah = tc::make_desc(a_hi + ks * 2 * TD_KS_A, TD_KS_A, 128);
+    const uint64_t al = tc::make_desc(a_lo + ks * 2 * TD_KS_A, TD_KS_A, 128);
+    const uint64_t bh = tc::make_desc(b_hi + ks * 2 * b_kstride, b_kstride, 128);
+    const uint64_t bl = tc::make_desc(b_lo + ks * 2 * b_kstride, b_kstride, 128);
+    tc::mma_tf32(d_tmem, ah, bh, idesc, ks > 0 ? 1u : 0u);
+    tc::mma_tf32(d_tmem + 32, al, bh, idesc, ks > 0 ? 1u : 0u);
+    tc::mma_tf32(d_tmem + 64, ah, bl, idesc, ks > 0 ? 1u : 0u);
+  }
+}
+
+// sum of the three partial accumulators of a 32x32 layer for this thread's row
+__device__ __forceinline__ void tmem_ld32_sum3(uint32_t taddr, float* v) {
+  float a[32];
+  tc::tmem_ld32(taddr, v);
+  tc::tmem_ld32(taddr + 32, a);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] += a[j];
+  tc::tmem_ld32(taddr + 64, a);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] += a[j];
 }
 
 // issue the K=32 contraction  D[128 x N] (+)= (Ahi+Alo)[128x32] . (Bhi+Blo)[N x 32]^T  as 4 k-steps x 3 MMAs
@@ -181,10 +209,13 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       tc::fence_smem_to_async();
       tc::fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc::fence_after_sync();
-        issue_k32_x3(tmem, a_hi, a_lo, w_s, w_s + TW_FCC_SLICE * 4, TD_KS_WC, IDESC_160, pl > 0);
-        tc::mma_commit(bar);
+        if (tc::elect_one()) {
+          issue_k32_x3(tmem, a_hi, a_lo, w_s, w_s + TW_FCC_SLICE * 4, TD_KS_WC, IDESC_160, pl > 0);
+          tc::mma_commit(bar);
+        }
+        __syncwarp();
       }
       tc::mbar_wait(bar, phase);   // MMAs done: A / W buffers reusable, C columns readable
       phase ^= 1u;
@@ -217,31 +248,37 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       tc::fence_smem_to_async();
       tc::fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc::fence_after_sync();
-        issue_k32_x3(tmem + 160, a_hi, a_lo, w_s, w_s + 4096, TD_KS_W, IDESC_32, false);   // fc_0
-        tc::mma_commit(bar);
+        if (tc::elect_one()) {
+          issue_k32_split3(tmem + 160, a_hi, a_lo, w_s, w_s + 4096, TD_KS_W, IDESC_32);   // fc_0
+          tc::mma_commit(bar);
+        }
+        __syncwarp();
       }
       tc::mbar_wait(bar, phase);
       phase ^= 1u;
       tc::fence_after_sync();
       const float* bs = reinterpret_cast<const float*>(sW) + 4096;   // b0[32], b1[32]
-      tc::tmem_ld32(tmem_row + 160, v);
+      tmem_ld32_sum3(tmem_row + 160, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bs[j], 0.f);
       store_a_row(sAhi, sAlo, tid, v);
       tc::fence_smem_to_async();
       tc::fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc::fence_after_sync();
-        issue_k32_x3(tmem + 160, a_hi, a_lo, w_s + 8192, w_s + 12288, TD_KS_W, IDESC_32, false);   // fc_1
-        tc::mma_commit(bar);
+        if (tc::elect_one()) {
+          issue_k32_split3(tmem + 160, a_hi, a_lo, w_s + 8192, w_s + 12288, TD_KS_W, IDESC_32);   // fc_1
+          tc::mma_commit(bar);
+        }
+        __syncwarp();
       }
       tc::mbar_wait(bar, phase);
       phase ^= 1u;
       tc::fence_after_sync();
-      tc::tmem_ld32(tmem_row + 160, v);
+      tmem_ld32_sum3(tmem_row + 160, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) h[j] += v[j] + bs[32 + j];     // x + fc_1(relu(fc_0(relu(x))))
       tc::fence_before_sync();

@@ -3,6 +3,7 @@
 #include "../../include/giga_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -14,6 +15,7 @@
 #include "decoder.cuh"
 #include "decoder_tc.cuh"
 #include "unet.cuh"
+#include "unet_tall.cuh"
 
 using namespace giga;
 
@@ -47,6 +49,18 @@ using K_u1c2 = Conv3x3Cfg<40, 32, 0, 32, 4, 32, 4, 16, false>;
 using K_u0up = ConvTCfg<10, 128, 64, 10, 16, 32>;
 using K_u1up = ConvTCfg<20, 64, 32, 4, 32, 32>;
 
+// tensor-core U-Net on TALL pre-split activations (HW, CIN0, CIN1, COUT, NTILE, NT, MODE, FUSE_FINAL)
+using T_c40 = TallCfg<40, 32, 0, 32, 32, 2, 0, false>;      // d0c1, d0c2
+using T_d1c1 = TallCfg<20, 32, 0, 64, 64, 1, 0, false>;
+using T_c20 = TallCfg<20, 64, 0, 64, 64, 1, 0, false>;      // d1c2, u0c2
+using T_d2c1 = TallCfg<10, 64, 0, 128, 64, 1, 0, false>;
+using T_d2c2 = TallCfg<10, 128, 0, 128, 64, 1, 0, false>;
+using T_u0up = TallCfg<10, 128, 0, 64, 64, 1, 1, false>;
+using T_u0c1 = TallCfg<20, 64, 64, 64, 64, 1, 0, false>;
+using T_u1up = TallCfg<20, 64, 0, 32, 32, 2, 1, false>;
+using T_u1c1 = TallCfg<40, 32, 32, 32, 32, 2, 0, false>;
+using T_u1c2 = TallCfg<40, 32, 0, 32, 32, 2, 0, true>;
+
 struct ParamSpec {
   const char* name;
   long numel;
@@ -58,6 +72,9 @@ struct EncLayout {
   long bias[10];
   long up_w[2], up_b[2];
   long fin_w, fin_b;
+  long tc_conv[10];  // tensor-core operand-layout weights (hi/lo tf32 splits) per conv layer
+  long tc_up[2];     // transpose convs, [ab][chunk][hi|lo][kc][co][4]
+  long tc_fin;       // conv_final as a 32x32 B operand [hi,lo][kc 8][n 32][4]
   long total;
 };
 const int kConvCin[10] = {32, 32, 32, 64, 64, 128, 128, 64, 64, 32};
@@ -75,6 +92,9 @@ EncLayout make_enc_layout() {
   for (int i = 0; i < 2; ++i) { L.up_w[i] = o; o += (long)kUpCin[i] * kUpCout[i] * 4; L.up_b[i] = o; o += kUpCout[i]; }
   L.fin_w = o; o += 32 * 32;
   L.fin_b = o; o += 32;
+  for (int i = 0; i < 10; ++i) { L.tc_conv[i] = o; o += (long)kConvCin[i] * kConvCout[i] * 9 * 2; }
+  for (int i = 0; i < 2; ++i) { L.tc_up[i] = o; o += (long)kUpCin[i] * kUpCout[i] * 4 * 2; }
+  L.tc_fin = o; o += 2 * 1024;
   L.total = o;
   return L;
 }
@@ -100,12 +120,19 @@ struct giga_ctx {
   float* d_heads = nullptr;  // [4][DW_HEAD]   fp32 FMA-pipe decoder
   float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo tf32 splits)
   int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
+  int encoder_impl = 1;      // U-Net convs: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
+  int last_impl = 0;
+  const char* timeline_layer = nullptr;   // debug (env GIGA_TIMELINE=<kernel name>): in-kernel phase timestamps
+  unsigned long long* d_timeline = nullptr;
+  long timeline_n = 0;
   // workspaces (sized for cap_B scenes)
   int cap_B = 0;
   int last_B = 0;
   float* d_pre = nullptr;      // [3][B][32][1600]
   float* d_xzpart = nullptr;   // [B][10][40][32][40]
   float* d_act[kNumActs] = {};
+  float* d_tall[kNumActs + 1] = {};   // TALL pre-split activations ([0] = pre, [1+i] = kActs[i]) for the tensor-core encoder
+  long tall_ps[kNumActs + 1] = {};
   // host-entry staging (device side)
   float *h_tsdf = nullptr, *h_planes = nullptr, *h_p = nullptr, *h_pt = nullptr;
   float *h_qual = nullptr, *h_rot = nullptr, *h_width = nullptr, *h_occ = nullptr;
@@ -160,6 +187,10 @@ int ensure_attrs(giga_ctx* ctx) {
   SET_CONV(K_d0c1); SET_CONV(K_d0c2); SET_CONV(K_d1c1); SET_CONV(K_d1c2); SET_CONV(K_d2c1);
   SET_CONV(K_d2c2); SET_CONV(K_u0c1); SET_CONV(K_u0c2); SET_CONV(K_u1c1); SET_CONV(K_u1c2);
 #undef SET_CONV
+#define SET_TC(K) CU_TRY(cudaFuncSetAttribute(conv_tall_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES))
+  SET_TC(T_c40); SET_TC(T_d1c1); SET_TC(T_c20); SET_TC(T_d2c1); SET_TC(T_d2c2); SET_TC(T_u0up); SET_TC(T_u0c1); SET_TC(T_u1up);
+  SET_TC(T_u1c1); SET_TC(T_u1c2);
+#undef SET_TC
   CU_TRY(cudaFuncSetAttribute(convT2x2_kernel<K_u0up>, cudaFuncAttributeMaxDynamicSharedMemorySize, K_u0up::SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(convT2x2_kernel<K_u1up>, cudaFuncAttributeMaxDynamicSharedMemorySize, K_u1up::SMEM_BYTES));
   ctx->attrs_set = true;
@@ -178,6 +209,15 @@ int ensure_workspace(giga_ctx* ctx, int B) {
   CU_TRY(cudaMalloc(&ctx->d_xzpart, sizeof(float) * (size_t)B * CI_NT * G * C * G));
   for (int i = 0; i < kNumActs; ++i)
     CU_TRY(cudaMalloc(&ctx->d_act[i], sizeof(float) * 3 * (size_t)B * kActs[i].ch * kActs[i].hw * kActs[i].hw));
+  for (int i = 0; i <= kNumActs; ++i) {   // zero-initialised once: padding positions are never written
+    const int hw = i == 0 ? 40 : kActs[i - 1].hw, ch = i == 0 ? 32 : kActs[i - 1].ch;
+    if (ctx->d_tall[i]) cudaFree(ctx->d_tall[i]);
+    ctx->d_tall[i] = nullptr;
+    ctx->tall_ps[i] = tall_ps(hw, 3 * B);
+    const size_t bytes = sizeof(float) * (size_t)tall_floats(hw, 3 * B, ch);
+    CU_TRY(cudaMalloc(&ctx->d_tall[i], bytes));
+    CU_TRY(cudaMemset(ctx->d_tall[i], 0, bytes));
+  }
   ctx->cap_B = B;
   return GIGA_OK;
 }
@@ -197,12 +237,55 @@ void launch_conv(giga_ctx* ctx, const char* name, int n_img, const float* s0, co
                                                               ctx->d_enc + ctx->el.bias[layer], out, pooled);
 }
 
+struct TallBuf { float* p = nullptr; long ps = 0; };
+
+template <class K>
+void launch_tall(giga_ctx* ctx, const char* name, int n_img, const TallBuf& s0, const TallBuf& s1, const float* w,
+                 const float* bias, const TallBuf& out, float* fin_out, cudaStream_t st) {
+  dim3 grid(K::num_ctas(n_img), K::NNT);
+  LaunchScope ls(ctx, name, st);
+  unsigned long long* tl = nullptr;
+  if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, name)) {   // debug: per-CTA phase timestamps of one layer
+    const size_t n = (size_t)grid.x * grid.y * 32;
+    if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+    cudaMalloc(&ctx->d_timeline, n * 8);
+    cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
+    ctx->timeline_n = (long)n;
+    tl = ctx->d_timeline;
+  }
+  conv_tall_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(s0.p, s0.ps, s1.p, s1.ps, w, bias, out.p, out.ps,
+                                                                ctx->d_enc + ctx->el.tc_fin, ctx->d_enc + ctx->el.fin_b, fin_out, n_img, tl);
+}
+
 template <class K>
 void launch_convT(giga_ctx* ctx, const char* name, int n_img, const float* src, int up, float* out, cudaStream_t st) {
   dim3 grid(K::NB * K::NCT, n_img);
   LaunchScope ls(ctx, name, st);
   convT2x2_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(src, ctx->d_enc + ctx->el.up_w[up],
                                                                ctx->d_enc + ctx->el.up_b[up], out);
+}
+
+float tf32_rn_host(float v);
+
+// [ntile][chunk][tap][hi,lo][kc 2][n NTILE][4]; MODE 0 from the reference's Conv2d [co][ci][3][3],
+// MODE 1 from ConvTranspose2d [ci][co][2][2] with ntile = a*2+b
+template <class K>
+void pack_conv_tc(const float* w, float* dst) {
+  for (int nt = 0; nt < K::NNT; ++nt)
+    for (int c = 0; c < K::NC; ++c)
+      for (int tap = 0; tap < K::NTAPS; ++tap)
+        for (int kc = 0; kc < 2; ++kc)
+          for (int n = 0; n < K::NTILE; ++n)
+            for (int j = 0; j < 4; ++j) {
+              const int ci = c * 8 + kc * 4 + j;
+              float v;
+              if (K::MODE == 0) v = w[((long)(nt * K::NTILE + n) * K::CIN + ci) * 9 + tap];
+              else v = w[((long)ci * K::COUT + n) * 4 + nt];
+              const float hi = tf32_rn_host(v);
+              const long base = ((((long)nt * K::NC + c) * K::NTAPS + tap) * 2) * 2 * K::NTILE * 4;
+              dst[base + ((0 * 2 + kc) * K::NTILE + n) * 4 + j] = hi;
+              dst[base + ((1 * 2 + kc) * K::NTILE + n) * 4 + j] = v - hi;
+            }
 }
 
 float tf32_rn_host(float v) {  // same rounding as decoder_tc.cuh::tf32_rn
@@ -242,6 +325,7 @@ int giga_ctx_create(giga_ctx** out, int device) {
                                  std::to_string(prop.minor) + "; this library is built for sm_100a only");
   giga_ctx* ctx = new giga_ctx();
   ctx->device = device;
+  ctx->timeline_layer = getenv("GIGA_TIMELINE");
   ctx->el = make_enc_layout();
   *out = ctx;
   return GIGA_OK;
@@ -256,6 +340,8 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   for (float* p : ptrs)
     if (p) cudaFree(p);
   for (float* p : ctx->d_act)
+    if (p) cudaFree(p);
+  for (float* p : ctx->d_tall)
     if (p) cudaFree(p);
   for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -314,6 +400,31 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
     for (int o = 0; o < 32; ++o)
       for (int c = 0; c < 32; ++c) blob[ctx->el.fin_w + c * 32 + o] = w[o * 32 + c];  // [ci][co]
     memcpy(blob.data() + ctx->el.fin_b, b, sizeof(float) * 32);
+    for (int k = 0; k < 32; ++k)
+      for (int n = 0; n < 32; ++n) {
+        const float v = w[n * 32 + k], hi = tf32_rn_host(v);
+        blob[ctx->el.tc_fin + ((k / 4) * 32 + n) * 4 + (k % 4)] = hi;
+        blob[ctx->el.tc_fin + 1024 + ((k / 4) * 32 + n) * 4 + (k % 4)] = v - hi;
+      }
+    {
+      const float* cw[10];
+      for (int i = 0; i < 10; ++i) get(ctx, std::string("encoder.unet.") + kConvName[i] + ".weight", (long)kConvCout[i] * kConvCin[i] * 9, &cw[i]);
+      pack_conv_tc<T_c40>(cw[0], blob.data() + ctx->el.tc_conv[0]);
+      pack_conv_tc<T_c40>(cw[1], blob.data() + ctx->el.tc_conv[1]);
+      pack_conv_tc<T_d1c1>(cw[2], blob.data() + ctx->el.tc_conv[2]);
+      pack_conv_tc<T_c20>(cw[3], blob.data() + ctx->el.tc_conv[3]);
+      pack_conv_tc<T_d2c1>(cw[4], blob.data() + ctx->el.tc_conv[4]);
+      pack_conv_tc<T_d2c2>(cw[5], blob.data() + ctx->el.tc_conv[5]);
+      pack_conv_tc<T_u0c1>(cw[6], blob.data() + ctx->el.tc_conv[6]);
+      pack_conv_tc<T_c20>(cw[7], blob.data() + ctx->el.tc_conv[7]);
+      pack_conv_tc<T_u1c1>(cw[8], blob.data() + ctx->el.tc_conv[8]);
+      pack_conv_tc<T_u1c2>(cw[9], blob.data() + ctx->el.tc_conv[9]);
+      const float* uw;
+      get(ctx, "encoder.unet.up_convs.0.upconv.weight", (long)kUpCin[0] * kUpCout[0] * 4, &uw);
+      pack_conv_tc<T_u0up>(uw, blob.data() + ctx->el.tc_up[0]);
+      get(ctx, "encoder.unet.up_convs.1.upconv.weight", (long)kUpCin[1] * kUpCout[1] * 4, &uw);
+      pack_conv_tc<T_u1up>(uw, blob.data() + ctx->el.tc_up[1]);
+    }
     if (!ctx->d_enc) CU_TRY(cudaMalloc(&ctx->d_enc, sizeof(float) * ctx->el.total));
     CU_TRY(cudaMemcpy(ctx->d_enc, blob.data(), sizeof(float) * ctx->el.total, cudaMemcpyHostToDevice));
     ctx->has_encoder = true;
@@ -426,6 +537,48 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
         *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),
         *u0 = act(ctx, "u0"), *u0c1 = act(ctx, "u0c1"), *u0c2 = act(ctx, "u0c2"), *u1 = act(ctx, "u1"),
         *u1c1 = act(ctx, "u1c1"), *u1c2 = act(ctx, "u1c2");
+  if (ctx->encoder_impl == 1) {
+    // tensor-core U-Net on TALL pre-split activations (unet_tall.cuh)
+    auto tb = [&](const char* nm) {
+      TallBuf t;
+      if (!strcmp(nm, "pre")) { t.p = ctx->d_tall[0]; t.ps = ctx->tall_ps[0]; return t; }
+      for (int i = 0; i < kNumActs; ++i)
+        if (!strcmp(kActs[i].name, nm)) { t.p = ctx->d_tall[1 + i]; t.ps = ctx->tall_ps[1 + i]; }
+      return t;
+    };
+    const TallBuf none;
+    const float* E = ctx->d_enc;
+    const EncLayout& L = ctx->el;
+    {
+      LaunchScope ls(ctx, "nchw_to_tall:pre", st);
+      nchw_to_tall_kernel<40, 8><<<ceil_div(n_img * 8 * G2, 256), 256, 0, st>>>(ctx->d_pre, tb("pre").p, tb("pre").ps, n_img);
+    }
+    launch_tall<T_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st);
+    launch_tall<T_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st);
+    {
+      LaunchScope ls(ctx, "maxpool:p0", st);
+      pool_tall_kernel<20, 8><<<ceil_div(n_img * 8 * 400, 256), 256, 0, st>>>(tb("d0c2").p, tb("d0c2").ps, tb("p0").p, tb("p0").ps, n_img);
+    }
+    launch_tall<T_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st);
+    launch_tall<T_c20>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st);
+    {
+      LaunchScope ls(ctx, "maxpool:p1", st);
+      pool_tall_kernel<10, 16><<<ceil_div(n_img * 16 * 100, 256), 256, 0, st>>>(tb("d1c2").p, tb("d1c2").ps, tb("p1").p, tb("p1").ps, n_img);
+    }
+    launch_tall<T_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st);
+    launch_tall<T_d2c2>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st);
+    launch_tall<T_u0up>(ctx, "convT:u0", n_img, tb("d2c2"), none, E + L.tc_up[0], E + L.up_b[0], tb("u0"), nullptr, st);
+    launch_tall<T_u0c1>(ctx, "conv3x3:u0c1", n_img, tb("u0"), tb("d1c2"), E + L.tc_conv[6], E + L.bias[6], tb("u0c1"), nullptr, st);
+    launch_tall<T_c20>(ctx, "conv3x3:u0c2", n_img, tb("u0c1"), none, E + L.tc_conv[7], E + L.bias[7], tb("u0c2"), nullptr, st);
+    launch_tall<T_u1up>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st);
+    launch_tall<T_u1c1>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st);
+    launch_tall<T_u1c2>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st);
+    ctx->last_B = B;
+    ctx->last_impl = 1;
+    CU_TRY(cudaGetLastError());
+    return GIGA_OK;
+  }
+  ctx->last_impl = 0;
   launch_conv<K_d0c1>(ctx, "conv3x3:d0c1", n_img, ctx->d_pre, nullptr, 0, d0c1, nullptr, st);
   launch_conv<K_d0c2>(ctx, "conv3x3:d0c2", n_img, d0c1, nullptr, 1, d0c2, p0, st);
   launch_conv<K_d1c1>(ctx, "conv3x3:d1c1", n_img, p0, nullptr, 2, d1c1, nullptr, st);
@@ -549,6 +702,11 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
     ctx->decoder_impl = value;
     return GIGA_OK;
   }
+  if (!strcmp(key, "encoder_impl")) {
+    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "encoder_impl must be 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
+    ctx->encoder_impl = value;
+    return GIGA_OK;
+  }
   return fail(GIGA_EINVAL, std::string("giga_ctx_set_option: unknown key '") + key + "'");
 }
 
@@ -592,6 +750,12 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
   if (int r = set_device(ctx)) return r;
   const float* src = nullptr;
   long numel = 0;
+  if (!strcmp(name, "timeline")) {   // u64 stamps reinterpreted as pairs of floats (debug only)
+    if (!ctx->d_timeline) return fail(GIGA_ESTATE, "giga_debug_copy: no timeline recorded (set GIGA_TIMELINE=<kernel name>)");
+    if (ctx->timeline_n * 2 > capacity) return fail(GIGA_EINVAL, "giga_debug_copy: destination too small");
+    CU_TRY(cudaMemcpyAsync(dst, ctx->d_timeline, ctx->timeline_n * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return ctx->timeline_n * 2;
+  }
   if (!strcmp(name, "pre")) {
     src = ctx->d_pre;
     numel = 3L * ctx->last_B * C * G2;
@@ -603,6 +767,26 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
       }
   }
   if (!src) return fail(GIGA_EINVAL, std::string("giga_debug_copy: unknown buffer '") + name + "'");
+  if (ctx->last_impl == 1 && strcmp(name, "pre")) {
+    if (!strcmp(name, "u1c2"))
+      return fail(GIGA_ESTATE, "giga_debug_copy: 'u1c2' is fused away by the tensor-core encoder (encoder_impl=1)");
+    // the tensor-core encoder keeps activations in the TALL pre-split layout: convert into the NCHW scratch first
+    int idx = -1;
+    for (int i = 0; i < kNumActs; ++i)
+      if (!strcmp(kActs[i].name, name)) idx = i;
+    const int n_img = 3 * ctx->last_B, hw = kActs[idx].hw, c4 = kActs[idx].ch / 4;
+    const float* tsrc = ctx->d_tall[1 + idx];
+    const long ps = ctx->tall_ps[1 + idx];
+    float* scratch = ctx->d_act[idx];
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = ceil_div(n_img * c4 * hw * hw, 256);
+    if (hw == 40 && c4 == 8) tall_to_nchw_kernel<40, 8><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    else if (hw == 20 && c4 == 8) tall_to_nchw_kernel<20, 8><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    else if (hw == 20 && c4 == 16) tall_to_nchw_kernel<20, 16><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    else if (hw == 10 && c4 == 16) tall_to_nchw_kernel<10, 16><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    else if (hw == 10 && c4 == 32) tall_to_nchw_kernel<10, 32><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    else return fail(GIGA_EINVAL, "giga_debug_copy: unexpected activation shape");
+  }
   if (numel > capacity) return fail(GIGA_EINVAL, "giga_debug_copy: destination too small");
   CU_TRY(cudaMemcpyAsync(dst, src, sizeof(float) * numel, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return numel;

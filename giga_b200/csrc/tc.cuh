@@ -80,6 +80,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One lane of a fully converged warp.  Issuing tcgen05.mma / bulk copies under this predicate (instead of
+// under a thread-index test) lets the compiler keep descriptors in uniform registers: back-to-back
+// UTCHMMA without the per-instruction ELECT/BRA.U.ANY lane loop (profiles/r01d: 3-4x faster issue).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // 3xTF32 operand split: hi keeps the top 19 bits (exactly representable in tf32), lo = v - hi is exact in fp32
 __host__ __device__ __forceinline__ float tf32_hi(float v) {
 #ifdef __CUDA_ARCH__

@@ -108,7 +108,8 @@ int giga_forward_host(giga_ctx *ctx, const float *tsdf, int B, const float *p, i
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 long giga_ctx_launch_count(const giga_ctx *ctx);
 /* implementation switches (A/B testing; defaults are the fastest parity-clean variants):
- *   "decoder_impl": 1 = tcgen05 tensor cores with 3xTF32 operand splitting (default), 0 = fp32 FMA pipe */
+ *   "decoder_impl": 1 = tcgen05 tensor cores with 3xTF32 operand splitting (default), 0 = fp32 FMA pipe
+ *   "encoder_impl": same switch for the U-Net 3x3 convolutions */
 int giga_ctx_set_option(giga_ctx *ctx, const char *key, int value);
 /* per-kernel device timing for the roofline report: when enabled every kernel launch is bracketed
  * by CUDA events recorded on the launch stream.  giga_ctx_timing_report() waits for the recorded

@@ -34,13 +34,18 @@ def main(B=2, N=300):
         cap = {}
         ref_planes = torch.stack([O.unet_forward(sd, pre_stack.reshape(3 * B, 32, 40, 40), capture=cap).reshape(3, B, 32, 40, 40)[i]
                                   for i in range(3)])
-        c = net.encode_inputs(x.to(dev))
-        torch.cuda.synchronize()
-        cmp("pre", net.debug_activation("pre", B), pre_stack)
-        for k in ["d0c1", "d0c2", "p0", "d1c1", "d1c2", "p1", "d2c1", "d2c2", "u0", "u0c1", "u0c2", "u1", "u1c1", "u1c2"]:
-            got = net.debug_activation(k, B)
-            cmp(k, got, cap[k].reshape(got.shape))
-        cmp("planes", torch.stack([c[k] for k in O.PLANES]), ref_planes)
+        for eimpl, etag in ((0, "ffma"), (1, "tc")):
+            net._engine().set_option("encoder_impl", eimpl)
+            c = net.encode_inputs(x.to(dev))
+            torch.cuda.synchronize()
+            cmp(etag + ".pre", net.debug_activation("pre", B), pre_stack)
+            for k in ["d0c1", "d0c2", "p0", "d1c1", "d1c2", "p1", "d2c1", "d2c2", "u0", "u0c1", "u0c2", "u1", "u1c1", "u1c2"]:
+                try:
+                    got = net.debug_activation(k, B)
+                except giga_b200.GigaError:
+                    continue
+                cmp(etag + "." + k, got, cap[k].reshape(got.shape))
+            cmp(etag + ".planes", torch.stack([c[k] for k in O.PLANES]), ref_planes)
         planes_ref = {k: ref_planes[i] for i, k in enumerate(O.PLANES)}
         cmp("feat96", net.sample_feature(p.to(dev), c, "concat"), O.sample_concat_feature(p, planes_ref))
         cmp("qfeat32", net.query_feature(p.to(dev), c), O.query_feature(p, planes_ref))
@@ -54,9 +59,9 @@ def main(B=2, N=300):
         cmp("host.qual", hq[0], rq); cmp("host.rot", hq[1], rr); cmp("host.width", hq[2], rw); cmp("host.occ", hq[3], ro)
         bv, bi = net.scene_argmax(qual)
         rows.append(("argmax", (B,), float((bi.cpu().long() - rq.argmax(1)).abs().max()), 0.0, 0.0, True))
-    print(f"{'stage':<12}{'shape':<24}{'max|d|':>12}{'mean|d|':>12}{'max|ref|':>12}  finite")
+    print(f"{'stage':<14}{'shape':<24}{'max|d|':>12}{'mean|d|':>12}{'max|ref|':>12}  finite")
     for r in rows:
-        print(f"{r[0]:<12}{str(r[1]):<24}{r[2]:>12.3e}{r[3]:>12.3e}{r[4]:>12.3e}  {r[5]}")
+        print(f"{r[0]:<14}{str(r[1]):<24}{r[2]:>12.3e}{r[3]:>12.3e}{r[4]:>12.3e}  {r[5]}")
     print("launches:", net.gpu_launches)
 
 

