@@ -31,6 +31,9 @@ SYMBOLS = {
     "giga_scene_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_forward_host_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_forward_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "giga_ctx_launch_count": (C.c_long, [C.c_void_p]),
     "giga_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "giga_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -24,17 +24,13 @@ struct ConvInParams {
   float b[32];
 };
 
-constexpr int CI_TY = 4;            // iy rows per CTA
-constexpr int CI_NT = G / CI_TY;    // 10 CTAs per scene
-constexpr int CI_THREADS = CI_TY * G;  // 160
-constexpr int CI_XS_Z = 44;         // padded iz extent (iz+1 in 0..41, +2 pad)
-constexpr int CI_XS_Y = CI_TY + 2;
-constexpr int CI_XS_X = G + 2;
-constexpr int CI_XS = CI_XS_X * CI_XS_Y * CI_XS_Z;        // 11088 floats
+constexpr int CI_TY = 5;            // iy rows per CTA
+constexpr int CI_NT = G / CI_TY;    // 8 CTAs per scene
+constexpr int CI_THREADS = CI_TY * G;  // 200
 constexpr int CI_RED_STRIDE = 41;
-constexpr int CI_RED = C * CI_TY * CI_RED_STRIDE;          // 5248 floats
-constexpr int CI_XYACC = C * CI_TY * CI_RED_STRIDE;        // 5248 floats
-constexpr int CI_SMEM_BYTES = (CI_XS + CI_RED + CI_XYACC) * 4;  // 86,336 B
+constexpr int CI_RED = C * CI_TY * CI_RED_STRIDE;          // 6560 floats
+constexpr int CI_XYACC = C * CI_TY * CI_RED_STRIDE;        // 6560 floats
+constexpr int CI_SMEM_BYTES = (CI_RED + CI_XYACC) * 4;     // 52,480 B
 
 // grid (CI_NT, B), block CI_THREADS
 __global__ void __launch_bounds__(CI_THREADS, 2)
@@ -43,8 +39,7 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
                       float* __restrict__ xz_part,   // [B][CI_NT][40 ix][32][40 iz]
                       int B, const __grid_constant__ ConvInParams P) {
   extern __shared__ __align__(16) float smem[];
-  float* xs = smem;                 // [42][TY+2][44]
-  float* red = xs + CI_XS;          // [32*TY][41]
+  float* red = smem;                // [32*TY][41]
   float* xyacc = red + CI_RED;      // [32*TY][41]  (col = ix)
 
   const int tile = blockIdx.x, b = blockIdx.y;
@@ -52,49 +47,49 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
   const int iyl = tid / G, iz = tid % G;
   const int iy0 = tile * CI_TY;
 
-  // stage the CTA's whole input footprint (42 x 6 x 44, zero padded halo)
+  // The thread's 3x3 (dy,dz) neighbourhood is read straight from global/L1 (the TSDF is 256 KB per scene and
+  // L2 resident); slab ix+2 is prefetched into registers while slab ix+1's 864 FMAs run.  Out-of-volume taps
+  // are zero (Conv3d padding=1): per-thread masks, fixed for the whole march.
   const float* xb = x + (size_t)b * G3;
-  for (int e = tid; e < CI_XS; e += CI_THREADS) {
-    const int zp = e % CI_XS_Z;
-    const int yp = (e / CI_XS_Z) % CI_XS_Y;
-    const int xp = e / (CI_XS_Z * CI_XS_Y);
-    const int gx = xp - 1, gy = iy0 + yp - 1, gz = zp - 1;
-    float v = 0.f;
-    if (gx >= 0 && gx < G && gy >= 0 && gy < G && gz >= 0 && gz < G) v = __ldg(xb + (gx * G + gy) * G + gz);
-    xs[e] = v;
-  }
-  __syncthreads();
+  int off[9];
+  bool ok[9];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz) {
+      const int gy = iy0 + iyl + dy - 1, gz = iz + dz - 1;
+      ok[dy * 3 + dz] = gy >= 0 && gy < G && gz >= 0 && gz < G;
+      off[dy * 3 + dz] = ok[dy * 3 + dz] ? gy * G + gz : 0;
+    }
 
   float yz[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) yz[c] = 0.f;
 
-  float win[3][9];  // [dx][dy*3+dz]
-  {
-    const float* s0 = xs + (0 * CI_XS_Y + iyl) * CI_XS_Z + iz;
-    const float* s1 = xs + (1 * CI_XS_Y + iyl) * CI_XS_Z + iz;
+  float win[3][9];  // [dx][dy*3+dz]; win[dx] holds slab ix+dx-1
+  float nxt[9];     // prefetched slab
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dz = 0; dz < 3; ++dz) {
-        win[1][dy * 3 + dz] = s0[dy * CI_XS_Z + dz];
-        win[2][dy * 3 + dz] = s1[dy * CI_XS_Z + dz];
-      }
+  for (int t = 0; t < 9; ++t) {
+    win[1][t] = 0.f;                                         // slab -1 (padding)
+    win[2][t] = ok[t] ? __ldg(xb + off[t]) : 0.f;            // slab 0
+    nxt[t] = ok[t] ? __ldg(xb + G2 + off[t]) : 0.f;          // slab 1
   }
 
 #pragma unroll 1
   for (int ix = 0; ix < G; ++ix) {
-    {
-      const float* s2 = xs + ((ix + 2) * CI_XS_Y + iyl) * CI_XS_Z + iz;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        win[0][t] = win[1][t];
-        win[1][t] = win[2][t];
-      }
+    for (int t = 0; t < 9; ++t) {
+      win[0][t] = win[1][t];
+      win[1][t] = win[2][t];
+      win[2][t] = nxt[t];
+    }
+    if (ix + 2 < G) {
+      const float* xs2 = xb + (size_t)(ix + 2) * G2;
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
+      for (int t = 0; t < 9; ++t) nxt[t] = ok[t] ? __ldg(xs2 + off[t]) : 0.f;
+    } else {
 #pragma unroll
-        for (int dz = 0; dz < 3; ++dz) win[2][dy * 3 + dz] = s2[dy * CI_XS_Z + dz];
+      for (int t = 0; t < 9; ++t) nxt[t] = 0.f;              // slab 40 (padding)
     }
     float f[C];
 #pragma unroll
@@ -134,15 +129,15 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
     __syncthreads();
   }
 
-  // yz[c][iz][iy]: transpose through smem so each (c,iz) row segment is one 16 B store
-  float* stage = red;  // [32][40][TY] = 5120 floats <= CI_RED
+  // yz[c][iz][iy]: transpose through smem so that rows of TY consecutive iy are written together
+  float* stage = red;  // [32][40][TY] = 6400 floats <= CI_RED
 #pragma unroll
   for (int c = 0; c < C; ++c) stage[(c * G + iz) * CI_TY + iyl] = yz[c] / 40.0f;
   __syncthreads();
   float* pre_yz = pre + ((size_t)(2 * B + b) * C) * G2;
-  for (int o = tid; o < C * G; o += CI_THREADS) {
-    const int c = o / G, z = o % G;
-    st4(pre_yz + (c * G + z) * G + iy0, ld4(stage + o * CI_TY));
+  for (int o = tid; o < C * G * CI_TY; o += CI_THREADS) {
+    const int cz = o / CI_TY, r = o % CI_TY;   // cz = c*40 + iz
+    pre_yz[cz * G + iy0 + r] = stage[o];
   }
   float* pre_xy = pre + ((size_t)(1 * B + b) * C) * G2;
   for (int o = tid; o < C * CI_TY * G; o += CI_THREADS) {

@@ -6,6 +6,7 @@
 //   fc_c  : [128 pts x 96 feat] . [96 x 160]   (all five blocks' fc_c at once, one plane (K=32) at a time)
 //   fc_0/1: [128 pts x 32]      . [32 x 32]    x 10 per head (the ResnetBlockFC chain)
 // A CTA owns 128 query points of one scene; thread t <-> point t <-> TMEM lane t.
+//   * weights: staged by cp.async.bulk (UBLKCP) with mbarrier completion, prefetched one stage ahead;
 //   * gather: warp-cooperative (lane = channel, 12 coalesced 128 B texel reads per point); the
 //     96 features of the warp's 32 points stay in REGISTERS (F[3][32] per lane) and are re-split
 //     into the shared-memory A operand (hi/lo tf32 pair) for every head -- gathered once per tile;
@@ -19,6 +20,7 @@
 #include "common.cuh"
 #include "decoder.cuh"
 #include "tc.cuh"
+#include "unet_tall.cuh"   // tc::bulk_g2s / mbar_arrive_expect_tx
 
 namespace giga {
 
@@ -39,8 +41,10 @@ constexpr int TD_W_BYTES = 2 * TW_FCC_SLICE * 4;  // staged weights: fc_c plane 
 constexpr int TD_OFF_ALO = TD_A_BYTES;
 constexpr int TD_OFF_W = 2 * TD_A_BYTES;          // 33024
 constexpr int TD_OFF_TINFO = TD_OFF_W + TD_W_BYTES;          // 73984
-constexpr int TD_OFF_BAR = TD_OFF_TINFO + TD_PTS * 24 * 4;   // 86272
-constexpr int TD_SMEM_BYTES = TD_OFF_BAR + 16;               // 86288
+constexpr int TD_OFF_WB0 = TD_OFF_TINFO + TD_PTS * 24 * 4;   // 86272: dedicated chain-weight buffer 0 (buffer 1 aliases sW)
+constexpr int TD_WB_BYTES = TW_BLK_SIZE * 4;                 // 16640
+constexpr int TD_OFF_BAR = TD_OFF_WB0 + TD_WB_BYTES;         // 102912
+constexpr int TD_SMEM_BYTES = TD_OFF_BAR + 48;               // 102960  (2 CTAs / SM)
 constexpr int TD_TMEM_COLS = 256;
 constexpr uint32_t TD_KS_WC = 160 * 16;           // fc_c B operand k-chunk stride (N=160)
 constexpr uint32_t TD_KS_W = 32 * 16;             // 32x32 B operand k-chunk stride
@@ -115,15 +119,18 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
                         const float* __restrict__ tw,      // [4][TW_HEAD]
                         int B, int N, unsigned heads,
                         float* __restrict__ qual, float* __restrict__ rot, float* __restrict__ width,
-                        float* __restrict__ occ) {
+                        float* __restrict__ occ, unsigned long long* __restrict__ tl) {   // tl: optional debug timeline
   extern __shared__ __align__(128) uint8_t smem_tc[];
   uint8_t* smem = smem_tc;
   uint8_t* sAhi = smem;
   uint8_t* sAlo = smem + TD_OFF_ALO;
   uint8_t* sW = smem + TD_OFF_W;
   float* tinfo = reinterpret_cast<float*>(smem + TD_OFF_TINFO);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TD_OFF_BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TD_OFF_BAR + 8);
+  uint8_t* sWB0 = smem + TD_OFF_WB0;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TD_OFF_BAR);       // MMA completion
+  uint64_t* wbar = bar + 1;                                             // [2] chain-weight buffers landed
+  uint64_t* pbar = bar + 3;                                             // fc_c plane slice landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TD_OFF_BAR + 40);
 
   const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * TD_PTS;
@@ -131,8 +138,22 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   const bool valid = n < N;
   const int nc = valid ? n : N - 1;
 
+  unsigned long long* tlc = tl ? tl + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+  int tslot = 0;
+  auto stamp = [&]() {
+    if (tlc && tid == 0 && tslot < 31) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      tlc[tslot] = t;
+    }
+    ++tslot;
+  };
+  stamp();   // 0: start
   if (warp == 0) tc::tmem_alloc(tmem_slot, TD_TMEM_COLS);
-  if (tid == 0) tc::mbar_init(bar, 1);
+  if (tid == 0) {
+    tc::mbar_init(bar, 1); tc::mbar_init(&wbar[0], 1); tc::mbar_init(&wbar[1], 1); tc::mbar_init(pbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   // ---- gather: the warp's 32 points, lane = channel; features stay in registers ----
   float F[3][32];
@@ -172,6 +193,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
 
   const float* pp = pts + ((size_t)b * N + nc) * 3;
   const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+  stamp();   // 1: gather done
 
   tc::fence_before_sync();
   __syncthreads();   // TMEM address + mbarrier init visible
@@ -183,19 +205,36 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   constexpr uint32_t IDESC_32 = tc::make_idesc_tf32(128, 32);
   uint32_t phase = 0;
 
+  // Weight staging is asynchronous (cp.async.bulk + mbarrier, issued by one elected lane of warp 0):
+  //   chain block i+1 is prefetched while block i computes (buffers: dedicated WB0 / the start of sW),
+  //   block 0 of a head is prefetched during its fc_c plane rounds, and the next head's first plane slice
+  //   during block 4.  Only plane slices 1 and 2 of each head are fetched on demand.
+  uint32_t wuse[2] = {0u, 0u}, puse = 0u;          // completed-use counters -> mbarrier parities
+  bool plane0_prefetched = false;
+  auto issue_bulk = [&](void* dst, const float* src, uint32_t bytes, uint64_t* mb) {
+    if (warp == 0) {
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(mb, bytes);
+        tc::bulk_g2s(dst, src, bytes, mb);
+      }
+      __syncwarp();
+    }
+  };
+
 #pragma unroll 1
   for (int head = 0; head < 4; ++head) {
     if (!(heads & (1u << head))) continue;
     const float* W = tw + (size_t)head * TW_HEAD;
+    int next_head = -1;
+    for (int hh = head + 1; hh < 4; ++hh)
+      if (heads & (1u << hh)) { next_head = hh; break; }
 
     // ---- fc_c for all five blocks: C[128 x 160] = F[128 x 96] . Wc^T, one plane (K = 32) per round ----
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
-      // stage the (head, plane) weight slice hi|lo, already in operand layout
-      const float4* src = reinterpret_cast<const float4*>(W + TW_FCC + pl * 2 * TW_FCC_SLICE);
-      float4* dst = reinterpret_cast<float4*>(sW);
-#pragma unroll 4
-      for (int e = tid; e < 2 * TW_FCC_SLICE / 4; e += TD_PTS) dst[e] = __ldg(src + e);
+      // (head, plane) weight slice hi|lo, already in operand layout; sW is free: its last readers' MMAs completed
+      if (!(pl == 0 && plane0_prefetched)) issue_bulk(sW, W + TW_FCC + pl * 2 * TW_FCC_SLICE, TD_W_BYTES, pbar);
+      if (pl == 0) issue_bulk(sWB0, W + TW_BLK, TD_WB_BYTES, &wbar[0]);   // chain block 0 -> dedicated buffer
       // A operand from the register-resident features: element (row = warp*32+q, k = lane)
       uint8_t* ah = sAhi + (lane >> 2) * TD_KS_A + (lane & 3) * 4 + (warp * 32) * 16;
       uint8_t* al = sAlo + (lane >> 2) * TD_KS_A + (lane & 3) * 4 + (warp * 32) * 16;
@@ -210,6 +249,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       tc::fence_before_sync();
       __syncthreads();
       if (warp == 0) {
+        tc::mbar_wait(pbar, puse & 1u);
         tc::fence_after_sync();
         if (tc::elect_one()) {
           issue_k32_x3(tmem, a_hi, a_lo, w_s, w_s + TW_FCC_SLICE * 4, TD_KS_WC, IDESC_160, pl > 0);
@@ -217,10 +257,13 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
         }
         __syncwarp();
       }
+      ++puse;
       tc::mbar_wait(bar, phase);   // MMAs done: A / W buffers reusable, C columns readable
       phase ^= 1u;
       tc::fence_after_sync();
+      stamp();   // per head: 3 plane rounds
     }
+    plane0_prefetched = false;
 
     // ---- fc_p on CUDA cores ----
     float h[32];
@@ -231,11 +274,14 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
 
 #pragma unroll 1
     for (int blk = 0; blk < 5; ++blk) {
-      // stage W0hi W0lo W1hi W1lo b0 b1 (4160 floats); the previous MMAs reading sW have completed
-      {
-        const float4* src = reinterpret_cast<const float4*>(W + TW_BLK + blk * TW_BLK_SIZE);
-        float4* dst = reinterpret_cast<float4*>(sW);
-        for (int e = tid; e < TW_BLK_SIZE / 4; e += TD_PTS) dst[e] = __ldg(src + e);
+      const int wb = blk & 1;                                   // 0: WB0, 1: start of sW
+      const uint8_t* wbuf = wb ? sW : sWB0;
+      const uint32_t w_b = tc::smem_u32(wbuf);
+      // prefetch: next block's weights into the other buffer; during the last block the next head's first plane slice
+      if (blk < 4) issue_bulk(wb ? (void*)sWB0 : (void*)sW, W + TW_BLK + (blk + 1) * TW_BLK_SIZE, TD_WB_BYTES, &wbar[wb ^ 1]);
+      else if (next_head >= 0) {
+        issue_bulk(sW, tw + (size_t)next_head * TW_HEAD + TW_FCC, TD_W_BYTES, pbar);
+        plane0_prefetched = true;
       }
       float v[32];
       tc::tmem_ld32(tmem_row + blk * 32, v);           // fc_c[blk] output for this point
@@ -248,10 +294,12 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       tc::fence_smem_to_async();
       tc::fence_before_sync();
       __syncthreads();
+      tc::mbar_wait(&wbar[wb], wuse[wb] & 1u);         // this block's weights have landed (all threads: they read b0/b1)
+      ++wuse[wb];
       if (warp == 0) {
         tc::fence_after_sync();
         if (tc::elect_one()) {
-          issue_k32_split3(tmem + 160, a_hi, a_lo, w_s, w_s + 4096, TD_KS_W, IDESC_32);   // fc_0
+          issue_k32_split3(tmem + 160, a_hi, a_lo, w_b, w_b + 4096, TD_KS_W, IDESC_32);   // fc_0
           tc::mma_commit(bar);
         }
         __syncwarp();
@@ -259,7 +307,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       tc::mbar_wait(bar, phase);
       phase ^= 1u;
       tc::fence_after_sync();
-      const float* bs = reinterpret_cast<const float*>(sW) + 4096;   // b0[32], b1[32]
+      const float* bs = reinterpret_cast<const float*>(wbuf) + 4096;   // b0[32], b1[32]
       tmem_ld32_sum3(tmem_row + 160, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bs[j], 0.f);
@@ -270,7 +318,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       if (warp == 0) {
         tc::fence_after_sync();
         if (tc::elect_one()) {
-          issue_k32_split3(tmem + 160, a_hi, a_lo, w_s + 8192, w_s + 12288, TD_KS_W, IDESC_32);   // fc_1
+          issue_k32_split3(tmem + 160, a_hi, a_lo, w_b + 8192, w_b + 12288, TD_KS_W, IDESC_32);   // fc_1
           tc::mma_commit(bar);
         }
         __syncwarp();
@@ -282,7 +330,8 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
 #pragma unroll
       for (int j = 0; j < 32; ++j) h[j] += v[j] + bs[32 + j];     // x + fc_1(relu(fc_0(relu(x))))
       tc::fence_before_sync();
-      __syncthreads();   // everyone has read b0/b1 and T before sW / T are overwritten by the next round
+      __syncthreads();   // everyone has read b0/b1 and T before this weight buffer / T are overwritten
+      stamp();   // per head: 5 block rounds
     }
 
     // ---- fc_out(relu(net)) + head epilogue on CUDA cores ----

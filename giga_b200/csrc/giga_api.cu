@@ -134,9 +134,15 @@ struct giga_ctx {
   float* d_tall[kNumActs + 1] = {};   // TALL pre-split activations ([0] = pre, [1+i] = kActs[i]) for the tensor-core encoder
   long tall_ps[kNumActs + 1] = {};
   // host-entry staging (device side)
-  float *h_tsdf = nullptr, *h_planes = nullptr, *h_p = nullptr, *h_pt = nullptr;
-  float *h_qual = nullptr, *h_rot = nullptr, *h_width = nullptr, *h_occ = nullptr;
-  int hcap_B = 0, hcap_Ng = 0, hcap_No = 0;
+  struct HostSlot {   // device-side staging of one in-flight host request
+    float *tsdf = nullptr, *planes = nullptr, *p = nullptr, *pt = nullptr;
+    float *qual = nullptr, *rot = nullptr, *width = nullptr, *occ = nullptr;
+    int cap_B = 0, cap_Ng = 0, cap_No = 0;
+    cudaEvent_t ev_in = nullptr, ev_compute = nullptr, ev_done = nullptr;
+    bool pending = false;
+  };
+  HostSlot slot[3];   // [0],[1]: pipelined submit/wait; [2]: the synchronous giga_forward_host
+  cudaStream_t st_h2d = nullptr, st_compute = nullptr, st_d2h = nullptr;   // pipelined host path
   long launches = 0;
   bool attrs_set = false;
   // optional per-kernel CUDA-event timing (bench.py roofline): events recorded on the launch stream
@@ -335,10 +341,21 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->h_tsdf, ctx->h_planes, ctx->h_p,
-                   ctx->h_pt,  ctx->h_qual,  ctx->h_rot, ctx->h_width,  ctx->h_occ};
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart};
   for (float* p : ptrs)
     if (p) cudaFree(p);
+  for (auto& s : ctx->slot) {
+    float* sp[] = {s.tsdf, s.planes, s.p, s.pt, s.qual, s.rot, s.width, s.occ};
+    for (float* p : sp)
+      if (p) cudaFree(p);
+    if (s.ev_in) cudaEventDestroy(s.ev_in);
+    if (s.ev_compute) cudaEventDestroy(s.ev_compute);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+  }
+  if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
+  if (ctx->st_compute) cudaStreamDestroy(ctx->st_compute);
+  if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
+  if (ctx->d_timeline) cudaFree(ctx->d_timeline);
   for (float* p : ctx->d_act)
     if (p) cudaFree(p);
   for (float* p : ctx->d_tall)
@@ -613,9 +630,19 @@ int giga_decode(giga_ctx* ctx, const float* planes, int B, const float* points, 
   cudaStream_t st = (cudaStream_t)stream;
   {
     LaunchScope ls(ctx, (heads & 15u) == GIGA_HEAD_TSDF ? "decode_points:tsdf" : "decode_points:grasp", st);
-    if (ctx->decoder_impl == 1)
+    if (ctx->decoder_impl == 1) {
+      unsigned long long* tl = nullptr;
+      if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, "decode")) {
+        const size_t n = (size_t)ceil_div(N, TD_PTS) * B * 32;
+        if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+        cudaMalloc(&ctx->d_timeline, n * 8);
+        cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
+        ctx->timeline_n = (long)n;
+        tl = ctx->d_timeline;
+      }
       decode_points_tc_kernel<<<dim3(ceil_div(N, TD_PTS), B), TD_PTS, TD_SMEM_BYTES, st>>>(planes, points, ctx->d_heads_tc, B,
-                                                                                           N, heads, qual, rot, width, occ);
+                                                                                           N, heads, qual, rot, width, occ, tl);
+    }
     else
       decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N,
                                                                                            heads, qual, rot, width, occ);
@@ -649,47 +676,119 @@ int giga_scene_argmax(giga_ctx* ctx, const float* qual, int B, int N, float* bes
   return GIGA_OK;
 }
 
-int giga_forward_host(giga_ctx* ctx, const float* tsdf, int B, const float* p, int Ng, const float* p_tsdf, int No,
-                      float* qual, float* rot, float* width, float* occ, void* stream) {
-  if (!ctx || !tsdf || B <= 0) return fail(GIGA_EINVAL, "giga_forward_host: bad argument");
+}  // extern "C" (re-opened below)
+
+namespace {
+
+int ensure_slot(giga_ctx* ctx, giga_ctx::HostSlot& s, int B, int Ng, int No) {
+  if (B <= s.cap_B && Ng <= s.cap_Ng && No <= s.cap_No) return GIGA_OK;
+  CU_TRY(cudaDeviceSynchronize());
+  float** ptrs[] = {&s.tsdf, &s.planes, &s.p, &s.pt, &s.qual, &s.rot, &s.width, &s.occ};
+  for (float** q : ptrs) { if (*q) cudaFree(*q); *q = nullptr; }
+  const int cB = B > s.cap_B ? B : s.cap_B, cg = Ng > s.cap_Ng ? Ng : s.cap_Ng, co = No > s.cap_No ? No : s.cap_No;
+  const size_t ng = (size_t)cB * (cg > 0 ? cg : 1), no = (size_t)cB * (co > 0 ? co : 1);
+  CU_TRY(cudaMalloc(&s.tsdf, sizeof(float) * (size_t)cB * G3));
+  CU_TRY(cudaMalloc(&s.planes, sizeof(float) * 3 * (size_t)cB * G2 * C));
+  CU_TRY(cudaMalloc(&s.p, sizeof(float) * ng * 3));
+  CU_TRY(cudaMalloc(&s.pt, sizeof(float) * no * 3));
+  CU_TRY(cudaMalloc(&s.qual, sizeof(float) * ng));
+  CU_TRY(cudaMalloc(&s.rot, sizeof(float) * ng * 4));
+  CU_TRY(cudaMalloc(&s.width, sizeof(float) * ng));
+  CU_TRY(cudaMalloc(&s.occ, sizeof(float) * no));
+  s.cap_B = cB; s.cap_Ng = cg; s.cap_No = co;
+  return GIGA_OK;
+}
+
+// H2D on `sin`, compute on `sc`, D2H on `sout`; when the three are one stream the event waits are no-ops.
+int enqueue_host_request(giga_ctx* ctx, giga_ctx::HostSlot& s, const float* tsdf, int B, const float* p, int Ng, const float* p_tsdf,
+                         int No, float* qual, float* rot, float* width, float* occ, cudaStream_t sin, cudaStream_t sc, cudaStream_t sout) {
   const bool grasp = p && Ng > 0, geo = p_tsdf && No > 0;
-  if (!grasp && !geo) return fail(GIGA_EINVAL, "giga_forward_host: no query points");
-  if (grasp && (!qual || !rot || !width)) return fail(GIGA_EINVAL, "giga_forward_host: grasp outputs are null");
-  if (geo && !occ) return fail(GIGA_EINVAL, "giga_forward_host: occ output is null");
-  if (int r = set_device(ctx)) return r;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (B > ctx->hcap_B || Ng > ctx->hcap_Ng || No > ctx->hcap_No) {
-    CU_TRY(cudaDeviceSynchronize());
-    float** ptrs[] = {&ctx->h_tsdf, &ctx->h_planes, &ctx->h_p, &ctx->h_pt, &ctx->h_qual, &ctx->h_rot, &ctx->h_width, &ctx->h_occ};
-    for (float** q : ptrs) { if (*q) cudaFree(*q); *q = nullptr; }
-    const int cB = B > ctx->hcap_B ? B : ctx->hcap_B, cg = Ng > ctx->hcap_Ng ? Ng : ctx->hcap_Ng, co = No > ctx->hcap_No ? No : ctx->hcap_No;
-    const size_t ng = (size_t)cB * (cg > 0 ? cg : 1), no = (size_t)cB * (co > 0 ? co : 1);
-    CU_TRY(cudaMalloc(&ctx->h_tsdf, sizeof(float) * (size_t)cB * G3));
-    CU_TRY(cudaMalloc(&ctx->h_planes, sizeof(float) * 3 * (size_t)cB * G2 * C));
-    CU_TRY(cudaMalloc(&ctx->h_p, sizeof(float) * ng * 3));
-    CU_TRY(cudaMalloc(&ctx->h_pt, sizeof(float) * no * 3));
-    CU_TRY(cudaMalloc(&ctx->h_qual, sizeof(float) * ng));
-    CU_TRY(cudaMalloc(&ctx->h_rot, sizeof(float) * ng * 4));
-    CU_TRY(cudaMalloc(&ctx->h_width, sizeof(float) * ng));
-    CU_TRY(cudaMalloc(&ctx->h_occ, sizeof(float) * no));
-    ctx->hcap_B = cB; ctx->hcap_Ng = cg; ctx->hcap_No = co;
+  CU_TRY(cudaMemcpyAsync(s.tsdf, tsdf, sizeof(float) * (size_t)B * G3, cudaMemcpyHostToDevice, sin));
+  if (grasp) CU_TRY(cudaMemcpyAsync(s.p, p, sizeof(float) * (size_t)B * Ng * 3, cudaMemcpyHostToDevice, sin));
+  if (geo) CU_TRY(cudaMemcpyAsync(s.pt, p_tsdf, sizeof(float) * (size_t)B * No * 3, cudaMemcpyHostToDevice, sin));
+  if (sin != sc) {
+    CU_TRY(cudaEventRecord(s.ev_in, sin));
+    CU_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
   }
-  CU_TRY(cudaMemcpyAsync(ctx->h_tsdf, tsdf, sizeof(float) * (size_t)B * G3, cudaMemcpyHostToDevice, st));
-  if (grasp) CU_TRY(cudaMemcpyAsync(ctx->h_p, p, sizeof(float) * (size_t)B * Ng * 3, cudaMemcpyHostToDevice, st));
-  if (geo) CU_TRY(cudaMemcpyAsync(ctx->h_pt, p_tsdf, sizeof(float) * (size_t)B * No * 3, cudaMemcpyHostToDevice, st));
-  if (int r = giga_encode(ctx, ctx->h_tsdf, B, ctx->h_planes, stream)) return r;
+  if (int r = giga_encode(ctx, s.tsdf, B, s.planes, sc)) return r;
   if (grasp) {
     const unsigned hm = ctx->heads & (GIGA_HEAD_QUAL | GIGA_HEAD_ROT | GIGA_HEAD_WIDTH);
-    if (int r = giga_decode(ctx, ctx->h_planes, B, ctx->h_p, Ng, hm, ctx->h_qual, ctx->h_rot, ctx->h_width, nullptr, stream)) return r;
-    CU_TRY(cudaMemcpyAsync(qual, ctx->h_qual, sizeof(float) * (size_t)B * Ng, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(rot, ctx->h_rot, sizeof(float) * (size_t)B * Ng * 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(width, ctx->h_width, sizeof(float) * (size_t)B * Ng, cudaMemcpyDeviceToHost, st));
+    if (int r = giga_decode(ctx, s.planes, B, s.p, Ng, hm, s.qual, s.rot, s.width, nullptr, sc)) return r;
   }
-  if (geo) {
-    if (int r = giga_decode(ctx, ctx->h_planes, B, ctx->h_pt, No, GIGA_HEAD_TSDF, nullptr, nullptr, nullptr, ctx->h_occ, stream)) return r;
-    CU_TRY(cudaMemcpyAsync(occ, ctx->h_occ, sizeof(float) * (size_t)B * No, cudaMemcpyDeviceToHost, st));
+  if (geo)
+    if (int r = giga_decode(ctx, s.planes, B, s.pt, No, GIGA_HEAD_TSDF, nullptr, nullptr, nullptr, s.occ, sc)) return r;
+  if (sc != sout) {
+    CU_TRY(cudaEventRecord(s.ev_compute, sc));
+    CU_TRY(cudaStreamWaitEvent(sout, s.ev_compute, 0));
   }
+  if (grasp) {
+    CU_TRY(cudaMemcpyAsync(qual, s.qual, sizeof(float) * (size_t)B * Ng, cudaMemcpyDeviceToHost, sout));
+    CU_TRY(cudaMemcpyAsync(rot, s.rot, sizeof(float) * (size_t)B * Ng * 4, cudaMemcpyDeviceToHost, sout));
+    CU_TRY(cudaMemcpyAsync(width, s.width, sizeof(float) * (size_t)B * Ng, cudaMemcpyDeviceToHost, sout));
+  }
+  if (geo) CU_TRY(cudaMemcpyAsync(occ, s.occ, sizeof(float) * (size_t)B * No, cudaMemcpyDeviceToHost, sout));
+  return GIGA_OK;
+}
+
+int check_host_args(const float* tsdf, int B, const float* p, int Ng, const float* p_tsdf, int No, float* qual, float* rot,
+                    float* width, float* occ, const char* who) {
+  if (!tsdf || B <= 0) return fail(GIGA_EINVAL, std::string(who) + ": bad argument");
+  const bool grasp = p && Ng > 0, geo = p_tsdf && No > 0;
+  if (!grasp && !geo) return fail(GIGA_EINVAL, std::string(who) + ": no query points");
+  if (grasp && (!qual || !rot || !width)) return fail(GIGA_EINVAL, std::string(who) + ": grasp outputs are null");
+  if (geo && !occ) return fail(GIGA_EINVAL, std::string(who) + ": occ output is null");
+  return GIGA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int giga_forward_host(giga_ctx* ctx, const float* tsdf, int B, const float* p, int Ng, const float* p_tsdf, int No,
+                      float* qual, float* rot, float* width, float* occ, void* stream) {
+  if (!ctx) return fail(GIGA_EINVAL, "giga_forward_host: ctx is null");
+  if (int r = check_host_args(tsdf, B, p, Ng, p_tsdf, No, qual, rot, width, occ, "giga_forward_host")) return r;
+  if (int r = set_device(ctx)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  giga_ctx::HostSlot& s = ctx->slot[2];
+  if (int r = ensure_slot(ctx, s, B, Ng, No)) return r;
+  if (int r = enqueue_host_request(ctx, s, tsdf, B, p, Ng, p_tsdf, No, qual, rot, width, occ, st, st, st)) return r;
   CU_TRY(cudaStreamSynchronize(st));
+  return GIGA_OK;
+}
+
+int giga_forward_host_submit(giga_ctx* ctx, int slot, const float* tsdf, int B, const float* p, int Ng, const float* p_tsdf, int No,
+                             float* qual, float* rot, float* width, float* occ) {
+  if (!ctx || slot < 0 || slot > 1) return fail(GIGA_EINVAL, "giga_forward_host_submit: bad ctx / slot (0 or 1)");
+  if (int r = check_host_args(tsdf, B, p, Ng, p_tsdf, No, qual, rot, width, occ, "giga_forward_host_submit")) return r;
+  if (int r = set_device(ctx)) return r;
+  giga_ctx::HostSlot& s = ctx->slot[slot];
+  if (s.pending) return fail(GIGA_ESTATE, "giga_forward_host_submit: slot still in flight (call giga_forward_host_wait first)");
+  if (!ctx->st_compute) {
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->st_compute, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking));
+  }
+  if (!s.ev_in) {
+    CU_TRY(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&s.ev_compute, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+  }
+  if (int r = ensure_slot(ctx, s, B, Ng, No)) return r;
+  if (int r = ensure_workspace(ctx, B)) return r;   // never (re)allocate while the other slot computes
+  if (int r = enqueue_host_request(ctx, s, tsdf, B, p, Ng, p_tsdf, No, qual, rot, width, occ, ctx->st_h2d, ctx->st_compute, ctx->st_d2h))
+    return r;
+  CU_TRY(cudaEventRecord(s.ev_done, ctx->st_d2h));
+  s.pending = true;
+  return GIGA_OK;
+}
+
+int giga_forward_host_wait(giga_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot > 1) return fail(GIGA_EINVAL, "giga_forward_host_wait: bad ctx / slot");
+  giga_ctx::HostSlot& s = ctx->slot[slot];
+  if (!s.pending) return fail(GIGA_ESTATE, "giga_forward_host_wait: nothing submitted on this slot");
+  CU_TRY(cudaEventSynchronize(s.ev_done));
+  s.pending = false;
   return GIGA_OK;
 }
 
@@ -746,7 +845,7 @@ long giga_ctx_timing_report(giga_ctx* ctx, char* buf, long cap) {
 
 long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity, void* stream) {
   if (!ctx || !name || !dst) return fail(GIGA_EINVAL, "giga_debug_copy: bad argument");
-  if (ctx->last_B <= 0) return fail(GIGA_ESTATE, "giga_debug_copy: no giga_encode call yet");
+  if (ctx->last_B <= 0 && strcmp(name, "timeline")) return fail(GIGA_ESTATE, "giga_debug_copy: no giga_encode call yet");
   if (int r = set_device(ctx)) return r;
   const float* src = nullptr;
   long numel = 0;

@@ -348,6 +348,26 @@ class _GigaBase(nn.Module):
         return out if No else out[:3]
 
 
+    # pipelined host path (serving loops): submit to slot 0/1, wait later; copies overlap the other slot's kernels
+    def forward_host_submit(self, slot: int, tsdf: torch.Tensor, p: Optional[torch.Tensor], p_tsdf: Optional[torch.Tensor], out):
+        eng = self._engine()
+        for t in (tsdf, p, p_tsdf) + tuple(out):
+            if t is not None and t.numel() and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_pinned()):
+                raise _lib.GigaError("forward_host_submit takes contiguous pinned fp32 host tensors")
+        B = tsdf.shape[0]
+        Ng = p.shape[1] if p is not None else 0
+        No = p_tsdf.shape[1] if p_tsdf is not None else 0
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
+        check(lib.giga_forward_host_submit(eng.h, slot, ptr(tsdf), B, ptr(p), Ng, ptr(p_tsdf), No, ptr(out[0]), ptr(out[1]),
+                                           ptr(out[2]), ptr(out[3])), "giga_forward_host_submit")
+        self.__dict__.setdefault("_inflight", {})[slot] = (tsdf, p, p_tsdf, out)   # keep the host buffers alive
+
+    def forward_host_wait(self, slot: int):
+        eng = self._engine()
+        check(lib.giga_forward_host_wait(eng.h, slot), "giga_forward_host_wait")
+        return self.__dict__.get("_inflight", {}).pop(slot, (None, None, None, None))[3]
+
+
 class ConvolutionalOccupancyNetwork(_GigaBase):
     """Drop-in for conv_onet/models/__init__.py:15-164 (giga, giga_aff, giga_detach)."""
 

@@ -104,6 +104,15 @@ int giga_scene_argmax(giga_ctx *ctx, const float *qual, int B, int N, float *bes
 int giga_forward_host(giga_ctx *ctx, const float *tsdf, int B, const float *p, int Ng, const float *p_tsdf, int No,
                       float *qual, float *rot, float *width, float *occ, void *stream);
 
+/* pipelined variant of giga_forward_host for serving loops: two request slots.  submit() enqueues the
+ * H2D copies on a copy stream, the kernels on the ctx's compute stream and the D2H copies on a third
+ * stream (event-chained) and returns at once; wait() blocks until that slot's results are in the host
+ * buffers.  With two slots in flight the PCIe copies of request i+1 / i-1 overlap the kernels of
+ * request i.  Host buffers must be pinned and stay valid until wait() returns. */
+int giga_forward_host_submit(giga_ctx *ctx, int slot, const float *tsdf, int B, const float *p, int Ng, const float *p_tsdf, int No,
+                             float *qual, float *rot, float *width, float *occ);
+int giga_forward_host_wait(giga_ctx *ctx, int slot);
+
 /* introspection ------------------------------------------------------------------- */
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 long giga_ctx_launch_count(const giga_ctx *ctx);

@@ -141,6 +141,23 @@ def test_forward_host_equals_device_path(net):
             assert not b.is_cuda and torch.equal(a.cpu(), b)
         host2 = net.forward_host(x, p, None)  # pageable host memory, grasp heads only
         assert len(host2) == 3 and torch.equal(host2[0], host[0])
+        # pipelined submit/wait: two slots in flight, results identical to the synchronous path
+        xs2, ps2, pts2 = O.seeded_inputs(3, 300, seed=10)
+        dev2 = net(xs2.to(DEV), ps2.to(DEV), p_tsdf=pts2.to(DEV))
+        pin = lambda *s: torch.empty(s, dtype=torch.float32).pin_memory()
+        outs = [(pin(3, 300), pin(3, 300, 4), pin(3, 300), pin(3, 300)) for _ in range(2)]
+        net.forward_host_submit(0, x.pin_memory(), p.pin_memory(), pt.pin_memory(), outs[0])
+        net.forward_host_submit(1, xs2.pin_memory(), ps2.pin_memory(), pts2.pin_memory(), outs[1])
+        with pytest.raises(Exception):
+            net.forward_host_submit(0, x.pin_memory(), p.pin_memory(), pt.pin_memory(), outs[0])   # slot busy
+        net.forward_host_wait(0)
+        net.forward_host_wait(1)
+        for a, b in zip(dev, outs[0]):
+            assert torch.equal(a.cpu(), b)
+        for a, b in zip(dev2, outs[1]):
+            assert torch.equal(a.cpu(), b)
+        with pytest.raises(Exception):
+            net.forward_host_wait(0)   # nothing in flight
 
 
 def test_scene_argmax(net):
