@@ -252,6 +252,9 @@ def main():
         houts = (hout, hout2)
         for i in range(3):
             net.forward_host(hx[i % 2], hp[i % 2], hpt[i % 2], out=hout)
+        for i in range(4):   # warm the pipelined path too (stream / slot creation happens on first use)
+            net.forward_host_submit(i % 2, hx[i % 2], hp[i % 2], hpt[i % 2], houts[i % 2])
+            net.forward_host_wait(i % 2)
         fence()
         # serving loop through the pipelined host entry point: every step's H2D, kernels and D2H are inside the
         # timed region; step i+1's input copy and step i-1's result copy overlap step i's kernels (two slots)

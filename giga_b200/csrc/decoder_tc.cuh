@@ -69,6 +69,17 @@ __device__ __forceinline__ void issue_k32_split3(uint32_t d_tmem, uint32_t a_hi,
   }
 }
 
+// one of the three 3xTF32 products of a 32x32 layer (kind 0: hi*hi, 1: lo*hi, 2: hi*lo) -> accumulator d_tmem + 32*kind.
+// Issued by three different warps concurrently: a single thread only issues one small MMA every ~85 cycles.
+__device__ __forceinline__ void issue_k32_one(int kind, uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                              uint32_t b_kstride, uint32_t idesc) {
+  const uint32_t a = kind == 1 ? a_lo : a_hi, b = kind == 2 ? b_lo : b_hi;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    tc::mma_tf32(d_tmem + 32 * kind, tc::make_desc(a + ks * 2 * TD_KS_A, TD_KS_A, 128), tc::make_desc(b + ks * 2 * b_kstride, b_kstride, 128),
+                 idesc, ks > 0 ? 1u : 0u);
+}
+
 // sum of the three partial accumulators of a 32x32 layer for this thread's row
 __device__ __forceinline__ void tmem_ld32_sum3(uint32_t taddr, float* v) {
   float a[32];
@@ -130,6 +141,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TD_OFF_BAR);       // MMA completion
   uint64_t* wbar = bar + 1;                                             // [2] chain-weight buffers landed
   uint64_t* pbar = bar + 3;                                             // fc_c plane slice landed
+  uint64_t* bar3 = bar + 4;                                             // 32x32 layer: three issuing warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TD_OFF_BAR + 40);
 
   const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -151,7 +163,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   stamp();   // 0: start
   if (warp == 0) tc::tmem_alloc(tmem_slot, TD_TMEM_COLS);
   if (tid == 0) {
-    tc::mbar_init(bar, 1); tc::mbar_init(&wbar[0], 1); tc::mbar_init(&wbar[1], 1); tc::mbar_init(pbar, 1);
+    tc::mbar_init(bar, 1); tc::mbar_init(&wbar[0], 1); tc::mbar_init(&wbar[1], 1); tc::mbar_init(pbar, 1); tc::mbar_init(bar3, 3);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
@@ -203,7 +215,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   const uint32_t a_hi = tc::smem_u32(sAhi), a_lo = tc::smem_u32(sAlo), w_s = tc::smem_u32(sW);
   constexpr uint32_t IDESC_160 = tc::make_idesc_tf32(128, 160);
   constexpr uint32_t IDESC_32 = tc::make_idesc_tf32(128, 32);
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase3 = 0;
 
   // Weight staging is asynchronous (cp.async.bulk + mbarrier, issued by one elected lane of warp 0):
   //   chain block i+1 is prefetched while block i computes (buffers: dedicated WB0 / the start of sW),
@@ -296,16 +308,16 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       __syncthreads();
       tc::mbar_wait(&wbar[wb], wuse[wb] & 1u);         // this block's weights have landed (all threads: they read b0/b1)
       ++wuse[wb];
-      if (warp == 0) {
+      if (warp < 3) {
         tc::fence_after_sync();
         if (tc::elect_one()) {
-          issue_k32_split3(tmem + 160, a_hi, a_lo, w_b, w_b + 4096, TD_KS_W, IDESC_32);   // fc_0
-          tc::mma_commit(bar);
+          issue_k32_one(warp, tmem + 160, a_hi, a_lo, w_b, w_b + 4096, TD_KS_W, IDESC_32);   // fc_0
+          tc::mma_commit(bar3);
         }
         __syncwarp();
       }
-      tc::mbar_wait(bar, phase);
-      phase ^= 1u;
+      tc::mbar_wait(bar3, phase3);
+      phase3 ^= 1u;
       tc::fence_after_sync();
       const float* bs = reinterpret_cast<const float*>(wbuf) + 4096;   // b0[32], b1[32]
       tmem_ld32_sum3(tmem_row + 160, v);
@@ -315,16 +327,16 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       tc::fence_smem_to_async();
       tc::fence_before_sync();
       __syncthreads();
-      if (warp == 0) {
+      if (warp < 3) {
         tc::fence_after_sync();
         if (tc::elect_one()) {
-          issue_k32_split3(tmem + 160, a_hi, a_lo, w_b + 8192, w_b + 12288, TD_KS_W, IDESC_32);   // fc_1
-          tc::mma_commit(bar);
+          issue_k32_one(warp, tmem + 160, a_hi, a_lo, w_b + 8192, w_b + 12288, TD_KS_W, IDESC_32);   // fc_1
+          tc::mma_commit(bar3);
         }
         __syncwarp();
       }
-      tc::mbar_wait(bar, phase);
-      phase ^= 1u;
+      tc::mbar_wait(bar3, phase3);
+      phase3 ^= 1u;
       tc::fence_after_sync();
       tmem_ld32_sum3(tmem_row + 160, v);
 #pragma unroll

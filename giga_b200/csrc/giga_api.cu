@@ -61,6 +61,18 @@ using T_u1up = TallCfg<20, 64, 0, 32, 32, 2, 1, false>;
 using T_u1c1 = TallCfg<40, 32, 32, 32, 32, 2, 0, false>;
 using T_u1c2 = TallCfg<40, 32, 0, 32, 32, 2, 0, true>;
 
+// persistent variants (one CTA per SM): <cfg, stages, resident weights>
+using P_c40 = PersistCfg<T_c40, 4, true>;
+using P_d1c1 = PersistCfg<T_d1c1, 4, false>;
+using P_c20 = PersistCfg<T_c20, 4, false>;
+using P_d2c1 = PersistCfg<T_d2c1, 4, false>;
+using P_d2c2 = PersistCfg<T_d2c2, 4, false>;
+using P_u0up = PersistCfg<T_u0up, 4, false>;
+using P_u0c1 = PersistCfg<T_u0c1, 4, false>;
+using P_u1up = PersistCfg<T_u1up, 4, false>;
+using P_u1c1 = PersistCfg<T_u1c1, 3, true>;
+using P_u1c2 = PersistCfg<T_u1c2, 4, true>;
+
 struct ParamSpec {
   const char* name;
   long numel;
@@ -122,6 +134,7 @@ struct giga_ctx {
   int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int encoder_impl = 1;      // U-Net convs: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int last_impl = 0;
+  int num_sms = 148;
   const char* timeline_layer = nullptr;   // debug (env GIGA_TIMELINE=<kernel name>): in-kernel phase timestamps
   unsigned long long* d_timeline = nullptr;
   long timeline_n = 0;
@@ -197,6 +210,11 @@ int ensure_attrs(giga_ctx* ctx) {
   SET_TC(T_c40); SET_TC(T_d1c1); SET_TC(T_c20); SET_TC(T_d2c1); SET_TC(T_d2c2); SET_TC(T_u0up); SET_TC(T_u0c1); SET_TC(T_u1up);
   SET_TC(T_u1c1); SET_TC(T_u1c2);
 #undef SET_TC
+#define SET_P(P) CU_TRY(cudaFuncSetAttribute(conv_tall_persistent_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES))
+  SET_P(P_c40); SET_P(P_d1c1); SET_P(P_c20); SET_P(P_d2c1); SET_P(P_d2c2); SET_P(P_u0up); SET_P(P_u0c1); SET_P(P_u1up); SET_P(P_u1c1);
+  SET_P(P_u1c2);
+#undef SET_P
+  CU_TRY(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
   CU_TRY(cudaFuncSetAttribute(convT2x2_kernel<K_u0up>, cudaFuncAttributeMaxDynamicSharedMemorySize, K_u0up::SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(convT2x2_kernel<K_u1up>, cudaFuncAttributeMaxDynamicSharedMemorySize, K_u1up::SMEM_BYTES));
   ctx->attrs_set = true;
@@ -261,6 +279,18 @@ void launch_tall(giga_ctx* ctx, const char* name, int n_img, const TallBuf& s0, 
   }
   conv_tall_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(s0.p, s0.ps, s1.p, s1.ps, w, bias, out.p, out.ps,
                                                                 ctx->d_enc + ctx->el.tc_fin, ctx->d_enc + ctx->el.fin_b, fin_out, n_img, tl);
+}
+
+template <class P>
+void launch_persist(giga_ctx* ctx, const char* name, int n_img, const TallBuf& s0, const TallBuf& s1, const float* w,
+                    const float* bias, const TallBuf& out, float* fin_out, cudaStream_t st) {
+  using K = typename P::K;
+  const int n_groups = K::num_ctas(n_img), n_items = n_groups * K::NNT;
+  const int grid = n_items < ctx->num_sms ? n_items : ctx->num_sms;
+  LaunchScope ls(ctx, name, st);
+  conv_tall_persistent_kernel<P><<<grid, P::NTHREADS, P::SMEM_BYTES, st>>>(s0.p, s0.ps, s1.p, s1.ps, w, bias, out.p, out.ps,
+                                                                           ctx->d_enc + ctx->el.tc_fin, ctx->d_enc + ctx->el.fin_b,
+                                                                           fin_out, n_img, n_groups);
 }
 
 template <class K>
@@ -554,8 +584,8 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
         *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),
         *u0 = act(ctx, "u0"), *u0c1 = act(ctx, "u0c1"), *u0c2 = act(ctx, "u0c2"), *u1 = act(ctx, "u1"),
         *u1c1 = act(ctx, "u1c1"), *u1c2 = act(ctx, "u1c2");
-  if (ctx->encoder_impl == 1) {
-    // tensor-core U-Net on TALL pre-split activations (unet_tall.cuh)
+  if (ctx->encoder_impl >= 1) {
+    // tensor-core U-Net on TALL pre-split activations (unet_tall.cuh); 1 = persistent kernels, 2 = one CTA per tile
     auto tb = [&](const char* nm) {
       TallBuf t;
       if (!strcmp(nm, "pre")) { t.p = ctx->d_tall[0]; t.ps = ctx->tall_ps[0]; return t; }
@@ -570,26 +600,49 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
       LaunchScope ls(ctx, "nchw_to_tall:pre", st);
       nchw_to_tall_kernel<40, 8><<<ceil_div(n_img * 8 * G2, 256), 256, 0, st>>>(ctx->d_pre, tb("pre").p, tb("pre").ps, n_img);
     }
-    launch_tall<T_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st);
-    launch_tall<T_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st);
-    {
-      LaunchScope ls(ctx, "maxpool:p0", st);
-      pool_tall_kernel<20, 8><<<ceil_div(n_img * 8 * 400, 256), 256, 0, st>>>(tb("d0c2").p, tb("d0c2").ps, tb("p0").p, tb("p0").ps, n_img);
+    if (ctx->encoder_impl == 1) {
+      launch_persist<P_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st);
+      launch_persist<P_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st);
+      {
+        LaunchScope ls(ctx, "maxpool:p0", st);
+        pool_tall_kernel<20, 8><<<ceil_div(n_img * 8 * 400, 256), 256, 0, st>>>(tb("d0c2").p, tb("d0c2").ps, tb("p0").p, tb("p0").ps, n_img);
+      }
+      launch_persist<P_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st);
+      launch_persist<P_c20>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st);
+      {
+        LaunchScope ls(ctx, "maxpool:p1", st);
+        pool_tall_kernel<10, 16><<<ceil_div(n_img * 16 * 100, 256), 256, 0, st>>>(tb("d1c2").p, tb("d1c2").ps, tb("p1").p, tb("p1").ps, n_img);
+      }
+      launch_persist<P_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st);
+      launch_persist<P_d2c2>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st);
+      launch_persist<P_u0up>(ctx, "convT:u0", n_img, tb("d2c2"), none, E + L.tc_up[0], E + L.up_b[0], tb("u0"), nullptr, st);
+      launch_persist<P_u0c1>(ctx, "conv3x3:u0c1", n_img, tb("u0"), tb("d1c2"), E + L.tc_conv[6], E + L.bias[6], tb("u0c1"), nullptr, st);
+      launch_persist<P_c20>(ctx, "conv3x3:u0c2", n_img, tb("u0c1"), none, E + L.tc_conv[7], E + L.bias[7], tb("u0c2"), nullptr, st);
+      launch_persist<P_u1up>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st);
+      launch_persist<P_u1c1>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st);
+      launch_persist<P_u1c2>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st);
+    } else {
+      launch_tall<T_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st);
+      launch_tall<T_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st);
+      {
+        LaunchScope ls(ctx, "maxpool:p0", st);
+        pool_tall_kernel<20, 8><<<ceil_div(n_img * 8 * 400, 256), 256, 0, st>>>(tb("d0c2").p, tb("d0c2").ps, tb("p0").p, tb("p0").ps, n_img);
+      }
+      launch_tall<T_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st);
+      launch_tall<T_c20>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st);
+      {
+        LaunchScope ls(ctx, "maxpool:p1", st);
+        pool_tall_kernel<10, 16><<<ceil_div(n_img * 16 * 100, 256), 256, 0, st>>>(tb("d1c2").p, tb("d1c2").ps, tb("p1").p, tb("p1").ps, n_img);
+      }
+      launch_tall<T_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st);
+      launch_tall<T_d2c2>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st);
+      launch_tall<T_u0up>(ctx, "convT:u0", n_img, tb("d2c2"), none, E + L.tc_up[0], E + L.up_b[0], tb("u0"), nullptr, st);
+      launch_tall<T_u0c1>(ctx, "conv3x3:u0c1", n_img, tb("u0"), tb("d1c2"), E + L.tc_conv[6], E + L.bias[6], tb("u0c1"), nullptr, st);
+      launch_tall<T_c20>(ctx, "conv3x3:u0c2", n_img, tb("u0c1"), none, E + L.tc_conv[7], E + L.bias[7], tb("u0c2"), nullptr, st);
+      launch_tall<T_u1up>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st);
+      launch_tall<T_u1c1>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st);
+      launch_tall<T_u1c2>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st);
     }
-    launch_tall<T_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st);
-    launch_tall<T_c20>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st);
-    {
-      LaunchScope ls(ctx, "maxpool:p1", st);
-      pool_tall_kernel<10, 16><<<ceil_div(n_img * 16 * 100, 256), 256, 0, st>>>(tb("d1c2").p, tb("d1c2").ps, tb("p1").p, tb("p1").ps, n_img);
-    }
-    launch_tall<T_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st);
-    launch_tall<T_d2c2>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st);
-    launch_tall<T_u0up>(ctx, "convT:u0", n_img, tb("d2c2"), none, E + L.tc_up[0], E + L.up_b[0], tb("u0"), nullptr, st);
-    launch_tall<T_u0c1>(ctx, "conv3x3:u0c1", n_img, tb("u0"), tb("d1c2"), E + L.tc_conv[6], E + L.bias[6], tb("u0c1"), nullptr, st);
-    launch_tall<T_c20>(ctx, "conv3x3:u0c2", n_img, tb("u0c1"), none, E + L.tc_conv[7], E + L.bias[7], tb("u0c2"), nullptr, st);
-    launch_tall<T_u1up>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st);
-    launch_tall<T_u1c1>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st);
-    launch_tall<T_u1c2>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st);
     ctx->last_B = B;
     ctx->last_impl = 1;
     CU_TRY(cudaGetLastError());
@@ -802,7 +855,7 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
     return GIGA_OK;
   }
   if (!strcmp(key, "encoder_impl")) {
-    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "encoder_impl must be 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
+    if (value < 0 || value > 2) return fail(GIGA_EINVAL, "encoder_impl must be 0 (fp32 FMA), 1 (tcgen05 persistent) or 2 (tcgen05 per-tile)");
     ctx->encoder_impl = value;
     return GIGA_OK;
   }

@@ -427,4 +427,302 @@ conv_tall_kernel(const float* __restrict__ src0, long ps0,   // TALL [2][CIN0/4]
   }
 }
 
+
+// =====================================================================================================
+// Persistent variant: one CTA per SM walks a strided list of work items (M-tile group x N tile) so that
+//   * the bulk-copy ring never drains between tiles (first-load latency paid once per CTA, not per tile),
+//   * the epilogue of tile t (drain warps) overlaps the MMAs of tile t+1 (control warp runs up to two
+//     chunks ahead through the alternating accumulator sets X/Y; the correction sets are double-buffered
+//     across tiles),
+//   * for the 40^2 layers the whole layer's weights (<= 147 KB) stay resident in shared memory (WRES).
+// Same arithmetic / operand layouts / accuracy scheme as conv_tall_kernel above.
+template <class K_, int S_, bool WRES_>
+struct PersistCfg {
+  using K = K_;
+  static constexpr int S = S_;
+  static constexpr bool WRES = WRES_;
+  static constexpr int W_BYTES = WRES ? K::NC * K::B_BYTES : 0;                 // resident weights (one N tile)
+  static constexpr int STAGE_BYTES = K::A_BYTES + (WRES ? 0 : K::B_BYTES);
+  static constexpr int OFF_STAGES = W_BYTES;
+  static constexpr int OFF_FIN = OFF_STAGES + S * STAGE_BYTES;                   // conv_final scratch (FUSE_FINAL)
+  static constexpr int FIN_BYTES = K::FUSE_FINAL ? 2 * K::FIN_A_BYTES + 8192 : 0;
+  static constexpr int OFF_BIAS = OFF_FIN + FIN_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + 64 * 4;
+  static constexpr int NBAR = 2 * S + 10;                                        // full[S] empty[S] acc_full[2] acc_empty[2] z_full[2] z_empty[2] wbar fin
+  static constexpr int NTHREADS = 256;                                           // 4 drain warps + loader warp + 3 MMA-issue warps
+  static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+  static constexpr int ACC = K::ACC;
+  static constexpr int TMEM_COLS = 512;                                          // X Y | Z1a Z2a | Z1b Z2b | final  (6*ACC + 32 <= 512)
+  static_assert(6 * ACC + 32 <= 512, "TMEM");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+  static_assert(!WRES || K::NNT == 1, "resident weights cover one N tile");
+};
+
+// A single thread issues a 128xNTILEx8 tcgen05.mma only every ~85 cycles (measured, profiles/r01i: one issuing
+// warp per SM ran at 93 cycles/MMA) while the MMA itself is shared-memory-bound at ~40 cycles, so three
+// warps issue concurrently: warp 5 the hi*hi products (drained sets X/Y), warps 6/7 the two correction
+// products (sets Z1/Z2).  Warp 4 only moves data (bulk copies), warps 0-3 drain and run the epilogue.
+// grid (min(#items, #SMs)), block 256, dynamic smem P::SMEM_BYTES, 1 CTA / SM
+template <class P>
+__global__ void __launch_bounds__(256, 1)
+conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const float* __restrict__ src1, long ps1,
+                            const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out, long pso,
+                            const float* __restrict__ fin_w, const float* __restrict__ fin_b, float* __restrict__ fin_out,
+                            int n_img, int n_groups) {
+  using K = typename P::K;
+  constexpr int HW = K::HW, WP = K::WP, HP1 = K::HP1, NTILE = K::NTILE, NT = K::NT, ACC = K::ACC, S = P::S, NC = K::NC;
+  extern __shared__ __align__(128) uint8_t smem_pt[];
+  uint8_t* smem = smem_pt;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
+  uint64_t* empty = full + S;
+  uint64_t* acc_full = empty + S;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* z_full = acc_empty + 2;
+  uint64_t* z_empty = z_full + 2;
+  uint64_t* wbar = z_empty + 2;
+  uint64_t* fin_bar = wbar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::OFF_BAR + P::NBAR * 8);
+  float* sbias = reinterpret_cast<float*>(smem + P::OFF_BIAS);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int total_rows = tall_rows(HW, n_img);
+  const int n_items = n_groups * K::NNT;
+  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x + j*gridDim.x
+
+  if (warp == 4) tc::tmem_alloc(tmem_slot, P::TMEM_COLS);
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 3); }   // 3 MMA warps release a stage
+    tc::mbar_init(&acc_full[0], 1); tc::mbar_init(&acc_full[1], 1);
+    tc::mbar_init(&acc_empty[0], 128); tc::mbar_init(&acc_empty[1], 128);
+    tc::mbar_init(&z_full[0], 2); tc::mbar_init(&z_full[1], 2);
+    tc::mbar_init(&z_empty[0], 128); tc::mbar_init(&z_empty[1], 128);
+    tc::mbar_init(wbar, 1); tc::mbar_init(fin_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (K::FUSE_FINAL && tid < 128) {   // conv_final weights: staged once per CTA
+    const float4* wsrc = reinterpret_cast<const float4*>(fin_w);
+    float4* wdst = reinterpret_cast<float4*>(smem + P::OFF_FIN + 2 * K::FIN_A_BYTES);
+    for (int e = tid; e < 512; e += 128) wdst[e] = __ldg(wsrc + e);
+  }
+  tc::fence_smem_to_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int total_chunks = my_items * NC;
+
+  if (warp == 4) {
+    // ============================ loader warp: bulk copies only ============================
+    if (P::WRES && my_items > 0) {   // the layer's weights, resident for the whole kernel (single N tile)
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(wbar, (uint32_t)P::W_BYTES);
+        for (int c = 0; c < NC; ++c)
+          tc::bulk_g2s(smem + c * K::B_BYTES, wt + (size_t)c * (K::B_BYTES / 4), K::B_BYTES, wbar);
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int i = 0; i < total_chunks; ++i) {   // i = flat chunk index of this CTA
+      const int s = i % S, j = i / NC, c = i - j * NC;
+      const int item = (int)blockIdx.x + j * (int)gridDim.x;
+      const int grp = item / K::NNT, nt = item - grp * K::NNT;
+      if (i >= S) tc::mbar_wait(&empty[s], (uint32_t)(((i / S) - 1) & 1));   // all three MMA warps are done with the stage
+      uint8_t* stA = smem + P::OFF_STAGES + s * P::STAGE_BYTES;
+      const int ch0 = c * 8;
+      const float* sp; long ps; int kch, kcn;
+      if (ch0 < K::CIN0) { sp = src0; ps = ps0; kch = ch0 / 4; kcn = K::CIN0 / 4; }
+      else { sp = src1; ps = ps1; kch = (ch0 - K::CIN0) / 4; kcn = K::CIN1 / 4; }
+      const long pos0 = TALL_MARGIN + (long)grp * K::MT - K::HALO;
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)P::STAGE_BYTES);
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+          for (int kc = 0; kc < 2; ++kc)
+            tc::bulk_g2s(stA + (hl * 2 + kc) * K::KS_A, sp + ((size_t)(hl * kcn + kch + kc) * ps + pos0) * 4, K::KS_A, &full[s]);
+        if (!P::WRES) tc::bulk_g2s(stA + K::A_BYTES, wt + ((size_t)nt * NC + c) * (K::B_BYTES / 4), K::B_BYTES, &full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 5) {
+    // ============================ MMA-issue warps: 5 = hi*hi, 6 = lo*hi, 7 = hi*lo ============================
+    constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NTILE);
+    const int kind = warp - 5;
+    if (P::WRES && my_items > 0) tc::mbar_wait(wbar, 0u);
+#pragma unroll 1
+    for (int i = 0; i < total_chunks; ++i) {
+      const int s = i % S, j = i / NC, c = i - j * NC, set = i & 1, zp = j & 1;
+      tc::mbar_wait(&full[s], (uint32_t)((i / S) & 1));
+      if (kind == 0) {
+        if (i >= 2) tc::mbar_wait(&acc_empty[set], (uint32_t)(((i - 2) >> 1) & 1));
+      } else if (c == 0 && j >= 2) {
+        tc::mbar_wait(&z_empty[zp], (uint32_t)(((j - 2) >> 1) & 1));
+      }
+      tc::fence_after_sync();
+      const uint32_t a_hi = tc::smem_u32(smem + P::OFF_STAGES + s * P::STAGE_BYTES), a_lo = a_hi + 2 * K::KS_A;
+      const uint32_t b0 = P::WRES ? tc::smem_u32(smem + c * K::B_BYTES) : a_hi + K::A_BYTES;
+      const uint32_t a_base = kind == 1 ? a_lo : a_hi;
+      const uint32_t b_off = kind == 2 ? 2 * NTILE * 16 : 0;
+      const uint32_t d_base = kind == 0 ? tmem + set * ACC : tmem + 2 * ACC + zp * 2 * ACC + (kind - 1) * ACC;
+      const bool fresh = kind == 0 ? true : (c == 0);   // first MMA of the chain overwrites the accumulator
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int tap = 0; tap < K::NTAPS; ++tap) {
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const uint64_t bd = tc::make_desc(b0 + tap * (4 * NTILE * 16) + b_off, NTILE * 16, 128);
+#pragma unroll
+          for (int mt = 0; mt < NT; ++mt) {
+            const uint32_t aoff = (uint32_t)(mt * 128 + (K::MODE == 0 ? dy * WP + dx : 0)) * 16;
+            tc::mma_tf32(d_base + mt * NTILE, tc::make_desc(a_base + aoff, K::KS_A, 128), bd, IDESC, (fresh && tap == 0) ? 0u : 1u);
+          }
+        }
+        tc::mma_commit(&empty[s]);
+        if (kind == 0) tc::mma_commit(&acc_full[set]);
+        else if (c == NC - 1) tc::mma_commit(&z_full[zp]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ============================ drain + epilogue warps ============================
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t fin_use = 0;
+#pragma unroll 1
+    for (int j = 0; j < my_items; ++j) {
+      const int item = (int)blockIdx.x + j * (int)gridDim.x;
+      const int grp = item / K::NNT, nt_idx = item - grp * K::NNT;
+      const int f0 = grp * K::MT, zp = j & 1;
+      if (tid < NTILE) sbias[tid] = __ldg(bias + (K::MODE == 0 ? nt_idx * NTILE : 0) + tid);
+      float acc[NT][NTILE];
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int q = 0; q < NTILE; ++q) acc[mt][q] = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < NC; ++c) {
+        const int i = j * NC + c, set = i & 1;
+        tc::mbar_wait(&acc_full[set], (uint32_t)((i >> 1) & 1));
+        tc::fence_after_sync();
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+          for (int n0 = 0; n0 < NTILE; n0 += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem_row + set * ACC + mt * NTILE + n0, v);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q];
+          }
+        tc::fence_before_sync();
+        tc::mbar_arrive(&acc_empty[set]);
+      }
+      // the two correction sets of this tile (issued by warps 6 and 7)
+      tc::mbar_wait(&z_full[zp], (uint32_t)((j >> 1) & 1));
+      tc::fence_after_sync();
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int n0 = 0; n0 < NTILE; n0 += 32) {
+          float v[32], w[32];
+          tc::tmem_ld32(tmem_row + 2 * ACC + zp * 2 * ACC + mt * NTILE + n0, v);
+          tc::tmem_ld32(tmem_row + 2 * ACC + zp * 2 * ACC + ACC + mt * NTILE + n0, w);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q] + w[q];
+        }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&z_empty[zp]);
+      tc::named_bar_sync(1, 128);   // sbias visible to all epilogue threads (and previous tile's readers are done)
+
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt) {
+        const int f = f0 + mt * 128 + tid;
+        const int r = f / WP, cc = f - r * WP;
+        const int rr = r - 1, img = rr / HP1, y = rr - img * HP1, x = cc - 1;
+        const bool valid = cc >= 1 && cc <= HW && r >= 1 && r < total_rows && y < HW;
+        if constexpr (K::MODE == 0 && !K::FUSE_FINAL) {
+          if (valid) {
+            const long pos = TALL_MARGIN + f;
+#pragma unroll
+            for (int kc = 0; kc < NTILE / 4; ++kc) {
+              const int co = nt_idx * NTILE + 4 * kc;
+              const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * kc);
+              const float4 v = make_float4(fmaxf(acc[mt][4 * kc + 0] + bv.x, 0.f), fmaxf(acc[mt][4 * kc + 1] + bv.y, 0.f),
+                                           fmaxf(acc[mt][4 * kc + 2] + bv.z, 0.f), fmaxf(acc[mt][4 * kc + 3] + bv.w, 0.f));
+              float4 h, l;
+              split4(v, h, l);
+              st4(out + ((size_t)(co / 4) * pso + pos) * 4, h);
+              st4(out + ((size_t)(K::COUT / 4 + co / 4) * pso + pos) * 4, l);
+            }
+          }
+        } else if constexpr (K::MODE == 1) {
+          if (valid) {
+            const int a = nt_idx >> 1, b = nt_idx & 1;
+            const long pos = TALL_MARGIN + tall_pos(2 * HW, img, 2 * y + a, 2 * x + b);
+#pragma unroll
+            for (int kc = 0; kc < NTILE / 4; ++kc) {
+              const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * kc);
+              const float4 v = make_float4(acc[mt][4 * kc + 0] + bv.x, acc[mt][4 * kc + 1] + bv.y, acc[mt][4 * kc + 2] + bv.z, acc[mt][4 * kc + 3] + bv.w);
+              float4 h, l;
+              split4(v, h, l);
+              st4(out + ((size_t)kc * pso + pos) * 4, h);
+              st4(out + ((size_t)(K::COUT / 4 + kc) * pso + pos) * 4, l);
+            }
+          }
+        } else {
+          uint8_t* fa_hi = smem + P::OFF_FIN;
+          uint8_t* fa_lo = fa_hi + K::FIN_A_BYTES;
+          uint8_t* fw = fa_lo + K::FIN_A_BYTES;
+#pragma unroll
+          for (int kc = 0; kc < 8; ++kc) {
+            const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * kc);
+            const float4 v = make_float4(fmaxf(acc[mt][4 * kc + 0] + bv.x, 0.f), fmaxf(acc[mt][4 * kc + 1] + bv.y, 0.f),
+                                         fmaxf(acc[mt][4 * kc + 2] + bv.z, 0.f), fmaxf(acc[mt][4 * kc + 3] + bv.w, 0.f));
+            float4 h, l;
+            split4(v, h, l);
+            *reinterpret_cast<float4*>(fa_hi + kc * K::FIN_KS + tid * 16) = h;
+            *reinterpret_cast<float4*>(fa_lo + kc * K::FIN_KS + tid * 16) = l;
+          }
+          tc::fence_smem_to_async();
+          tc::fence_before_sync();
+          tc::named_bar_sync(1, 128);
+          if (warp == 0) {
+            tc::fence_after_sync();
+            const uint32_t ah0 = tc::smem_u32(fa_hi), al0 = tc::smem_u32(fa_lo), w0 = tc::smem_u32(fw);
+            constexpr uint32_t ID32 = tc::make_idesc_tf32(128, 32);
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ah = tc::make_desc(ah0 + ks * 2 * K::FIN_KS, K::FIN_KS, 128);
+                const uint64_t al = tc::make_desc(al0 + ks * 2 * K::FIN_KS, K::FIN_KS, 128);
+                const uint64_t bh = tc::make_desc(w0 + ks * 2 * 512, 512, 128);
+                const uint64_t bl = tc::make_desc(w0 + 4096 + ks * 2 * 512, 512, 128);
+                tc::mma_tf32(tmem + 6 * ACC, ah, bh, ID32, ks > 0 ? 1u : 0u);
+                tc::mma_tf32(tmem + 6 * ACC, al, bh, ID32, 1u);
+                tc::mma_tf32(tmem + 6 * ACC, ah, bl, ID32, 1u);
+              }
+              tc::mma_commit(fin_bar);
+            }
+            __syncwarp();
+          }
+          tc::mbar_wait(fin_bar, fin_use & 1u);
+          ++fin_use;
+          tc::fence_after_sync();
+          float v[32];
+          tc::tmem_ld32(tmem_row + 6 * ACC, v);
+          if (valid) {
+            float* op = fin_out + ((size_t)img * (HW * HW) + y * HW + x) * 32;
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              st4(op + q, make_float4(v[q] + __ldg(fin_b + q), v[q + 1] + __ldg(fin_b + q + 1), v[q + 2] + __ldg(fin_b + q + 2),
+                                      v[q + 3] + __ldg(fin_b + q + 3)));
+          }
+          tc::fence_before_sync();
+          tc::named_bar_sync(1, 128);   // scratch / final accumulator free for the next M tile
+        }
+      }
+      tc::named_bar_sync(1, 128);   // everyone is done with sbias before the next item overwrites it
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, P::TMEM_COLS);
+}
+
 }  // namespace giga

@@ -284,12 +284,13 @@ def test_decoder_implementations(oracle_sd, impl):
         assert torch.equal(out[0].argmax(1).cpu(), ref[0].argmax(1))
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_encoder_implementations(oracle_sd, impl):
-    """encoder_impl 0 = fp32 FMA-pipe U-Net convs, 1 = tcgen05 3xTF32 implicit GEMM (default)."""
+    """encoder_impl 0 = fp32 FMA-pipe U-Net convs, 1 = tcgen05 3xTF32 implicit GEMM with persistent CTAs (default),
+    2 = the same arithmetic with one CTA per tile."""
     net = make_net("giga", oracle_sd)
     net._engine().set_option("encoder_impl", impl)
-    for B, seed in ((1, 1), (5, 2)):
+    for B, seed in ((1, 1), (5, 2), (32, 3)):
         x, p, pt = O.seeded_inputs(B, 64, seed=40 + seed)
         with torch.no_grad():
             ref = O.encode_inputs(oracle_sd, x)
