@@ -62,16 +62,16 @@ using T_u1c1 = TallCfg<40, 32, 32, 32, 32, 2, 0, false>;
 using T_u1c2 = TallCfg<40, 32, 0, 32, 32, 2, 0, true>;
 
 // persistent variants (one CTA per SM): <cfg, stages, resident weights>
-using P_c40 = PersistCfg<T_c40, 4, true>;
+using P_c40 = PersistCfg<T_c40, 4, true, true>;
 using P_d1c1 = PersistCfg<T_d1c1, 4, false>;
 using P_c20 = PersistCfg<T_c20, 4, false>;
 using P_d2c1 = PersistCfg<T_d2c1, 4, false>;
 using P_d2c2 = PersistCfg<T_d2c2, 4, false>;
 using P_u0up = PersistCfg<T_u0up, 4, false>;
 using P_u0c1 = PersistCfg<T_u0c1, 4, false>;
-using P_u1up = PersistCfg<T_u1up, 4, false>;
-using P_u1c1 = PersistCfg<T_u1c1, 3, true>;
-using P_u1c2 = PersistCfg<T_u1c2, 4, true>;
+using P_u1up = PersistCfg<T_u1up, 4, false, true>;
+using P_u1c1 = PersistCfg<T_u1c1, 3, true, true>;
+using P_u1c2 = PersistCfg<T_u1c2, 4, true, true>;
 
 struct ParamSpec {
   const char* name;
@@ -287,10 +287,19 @@ void launch_persist(giga_ctx* ctx, const char* name, int n_img, const TallBuf& s
   using K = typename P::K;
   const int n_groups = K::num_ctas(n_img), n_items = n_groups * K::NNT;
   const int grid = n_items < ctx->num_sms ? n_items : ctx->num_sms;
+  unsigned long long* tl = nullptr;
+  if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, name)) {   // debug: per-CTA stall accounting of one layer
+    const size_t n = (size_t)grid * 32;
+    if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+    cudaMalloc(&ctx->d_timeline, n * 8);
+    cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
+    ctx->timeline_n = (long)n;
+    tl = ctx->d_timeline;
+  }
   LaunchScope ls(ctx, name, st);
   conv_tall_persistent_kernel<P><<<grid, P::NTHREADS, P::SMEM_BYTES, st>>>(s0.p, s0.ps, s1.p, s1.ps, w, bias, out.p, out.ps,
                                                                            ctx->d_enc + ctx->el.tc_fin, ctx->d_enc + ctx->el.fin_b,
-                                                                           fin_out, n_img, n_groups);
+                                                                           fin_out, n_img, n_groups, tl);
 }
 
 template <class K>
@@ -303,7 +312,7 @@ void launch_convT(giga_ctx* ctx, const char* name, int n_img, const float* src, 
 
 float tf32_rn_host(float v);
 
-// [ntile][chunk][tap][hi,lo][kc 2][n NTILE][4]; MODE 0 from the reference's Conv2d [co][ci][3][3],
+// [ntile][chunk][tap][kc 2][hi,lo][n NTILE][4]; MODE 0 from the reference's Conv2d [co][ci][3][3],
 // MODE 1 from ConvTranspose2d [ci][co][2][2] with ntile = a*2+b
 template <class K>
 void pack_conv_tc(const float* w, float* dst) {
@@ -319,8 +328,8 @@ void pack_conv_tc(const float* w, float* dst) {
               else v = w[((long)ci * K::COUT + n) * 4 + nt];
               const float hi = tf32_rn_host(v);
               const long base = ((((long)nt * K::NC + c) * K::NTAPS + tap) * 2) * 2 * K::NTILE * 4;
-              dst[base + ((0 * 2 + kc) * K::NTILE + n) * 4 + j] = hi;
-              dst[base + ((1 * 2 + kc) * K::NTILE + n) * 4 + j] = v - hi;
+              dst[base + ((kc * 2 + 0) * K::NTILE + n) * 4 + j] = hi;     // [kc][hi|lo][n][4]
+              dst[base + ((kc * 2 + 1) * K::NTILE + n) * 4 + j] = v - hi;
             }
 }
 

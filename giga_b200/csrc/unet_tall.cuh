@@ -137,7 +137,7 @@ struct TallCfg {
   static constexpr int ROWS_WIN = MT + 2 * HALO;
   static constexpr int KS_A = ROWS_WIN * 16;                 // bytes per staged k-chunk
   static constexpr int A_BYTES = 4 * KS_A;                   // hi kc0, hi kc1, lo kc0, lo kc1
-  static constexpr int B_BYTES = NTAPS * 2 * 2 * NTILE * 16; // [tap][hi|lo][kc][n][4]
+  static constexpr int B_BYTES = NTAPS * 2 * 2 * NTILE * 16; // [tap][kc][hi|lo][n][4]
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NNT = MODE == 0 ? COUT / NTILE : 4;   // grid.y
   static constexpr int ACC = NT * NTILE;                     // columns per accumulator set
@@ -156,7 +156,7 @@ struct TallCfg {
   static_assert(!FUSE_FINAL || (MODE == 0 && COUT == 32 && NTILE == 32 && 2 * FIN_A_BYTES + 8192 <= 2 * STAGE_BYTES), "fused conv_final");
   static_assert(HALO + MT + 128 <= TALL_MARGIN, "margin");
   static int num_ctas(int n_img) { return ceil_div((int)ceil_div((long)tall_positions(HW, n_img), 128L), NT); }
-  // packed weights: [ntile][chunk][tap][hi|lo][kc 2][n NTILE][4]
+  // packed weights: [ntile][chunk][tap][kc 2][hi|lo][n NTILE][4]
   static constexpr long weight_floats() { return (long)NNT * NC * (B_BYTES / 4); }
 };
 
@@ -254,9 +254,9 @@ conv_tall_kernel(const float* __restrict__ src0, long ps0,   // TALL [2][CIN0/4]
 #pragma unroll
         for (int tap = 0; tap < K::NTAPS; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
-          const uint32_t bb = b0 + tap * (4 * NTILE * 16);
-          const uint64_t bh = tc::make_desc(bb, NTILE * 16, 128);
-          const uint64_t bl = tc::make_desc(bb + 2 * NTILE * 16, NTILE * 16, 128);
+          const uint32_t bb = b0 + tap * (4 * NTILE * 16);          // [kc][hi|lo][n][4]: k-chunk stride 2*NTILE*16
+          const uint64_t bh = tc::make_desc(bb, 2 * NTILE * 16, 128);
+          const uint64_t bl = tc::make_desc(bb + NTILE * 16, 2 * NTILE * 16, 128);
 #pragma unroll
           for (int mt = 0; mt < NT; ++mt) {   // hi*hi -> the drained set
             const uint32_t aoff = (uint32_t)(mt * 128 + (K::MODE == 0 ? dy * WP + dx : 0)) * 16;
@@ -436,11 +436,20 @@ conv_tall_kernel(const float* __restrict__ src0, long ps0,   // TALL [2][CIN0/4]
 //     across tiles),
 //   * for the 40^2 layers the whole layer's weights (<= 147 KB) stay resident in shared memory (WRES).
 // Same arithmetic / operand layouts / accuracy scheme as conv_tall_kernel above.
-template <class K_, int S_, bool WRES_>
+template <class K_, int S_, bool WRES_, bool NCONCAT_ = false>
 struct PersistCfg {
   using K = K_;
   static constexpr int S = S_;
   static constexpr bool WRES = WRES_;
+  // NCONCAT: hi*hi and hi*lo share the A operand, so they are ONE MMA against the row-concatenated B operand
+  // [Bhi;Blo] (N = 2*NTILE): A is fetched once for both products (the A fetch is 80 % of an N=32 MMA's
+  // shared-memory traffic, which is what bounds these MMAs).  Two issue warps: D1 = Ahi.[Bhi;Blo]^T, D2 = Alo.Bhi^T.
+  static constexpr bool NCONCAT = NCONCAT_;
+  static constexpr int NMMAW = NCONCAT ? 2 : 3;                                  // MMA-issue warps
+  static constexpr int ACC1 = NCONCAT ? 2 * K_::ACC : K_::ACC;                   // columns of a drained set (X or Y)
+  static constexpr int ZCOLS = NCONCAT ? K_::ACC : 2 * K_::ACC;                  // columns of one tile's correction accumulators
+  static constexpr int OFF_Z = 2 * ACC1;
+  static constexpr int OFF_FINACC = OFF_Z + 2 * ZCOLS;
   static constexpr int W_BYTES = WRES ? K::NC * K::B_BYTES : 0;                 // resident weights (one N tile)
   static constexpr int STAGE_BYTES = K::A_BYTES + (WRES ? 0 : K::B_BYTES);
   static constexpr int OFF_STAGES = W_BYTES;
@@ -449,11 +458,12 @@ struct PersistCfg {
   static constexpr int OFF_BIAS = OFF_FIN + FIN_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 64 * 4;
   static constexpr int NBAR = 2 * S + 10;                                        // full[S] empty[S] acc_full[2] acc_empty[2] z_full[2] z_empty[2] wbar fin
-  static constexpr int NTHREADS = 256;                                           // 4 drain warps + loader warp + 3 MMA-issue warps
+  static constexpr int NTHREADS = 32 * (5 + NMMAW);                              // 4 drain warps + loader warp + MMA-issue warps
   static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
   static constexpr int ACC = K::ACC;
   static constexpr int TMEM_COLS = 512;                                          // X Y | Z1a Z2a | Z1b Z2b | final  (6*ACC + 32 <= 512)
-  static_assert(6 * ACC + 32 <= 512, "TMEM");
+  static_assert(OFF_FINACC + 32 <= 512, "TMEM");
+  static_assert(!NCONCAT || K::NTILE == 32, "N-concat doubles the MMA's N; kept for the NTILE=32 layers");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
   static_assert(!WRES || K::NNT == 1, "resident weights cover one N tile");
 };
@@ -464,11 +474,11 @@ struct PersistCfg {
 // products (sets Z1/Z2).  Warp 4 only moves data (bulk copies), warps 0-3 drain and run the epilogue.
 // grid (min(#items, #SMs)), block 256, dynamic smem P::SMEM_BYTES, 1 CTA / SM
 template <class P>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(P::NTHREADS, 1)
 conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const float* __restrict__ src1, long ps1,
                             const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out, long pso,
                             const float* __restrict__ fin_w, const float* __restrict__ fin_b, float* __restrict__ fin_out,
-                            int n_img, int n_groups) {
+                            int n_img, int n_groups, unsigned long long* __restrict__ tl) {   // tl: optional stall accounting (debug)
   using K = typename P::K;
   constexpr int HW = K::HW, WP = K::WP, HP1 = K::HP1, NTILE = K::NTILE, NT = K::NT, ACC = K::ACC, S = P::S, NC = K::NC;
   extern __shared__ __align__(128) uint8_t smem_pt[];
@@ -490,10 +500,10 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
 
   if (warp == 4) tc::tmem_alloc(tmem_slot, P::TMEM_COLS);
   if (tid == 0) {
-    for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 3); }   // 3 MMA warps release a stage
+    for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], P::NMMAW); }   // every MMA warp releases a stage
     tc::mbar_init(&acc_full[0], 1); tc::mbar_init(&acc_full[1], 1);
     tc::mbar_init(&acc_empty[0], 128); tc::mbar_init(&acc_empty[1], 128);
-    tc::mbar_init(&z_full[0], 2); tc::mbar_init(&z_full[1], 2);
+    tc::mbar_init(&z_full[0], P::NMMAW - 1); tc::mbar_init(&z_full[1], P::NMMAW - 1);
     tc::mbar_init(&z_empty[0], 128); tc::mbar_init(&z_empty[1], 128);
     tc::mbar_init(wbar, 1); tc::mbar_init(fin_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -509,6 +519,15 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const int total_chunks = my_items * NC;
+  // debug stall accounting: cycles spent in each kind of wait, per role (slots: 32 u64 per CTA)
+  unsigned long long* tlc = tl ? tl + (size_t)blockIdx.x * 32 : nullptr;
+  long long w_a = 0, w_b = 0, w_c = 0;
+  const long long t_begin = clock64();
+  auto twait = [&](uint64_t* bar, uint32_t parity, long long& accum) {
+    const long long t = clock64();
+    tc::mbar_wait(bar, parity);
+    accum += clock64() - t;
+  };
 
   if (warp == 4) {
     // ============================ loader warp: bulk copies only ============================
@@ -525,7 +544,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
       const int s = i % S, j = i / NC, c = i - j * NC;
       const int item = (int)blockIdx.x + j * (int)gridDim.x;
       const int grp = item / K::NNT, nt = item - grp * K::NNT;
-      if (i >= S) tc::mbar_wait(&empty[s], (uint32_t)(((i / S) - 1) & 1));   // all three MMA warps are done with the stage
+      if (i >= S) twait(&empty[s], (uint32_t)(((i / S) - 1) & 1), w_a);   // all three MMA warps are done with the stage
       uint8_t* stA = smem + P::OFF_STAGES + s * P::STAGE_BYTES;
       const int ch0 = c * 8;
       const float* sp; long ps; int kch, kcn;
@@ -543,36 +562,41 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
       }
       __syncwarp();
     }
+    if (tlc && (tid & 31) == 0) { tlc[0] = (unsigned long long)w_a; tlc[1] = (unsigned long long)(clock64() - t_begin); }
   } else if (warp >= 5) {
-    // ============================ MMA-issue warps: 5 = hi*hi, 6 = lo*hi, 7 = hi*lo ============================
-    constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NTILE);
+    // ============================ MMA-issue warps ============================
+    // 3-product form: 5 = hi*hi, 6 = lo*hi, 7 = hi*lo.   N-concat form: 5 = Ahi.[Bhi;Blo]^T, 6 = Alo.Bhi^T.
     const int kind = warp - 5;
+    constexpr int NMMA = (P::NCONCAT ? 2 : 1) * NTILE;             // N of warp 5's MMAs
+    const uint32_t idesc = (P::NCONCAT && kind == 0) ? tc::make_idesc_tf32(128, NMMA) : tc::make_idesc_tf32(128, NTILE);
     if (P::WRES && my_items > 0) tc::mbar_wait(wbar, 0u);
 #pragma unroll 1
     for (int i = 0; i < total_chunks; ++i) {
       const int s = i % S, j = i / NC, c = i - j * NC, set = i & 1, zp = j & 1;
-      tc::mbar_wait(&full[s], (uint32_t)((i / S) & 1));
+      twait(&full[s], (uint32_t)((i / S) & 1), w_a);
       if (kind == 0) {
-        if (i >= 2) tc::mbar_wait(&acc_empty[set], (uint32_t)(((i - 2) >> 1) & 1));
+        if (i >= 2) twait(&acc_empty[set], (uint32_t)(((i - 2) >> 1) & 1), w_b);
       } else if (c == 0 && j >= 2) {
-        tc::mbar_wait(&z_empty[zp], (uint32_t)(((j - 2) >> 1) & 1));
+        twait(&z_empty[zp], (uint32_t)(((j - 2) >> 1) & 1), w_b);
       }
+      const long long t_issue = clock64();
       tc::fence_after_sync();
       const uint32_t a_hi = tc::smem_u32(smem + P::OFF_STAGES + s * P::STAGE_BYTES), a_lo = a_hi + 2 * K::KS_A;
       const uint32_t b0 = P::WRES ? tc::smem_u32(smem + c * K::B_BYTES) : a_hi + K::A_BYTES;
       const uint32_t a_base = kind == 1 ? a_lo : a_hi;
-      const uint32_t b_off = kind == 2 ? 2 * NTILE * 16 : 0;
-      const uint32_t d_base = kind == 0 ? tmem + set * ACC : tmem + 2 * ACC + zp * 2 * ACC + (kind - 1) * ACC;
+      const uint32_t b_off = (!P::NCONCAT && kind == 2) ? NTILE * 16 : 0;          // [kc][hi|lo][n][4]: lo rows follow the hi rows
+      const uint32_t d_stride = (P::NCONCAT && kind == 0) ? 2 * NTILE : NTILE;     // accumulator columns per M tile
+      const uint32_t d_base = kind == 0 ? tmem + set * P::ACC1 : tmem + P::OFF_Z + zp * P::ZCOLS + (kind - 1) * ACC;
       const bool fresh = kind == 0 ? true : (c == 0);   // first MMA of the chain overwrites the accumulator
       if (tc::elect_one()) {
 #pragma unroll
         for (int tap = 0; tap < K::NTAPS; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
-          const uint64_t bd = tc::make_desc(b0 + tap * (4 * NTILE * 16) + b_off, NTILE * 16, 128);
+          const uint64_t bd = tc::make_desc(b0 + tap * (4 * NTILE * 16) + b_off, 2 * NTILE * 16, 128);
 #pragma unroll
           for (int mt = 0; mt < NT; ++mt) {
             const uint32_t aoff = (uint32_t)(mt * 128 + (K::MODE == 0 ? dy * WP + dx : 0)) * 16;
-            tc::mma_tf32(d_base + mt * NTILE, tc::make_desc(a_base + aoff, K::KS_A, 128), bd, IDESC, (fresh && tap == 0) ? 0u : 1u);
+            tc::mma_tf32(d_base + mt * d_stride, tc::make_desc(a_base + aoff, K::KS_A, 128), bd, idesc, (fresh && tap == 0) ? 0u : 1u);
           }
         }
         tc::mma_commit(&empty[s]);
@@ -580,6 +604,11 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
         else if (c == NC - 1) tc::mma_commit(&z_full[zp]);
       }
       __syncwarp();
+      w_c += clock64() - t_issue;
+    }
+    if (tlc && (tid & 31) == 0) {
+      tlc[4 + 4 * kind] = (unsigned long long)w_a; tlc[5 + 4 * kind] = (unsigned long long)w_b;
+      tlc[6 + 4 * kind] = (unsigned long long)w_c; tlc[7 + 4 * kind] = (unsigned long long)(clock64() - t_begin);
     }
   } else {
     // ============================ drain + epilogue warps ============================
@@ -599,32 +628,47 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
 #pragma unroll 1
       for (int c = 0; c < NC; ++c) {
         const int i = j * NC + c, set = i & 1;
-        tc::mbar_wait(&acc_full[set], (uint32_t)((i >> 1) & 1));
+        twait(&acc_full[set], (uint32_t)((i >> 1) & 1), w_a);
         tc::fence_after_sync();
+        const long long t_d = clock64();
 #pragma unroll
         for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
           for (int n0 = 0; n0 < NTILE; n0 += 32) {
             float v[32];
-            tc::tmem_ld32(tmem_row + set * ACC + mt * NTILE + n0, v);
+            if constexpr (P::NCONCAT) {   // columns [mt*2N, +N) = hi*hi, [mt*2N+N, +N) = hi*lo
+              float w[32];
+              tc::tmem_ld32(tmem_row + set * P::ACC1 + mt * 2 * NTILE + n0, v);
+              tc::tmem_ld32(tmem_row + set * P::ACC1 + mt * 2 * NTILE + NTILE + n0, w);
 #pragma unroll
-            for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q];
+              for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q] + w[q];
+            } else {
+              tc::tmem_ld32(tmem_row + set * P::ACC1 + mt * NTILE + n0, v);
+#pragma unroll
+              for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q];
+            }
           }
         tc::fence_before_sync();
         tc::mbar_arrive(&acc_empty[set]);
+        w_b += clock64() - t_d;
       }
+      const long long t_e = clock64();
       // the two correction sets of this tile (issued by warps 6 and 7)
-      tc::mbar_wait(&z_full[zp], (uint32_t)((j >> 1) & 1));
+      twait(&z_full[zp], (uint32_t)((j >> 1) & 1), w_a);
       tc::fence_after_sync();
 #pragma unroll
       for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
         for (int n0 = 0; n0 < NTILE; n0 += 32) {
-          float v[32], w[32];
-          tc::tmem_ld32(tmem_row + 2 * ACC + zp * 2 * ACC + mt * NTILE + n0, v);
-          tc::tmem_ld32(tmem_row + 2 * ACC + zp * 2 * ACC + ACC + mt * NTILE + n0, w);
+          float v[32];
+          tc::tmem_ld32(tmem_row + P::OFF_Z + zp * P::ZCOLS + mt * NTILE + n0, v);
 #pragma unroll
-          for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q] + w[q];
+          for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q];
+          if constexpr (!P::NCONCAT) {
+            tc::tmem_ld32(tmem_row + P::OFF_Z + zp * P::ZCOLS + ACC + mt * NTILE + n0, v);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q];
+          }
         }
       tc::fence_before_sync();
       tc::mbar_arrive(&z_empty[zp]);
@@ -693,9 +737,9 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
                 const uint64_t al = tc::make_desc(al0 + ks * 2 * K::FIN_KS, K::FIN_KS, 128);
                 const uint64_t bh = tc::make_desc(w0 + ks * 2 * 512, 512, 128);
                 const uint64_t bl = tc::make_desc(w0 + 4096 + ks * 2 * 512, 512, 128);
-                tc::mma_tf32(tmem + 6 * ACC, ah, bh, ID32, ks > 0 ? 1u : 0u);
-                tc::mma_tf32(tmem + 6 * ACC, al, bh, ID32, 1u);
-                tc::mma_tf32(tmem + 6 * ACC, ah, bl, ID32, 1u);
+                tc::mma_tf32(tmem + P::OFF_FINACC, ah, bh, ID32, ks > 0 ? 1u : 0u);
+                tc::mma_tf32(tmem + P::OFF_FINACC, al, bh, ID32, 1u);
+                tc::mma_tf32(tmem + P::OFF_FINACC, ah, bl, ID32, 1u);
               }
               tc::mma_commit(fin_bar);
             }
@@ -705,7 +749,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           ++fin_use;
           tc::fence_after_sync();
           float v[32];
-          tc::tmem_ld32(tmem_row + 6 * ACC, v);
+          tc::tmem_ld32(tmem_row + P::OFF_FINACC, v);
           if (valid) {
             float* op = fin_out + ((size_t)img * (HW * HW) + y * HW + x) * 32;
 #pragma unroll
@@ -718,6 +762,11 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
         }
       }
       tc::named_bar_sync(1, 128);   // everyone is done with sbias before the next item overwrites it
+      w_c += clock64() - t_e;
+    }
+    if (tlc && tid == 0) {
+      tlc[16] = (unsigned long long)w_a; tlc[17] = (unsigned long long)w_b; tlc[18] = (unsigned long long)w_c;
+      tlc[19] = (unsigned long long)(clock64() - t_begin); tlc[20] = (unsigned long long)my_items;
     }
   }
   tc::fence_before_sync();

@@ -70,6 +70,14 @@ int main() {
   run<64>(1, 4, 343, 1); run<64>(2, 4, 343, 1);
   run<128>(1, 4, 343, 1); run<128>(2, 2, 343, 1);
   run<256>(1, 2, 343, 1);
-  run<32>(2, 4, 129, 1); run<32>(2, 4, 128, 1); run<32>(2, 4, 136, 1);
+  printf("-- conv-like issue patterns\n");
+  run<32>(3, 2, 343, 1);   // 40^2 layers today: 3 issuing warps x 2 chains (mt)
+  run<32>(3, 1, 343, 1);
+  run<64>(3, 1, 175, 1);   // 20^2 / 10^2 layers today: 3 warps x 1 chain, N=64
+  run<64>(3, 2, 175, 1);
+  run<64>(2, 2, 343, 1);   // N-concat D1 for NTILE=32, NT=2
+  run<128>(2, 1, 175, 1);
+  run<128>(1, 1, 175, 1);
+  run<128>(1, 2, 175, 1);
   return 0;
 }
