@@ -304,7 +304,7 @@ def main():
             avg_us = 1e3 * ms / cnt
             if name in macs:
                 fl = 2.0 * macs[name] * n_img
-            elif name == "conv_in_planes":
+            elif name in ("conv_in_planes", "conv_in_tc"):
                 fl = 2.0 * GRID3 * 27 * 32 * B
             elif name == "decode_points:grasp":
                 fl = 2.0 * (HEAD_MAC["qual"] + HEAD_MAC["rot"] + HEAD_MAC["width"]) * B * N
@@ -325,7 +325,7 @@ def main():
                     "frac": round(dom_fl / peaks["bf16_tflops"], 5), "traffic": traffic, "peak_src": peaks["src"],
                     "note": ("dominant kernel by CUDA-event time in the instrumented pass; tensor-core kernels run 3xTF32 (3 MMAs per fp32-equivalent "
                              "product, fp32 FLOPs counted once); FMA-pipe kernels are also reported against the fp32 FMA peak at the observed SM clock"),
-                    "alg_bytes_per_launch": {"conv_in_planes": B * (GRID3 * 4 + 3 * 32 * 1600 * 4)}.get(dom),
+                    "alg_bytes_per_launch": {"conv_in_planes": B * (GRID3 * 4 + 3 * 32 * 1600 * 4), "conv_in_tc": B * (GRID3 * 4 + 3 * 32 * 1600 * 4)}.get(dom),
                     "fp32_fma_peak": round(fma_peak, 1), "frac_fp32_fma": round(dom_fl / fma_peak, 4),
                     "step_tflops": round(2.0 * (ENC_MAC + N * sum(HEAD_MAC.values())) * B / (ms_per_step * 1e-3) / 1e12, 3),
                     "step_hbm_frac": round((362_496 * B / (ms_per_step * 1e-3)) / 1e9 / peaks["hbm_gbs"], 5)}

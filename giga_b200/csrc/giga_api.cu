@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "conv_in.cuh"
+#include "conv_in_tc.cuh"
 #include "decoder.cuh"
 #include "decoder_tc.cuh"
 #include "unet.cuh"
@@ -87,6 +88,8 @@ struct EncLayout {
   long tc_conv[10];  // tensor-core operand-layout weights (hi/lo tf32 splits) per conv layer
   long tc_up[2];     // transpose convs, [ab][chunk][hi|lo][kc][co][4]
   long tc_fin;       // conv_final as a 32x32 B operand [hi,lo][kc 8][n 32][4]
+  long cin_b;        // conv_in bias (device copy for the tensor-core conv_in)
+  long tc_cin;       // conv_in as 9 (dx,dy) taps x [kc 2][hi|lo][n 32][4] with k = dz (conv_in_tc.cuh)
   long total;
 };
 const int kConvCin[10] = {32, 32, 32, 64, 64, 128, 128, 64, 64, 32};
@@ -107,6 +110,8 @@ EncLayout make_enc_layout() {
   for (int i = 0; i < 10; ++i) { L.tc_conv[i] = o; o += (long)kConvCin[i] * kConvCout[i] * 9 * 2; }
   for (int i = 0; i < 2; ++i) { L.tc_up[i] = o; o += (long)kUpCin[i] * kUpCout[i] * 4 * 2; }
   L.tc_fin = o; o += 2 * 1024;
+  L.tc_cin = o; o += CT_WEIGHT_FLOATS;
+  L.cin_b = o; o += 32;
   L.total = o;
   return L;
 }
@@ -133,7 +138,9 @@ struct giga_ctx {
   float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo tf32 splits)
   int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int encoder_impl = 1;      // U-Net convs: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
+  int conv_in_impl = 0;      // conv_in: 0 = fp32 FMA pipe (default), 1 = tcgen05 variant (experimental, not faster: DESIGN.md 5)
   int last_impl = 0;
+  bool last_cin_tc = false;
   int num_sms = 148;
   const char* timeline_layer = nullptr;   // debug (env GIGA_TIMELINE=<kernel name>): in-kernel phase timestamps
   unsigned long long* d_timeline = nullptr;
@@ -142,7 +149,8 @@ struct giga_ctx {
   int cap_B = 0;
   int last_B = 0;
   float* d_pre = nullptr;      // [3][B][32][1600]
-  float* d_xzpart = nullptr;   // [B][10][40][32][40]
+  float* d_xzpart = nullptr;   // [B][CI_NT][40][32][40]
+  float* d_yzpart = nullptr;   // [B][CT_NG][40][32][40]  (tensor-core conv_in)
   float* d_act[kNumActs] = {};
   float* d_tall[kNumActs + 1] = {};   // TALL pre-split activations ([0] = pre, [1+i] = kActs[i]) for the tensor-core encoder
   long tall_ps[kNumActs + 1] = {};
@@ -199,6 +207,7 @@ struct LaunchScope {
 int ensure_attrs(giga_ctx* ctx) {
   if (ctx->attrs_set) return GIGA_OK;
   CU_TRY(cudaFuncSetAttribute(conv_in_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CI_SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(sample_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
@@ -231,6 +240,9 @@ int ensure_workspace(giga_ctx* ctx, int B) {
   ctx->cap_B = 0;
   CU_TRY(cudaMalloc(&ctx->d_pre, sizeof(float) * 3 * (size_t)B * C * G2));
   CU_TRY(cudaMalloc(&ctx->d_xzpart, sizeof(float) * (size_t)B * CI_NT * G * C * G));
+  if (ctx->d_yzpart) cudaFree(ctx->d_yzpart);
+  ctx->d_yzpart = nullptr;
+  CU_TRY(cudaMalloc(&ctx->d_yzpart, sizeof(float) * (size_t)B * CT_NG * G * C * G));
   for (int i = 0; i < kNumActs; ++i)
     CU_TRY(cudaMalloc(&ctx->d_act[i], sizeof(float) * 3 * (size_t)B * kActs[i].ch * kActs[i].hw * kActs[i].hw));
   for (int i = 0; i <= kNumActs; ++i) {   // zero-initialised once: padding positions are never written
@@ -380,7 +392,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart};
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_yzpart};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : ctx->slot) {
@@ -432,7 +444,20 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       for (int t = 0; t < 27; ++t) ctx->conv_in.w[t][c] = w[c * 27 + t];  // [co][0][dx][dy][dz] -> [tap][co]
       ctx->conv_in.b[c] = b[c];
     }
-    std::vector<float> blob(ctx->el.total);
+    std::vector<float> blob(ctx->el.total, 0.f);
+    for (int c = 0; c < 32; ++c)
+      for (int tap = 0; tap < 9; ++tap)       // tap = dx*3 + dy ; k = dz
+        for (int dz = 0; dz < 3; ++dz) {
+          const float v = w[c * 27 + tap * 3 + dz], hi = tf32_rn_host(v);
+          blob[ctx->el.tc_cin + tap * 512 + (0 * 2 + 0) * 128 + c * 4 + dz] = hi;
+          blob[ctx->el.tc_cin + tap * 512 + (0 * 2 + 1) * 128 + c * 4 + dz] = v - hi;
+        }
+    for (int c = 0; c < 32; ++c) {   // bias rides on the centre tap (dx=1,dy=1): the A operand's 4th k is the constant 1
+      const float bv = b[c], hi = tf32_rn_host(bv);
+      blob[ctx->el.tc_cin + 4 * 512 + (0 * 2 + 0) * 128 + c * 4 + 3] = hi;
+      blob[ctx->el.tc_cin + 4 * 512 + (0 * 2 + 1) * 128 + c * 4 + 3] = bv - hi;
+    }
+    memcpy(blob.data() + ctx->el.cin_b, ctx->conv_in.b, sizeof(float) * 32);
     for (int i = 0; i < 10; ++i) {
       const int ci = kConvCin[i], co = kConvCout[i];
       std::string base = std::string("encoder.unet.") + kConvName[i];
@@ -581,13 +606,35 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
   if (int r = ensure_workspace(ctx, B)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_img = 3 * B;
-  {
-    LaunchScope ls(ctx, "conv_in_planes", st);
-    conv_in_planes_kernel<<<dim3(CI_NT, B), CI_THREADS, CI_SMEM_BYTES, st>>>(tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
-  }
-  {
-    LaunchScope ls(ctx, "xz_finish", st);
-    xz_finish_kernel<<<dim3(C, B), 256, 0, st>>>(ctx->d_xzpart, ctx->d_pre, B);
+  const bool cin_tc = ctx->encoder_impl >= 1 && ctx->conv_in_impl == 1;
+  if (cin_tc) {   // tensor-core conv_in writes the TALL pre-split planes directly
+    {
+      unsigned long long* tl = nullptr;
+      if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, "conv_in_tc")) {
+        const size_t n = (size_t)CT_NG * B * 32;
+        if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+        cudaMalloc(&ctx->d_timeline, n * 8);
+        cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
+        ctx->timeline_n = (long)n;
+        tl = ctx->d_timeline;
+      }
+      LaunchScope ls(ctx, "conv_in_tc", st);
+      conv_in_tc_kernel<<<dim3(CT_NG, B), 256, CT_SMEM_BYTES, st>>>(tsdf, ctx->d_enc + ctx->el.tc_cin, ctx->d_enc + ctx->el.cin_b,
+                                                                     ctx->d_tall[0], ctx->tall_ps[0], ctx->d_yzpart, B, tl);
+    }
+    {
+      LaunchScope ls(ctx, "yz_finish", st);
+      yz_finish_tall_kernel<<<dim3(G, B), 320, 0, st>>>(ctx->d_yzpart, ctx->d_tall[0], ctx->tall_ps[0], B);
+    }
+  } else {
+    {
+      LaunchScope ls(ctx, "conv_in_planes", st);
+      conv_in_planes_kernel<<<dim3(CI_NT, B), CI_THREADS, CI_SMEM_BYTES, st>>>(tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+    }
+    {
+      LaunchScope ls(ctx, "xz_finish", st);
+      xz_finish_kernel<<<dim3(C, B), 256, 0, st>>>(ctx->d_xzpart, ctx->d_pre, B);
+    }
   }
   float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"),
         *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),
@@ -605,7 +652,7 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
     const TallBuf none;
     const float* E = ctx->d_enc;
     const EncLayout& L = ctx->el;
-    {
+    if (!cin_tc) {
       LaunchScope ls(ctx, "nchw_to_tall:pre", st);
       nchw_to_tall_kernel<40, 8><<<ceil_div(n_img * 8 * G2, 256), 256, 0, st>>>(ctx->d_pre, tb("pre").p, tb("pre").ps, n_img);
     }
@@ -653,11 +700,13 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
       launch_tall<T_u1c2>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st);
     }
     ctx->last_B = B;
-    ctx->last_impl = 1;
+    ctx->last_impl = ctx->encoder_impl;
+    ctx->last_cin_tc = cin_tc;
     CU_TRY(cudaGetLastError());
     return GIGA_OK;
   }
   ctx->last_impl = 0;
+  ctx->last_cin_tc = false;
   launch_conv<K_d0c1>(ctx, "conv3x3:d0c1", n_img, ctx->d_pre, nullptr, 0, d0c1, nullptr, st);
   launch_conv<K_d0c2>(ctx, "conv3x3:d0c2", n_img, d0c1, nullptr, 1, d0c2, p0, st);
   launch_conv<K_d1c1>(ctx, "conv3x3:d1c1", n_img, p0, nullptr, 2, d1c1, nullptr, st);
@@ -863,6 +912,11 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
     ctx->decoder_impl = value;
     return GIGA_OK;
   }
+  if (!strcmp(key, "conv_in_impl")) {
+    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "conv_in_impl must be 0 (fp32 FMA) or 1 (tcgen05, experimental)");
+    ctx->conv_in_impl = value;
+    return GIGA_OK;
+  }
   if (!strcmp(key, "encoder_impl")) {
     if (value < 0 || value > 2) return fail(GIGA_EINVAL, "encoder_impl must be 0 (fp32 FMA), 1 (tcgen05 persistent) or 2 (tcgen05 per-tile)");
     ctx->encoder_impl = value;
@@ -928,7 +982,11 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
       }
   }
   if (!src) return fail(GIGA_EINVAL, std::string("giga_debug_copy: unknown buffer '") + name + "'");
-  if (ctx->last_impl == 1 && strcmp(name, "pre")) {
+  if (ctx->last_cin_tc && !strcmp(name, "pre")) {   // tensor-core conv_in: planes exist only in the TALL layout
+    const int n_img = 3 * ctx->last_B;
+    tall_to_nchw_kernel<40, 8><<<ceil_div(n_img * 8 * G2, 256), 256, 0, (cudaStream_t)stream>>>(ctx->d_tall[0], ctx->d_pre, ctx->tall_ps[0], n_img);
+  }
+  if (ctx->last_impl >= 1 && strcmp(name, "pre")) {
     if (!strcmp(name, "u1c2"))
       return fail(GIGA_ESTATE, "giga_debug_copy: 'u1c2' is fused away by the tensor-core encoder (encoder_impl=1)");
     // the tensor-core encoder keeps activations in the TALL pre-split layout: convert into the NCHW scratch first

@@ -222,6 +222,17 @@ class _GigaBase(nn.Module):
         model._device = device
         return model
 
+    # -- training bridge (opt-in; see giga_b200/training.py) --------------------------------
+    def enable_training_bridge(self, enabled: bool = True):
+        """Make `forward()` differentiable w.r.t. the parameters: forward values still come from the CUDA
+        library, gradients from a PyTorch-autograd recompute on the GPU (library kernels) until the native
+        backward kernels exist.  Off by default: without it outputs carry no graph and backward() raises."""
+        self.__dict__["_train_bridge"] = bool(enabled)
+        return self
+
+    def _bridge_active(self) -> bool:
+        return bool(self.__dict__.get("_train_bridge")) and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     @property
     def gpu_launches(self) -> int:
         eng = self.__dict__.get("_eng")
@@ -385,14 +396,22 @@ class ConvolutionalOccupancyNetwork(_GigaBase):
         if device is not None:
             self.to(device)
 
-    def forward(self, inputs, p, p_tsdf=None, sample=True, **kwargs):
-        """models/__init__.py:42-67"""
+    def _forward_native(self, inputs, p, p_tsdf=None):
         c = self.encode_inputs(inputs)
         qual, rot, width = self.decode(p, c)
         if p_tsdf is not None:
-            tsdf = self.decoder_tsdf(p_tsdf, c, **kwargs)
+            tsdf = self.decoder_tsdf(p_tsdf, c)
             return qual, rot, width, tsdf
         return qual, rot, width
+
+    def forward(self, inputs, p, p_tsdf=None, sample=True, **kwargs):
+        """models/__init__.py:42-67"""
+        if self._bridge_active():
+            from .training import bridged_forward
+            eng = self._engine()
+            return bridged_forward(self, _prep(inputs, eng.device), _prep(p, eng.device),
+                                   _prep(p_tsdf, eng.device) if p_tsdf is not None else None)
+        return self._forward_native(inputs, p, p_tsdf)
 
     def decode(self, p, c, **kwargs):
         """models/__init__.py:111-124 (sigmoid / normalise fused into the kernel epilogue)."""
@@ -427,6 +446,14 @@ class ConvolutionalOccupancyNetworkGeometry(_GigaBase):
         if device is not None:
             self.to(device)
 
+    def _forward_native(self, inputs, p, p_tsdf=None):
+        return (self.infer_geo(inputs, p_tsdf),)
+
     def forward(self, inputs, p, p_tsdf, sample=True, **kwargs):
         """models/__init__.py:179-195"""
+        if self._bridge_active():
+            from .training import bridged_forward
+            eng = self._engine()
+            pt = _prep(p_tsdf, eng.device)
+            return bridged_forward(self, _prep(inputs, eng.device), pt, pt)[0]
         return self.infer_geo(inputs, p_tsdf)

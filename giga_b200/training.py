@@ -1,0 +1,157 @@
+"""Training bridge (opt-in) and data-parallel gradient exchange for `scripts/train_giga.py`-style steps.
+
+STATUS -- read this first.  The hand-written sm_100a kernels in libgiga_b200.so implement the FORWARD of
+the hot path.  Native backward kernels (MLP dgrad/wgrad, grid-sample scatter, conv/convT dgrad+wgrad,
+max-pool and plane-mean backward) are not built yet.  Until they are, a model can
+opt in to this bridge with `net.enable_training_bridge()`:
+
+  * forward values ALWAYS come from the CUDA library (identical to inference, parity-tested);
+  * backward re-evaluates the same function with PyTorch ops on the GPU under autograd and returns the
+    parameter gradients -- i.e. library (ATen/cuDNN) kernels, GPU only, gradients only.
+
+Without the opt-in the model's outputs carry no autograd graph and `loss.backward()` raises, so nothing
+falls back silently.  The bridge never runs on the CPU and is never used for inference.
+
+Also here: `allreduce_gradients` -- the single flat all-reduce of the 581,863-element gradient buffer
+(2.33 MB) that a scene-sharded data-parallel step needs, one process per GPU.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+PLANES = ("xz", "xy", "yz")
+_AX = {"xz": (0, 2), "xy": (0, 1), "yz": (1, 2)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# the model function in differentiable PyTorch ops (GPU), parameterised by a name -> tensor mapping
+# ------------------------------------------------------------------------------------------------------
+def _unet(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    g = lambda n: sd["encoder.unet." + n]
+    enc = []
+    for i in range(3):
+        x = F.relu(F.conv2d(x, g(f"down_convs.{i}.conv1.weight"), g(f"down_convs.{i}.conv1.bias"), padding=1))
+        x = F.relu(F.conv2d(x, g(f"down_convs.{i}.conv2.weight"), g(f"down_convs.{i}.conv2.bias"), padding=1))
+        enc.append(x)
+        if i < 2:
+            x = F.max_pool2d(x, 2, 2)
+    for i in range(2):
+        up = F.conv_transpose2d(x, g(f"up_convs.{i}.upconv.weight"), g(f"up_convs.{i}.upconv.bias"), stride=2)
+        x = torch.cat((up, enc[-(i + 2)]), 1)
+        x = F.relu(F.conv2d(x, g(f"up_convs.{i}.conv1.weight"), g(f"up_convs.{i}.conv1.bias"), padding=1))
+        x = F.relu(F.conv2d(x, g(f"up_convs.{i}.conv2.weight"), g(f"up_convs.{i}.conv2.bias"), padding=1))
+    return F.conv2d(x, g("conv_final.weight"), g("conv_final.bias"))
+
+
+def _encode(sd, x):
+    f = F.relu(F.conv3d(x.unsqueeze(1), sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1))  # [b,c,ix,iy,iz]
+    # 40^3 voxels onto 40^2 cells: the scatter_mean is the mean along the perpendicular axis
+    pre = {"xz": f.mean(3).transpose(2, 3), "xy": f.mean(4).transpose(2, 3), "yz": f.mean(2).transpose(2, 3)}
+    return {k: _unet(sd, v) for k, v in pre.items()}
+
+
+def _norm_axis(v):
+    t = v / 1.00001 + 0.5
+    t = torch.where(t >= 1, torch.full_like(t, 1 - 10e-6), t)
+    return torch.where(t < 0, torch.zeros_like(t), t)
+
+
+def _features(p, planes):
+    out = []
+    for k in PLANES:
+        a0, a1 = _AX[k]
+        uv = torch.stack((_norm_axis(p[..., a0]), _norm_axis(p[..., a1])), -1)
+        grid = (2.0 * uv - 1.0)[:, :, None]
+        out.append(F.grid_sample(planes[k], grid, padding_mode="border", align_corners=True, mode="bilinear").squeeze(-1))
+    return torch.cat(out, 1).transpose(1, 2)
+
+
+def _head(sd, name, p, c):
+    pre = f"decoder_{name}."
+    net = F.linear(p, sd[pre + "fc_p.weight"], sd[pre + "fc_p.bias"])
+    for i in range(5):
+        net = net + F.linear(c, sd[pre + f"fc_c.{i}.weight"], sd[pre + f"fc_c.{i}.bias"])
+        h = F.linear(F.relu(net), sd[pre + f"blocks.{i}.fc_0.weight"], sd[pre + f"blocks.{i}.fc_0.bias"])
+        net = net + F.linear(F.relu(h), sd[pre + f"blocks.{i}.fc_1.weight"], sd[pre + f"blocks.{i}.fc_1.bias"])
+    return F.linear(F.relu(net), sd[pre + "fc_out.weight"], sd[pre + "fc_out.bias"]).squeeze(-1)
+
+
+def _forward_torch(sd, x, p, p_tsdf, detach_tsdf: bool, has_grasp: bool):
+    planes = _encode(sd, x)
+    outs = []
+    if has_grasp:
+        c = _features(p, planes)
+        outs += [torch.sigmoid(_head(sd, "qual", p, c)), F.normalize(_head(sd, "rot", p, c), dim=2), _head(sd, "width", p, c)]
+    if p_tsdf is not None:
+        pl = {k: v.detach() for k, v in planes.items()} if detach_tsdf else planes
+        outs.append(_head(sd, "tsdf", p_tsdf, _features(p_tsdf, pl)))
+    return tuple(outs)
+
+
+class _Bridge(torch.autograd.Function):
+    """forward: native CUDA kernels; backward: autograd through `_forward_torch` (recompute)."""
+
+    @staticmethod
+    def forward(ctx, net, x, p, p_tsdf, names, *params):
+        with torch.no_grad():
+            outs = net._forward_native(x, p, p_tsdf)
+        ctx.net, ctx.names, ctx.has_tsdf = net, names, p_tsdf is not None
+        ctx.save_for_backward(x, p, p_tsdf if p_tsdf is not None else x.new_empty(0), *params)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, p, pt, *params = ctx.saved_tensors
+        leaves = [t.detach().requires_grad_(True) for t in params]
+        sd = dict(zip(ctx.names, leaves))
+        # fp32 library kernels for the recompute (cuDNN/cuBLAS default to TF32, which costs ~1e-2 relative on gradients)
+        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            return _Bridge._backward_impl(ctx, leaves, sd, x, p, pt, grads)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+    @staticmethod
+    def _backward_impl(ctx, leaves, sd, x, p, pt, grads):
+        with torch.enable_grad():
+            outs = _forward_torch(sd, x, p, pt if ctx.has_tsdf else None, getattr(ctx.net, "detach_tsdf", False), hasattr(ctx.net, "decoder_qual"))
+            pairs = [(o, g) for o, g in zip(outs, grads) if g is not None]
+            gp = torch.autograd.grad([o for o, _ in pairs], leaves, [g for _, g in pairs], allow_unused=True)
+        return (None, None, None, None, None) + tuple(gp)
+
+
+def bridged_forward(net, x, p, p_tsdf):
+    named = [(k, v) for k, v in net.named_parameters()]
+    return _Bridge.apply(net, x, p, p_tsdf, [k for k, _ in named], *[v for _, v in named])
+
+
+# ------------------------------------------------------------------------------------------------------
+# data-parallel gradient exchange (one process per GPU, scenes sharded by the data loader)
+# ------------------------------------------------------------------------------------------------------
+def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, average: bool = True) -> Optional[torch.Tensor]:
+    """One flat all-reduce (sum, then /world) over every parameter gradient: 581,863 floats = 2.33 MB for GIGA,
+    latency-bound on NVLink -> a single bucket.  Parameters without a gradient
+    contribute zeros (all ranks must agree on the layout).  Returns the flat buffer (or None single-process)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    params = list(params)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return flat

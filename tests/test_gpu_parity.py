@@ -284,6 +284,21 @@ def test_decoder_implementations(oracle_sd, impl):
         assert torch.equal(out[0].argmax(1).cpu(), ref[0].argmax(1))
 
 
+def test_conv_in_tensor_core_variant(oracle_sd):
+    """conv_in_impl=1: the experimental tcgen05 Conv3d + plane-mean kernel (same parity bar)."""
+    net = make_net("giga", oracle_sd)
+    net._engine().set_option("conv_in_impl", 1)
+    for B, seed in ((1, 1), (3, 2)):
+        x, p, pt = O.seeded_inputs(B, 64, seed=60 + seed)
+        with torch.no_grad():
+            pre = O.plane_features_pre_unet(oracle_sd, x)
+            ref = O.encode_inputs(oracle_sd, x)
+            c = net.encode_inputs(x.to(DEV))
+            _close(net.debug_activation("pre", B), torch.stack([pre[k] for k in O.PLANES]), tol=1e-5, name="pre(tc)")
+        for k in O.PLANES:
+            _close(c[k], ref[k], name=f"cin_tc.{k}")
+
+
 @pytest.mark.parametrize("impl", [0, 1, 2])
 def test_encoder_implementations(oracle_sd, impl):
     """encoder_impl 0 = fp32 FMA-pipe U-Net convs, 1 = tcgen05 3xTF32 implicit GEMM with persistent CTAs (default),
@@ -297,3 +312,45 @@ def test_encoder_implementations(oracle_sd, impl):
             c = net.encode_inputs(x.to(DEV))
         for k in O.PLANES:
             _close(c[k], ref[k], name=f"enc{impl}.{k}")
+
+
+def test_training_bridge_matches_reference_gradients(oracle_sd):
+    """scripts/train_giga.py:199-211 style step through the opt-in training bridge: forward values from the CUDA
+    library, gradients (PyTorch recompute on the GPU) equal to autograd through the CPU oracle."""
+    import torch.nn.functional as F
+
+    net = make_net("giga", oracle_sd)
+    x, p, pt = O.seeded_inputs(4, 1, seed=50)       # one grasp point per sample, as prepare_batch() gives
+    _, _, pt = O.seeded_inputs(4, 128, seed=51)
+    label = torch.tensor([1.0, 0.0, 1.0, 1.0])
+    occ_t = (torch.rand(4, 128, generator=torch.Generator().manual_seed(0)) > 0.5).float()
+
+    def loss_fn(out, dev):
+        qual, rot, width, occ = out
+        l = F.binary_cross_entropy(qual.squeeze(-1), label.to(dev))
+        tgt = torch.tensor([0.5, -0.5, 0.5, 0.5], device=dev)          # quaternion loss of train_giga.py:180-182
+        l = l + (label.to(dev) * (1.0 - (rot.squeeze(1) * tgt).sum(-1).abs())).mean() + 0.01 * F.mse_loss(40 * width.squeeze(-1), torch.ones(4, device=dev))
+        return l + F.binary_cross_entropy(torch.sigmoid(occ), occ_t.to(dev))
+
+    # without the opt-in nothing is differentiable (and nothing falls back silently)
+    out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+    assert not any(o.requires_grad for o in out)
+    net.enable_training_bridge()
+    out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+    ref_leaves = {k: v.clone().requires_grad_(True) for k, v in oracle_sd.items()}
+    ref_out = O.forward(ref_leaves, x, p, pt)
+    for a, b in zip(out, ref_out):
+        _close(a, b.detach(), name="bridge forward")
+    loss_fn(out, DEV).backward()
+    loss_fn(ref_out, "cpu").backward()
+    worst = 0.0
+    for k, prm in net.named_parameters():
+        g, r = prm.grad.cpu(), ref_leaves[k].grad
+        worst = max(worst, ((g - r).abs().max() / (r.abs().max() + 1e-4)).item())   # TF32 cuDNN backward: ~1e-3 relative
+    assert worst < 5e-3, worst
+    # an Adam step changes the parameters and the next forward picks them up (engine re-commit)
+    opt = torch.optim.Adam(net.parameters(), lr=2e-4)
+    opt.step()
+    with torch.no_grad():
+        out2 = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+    assert not torch.equal(out2[3], out[3].detach())

@@ -77,3 +77,32 @@ def test_single_process_path():
     v, i = sharding.sharded_best_grasp(_score, tsdf, pts)
     rv, ri = _score(tsdf, pts)
     assert torch.equal(v, rv) and torch.equal(i, ri)
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from giga_b200.training import allreduce_gradients
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.randn(7, 3)), torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(2, 2))]
+        params[0].grad = torch.full((7, 3), float(rank + 1))
+        params[1].grad = torch.arange(5.0) * (rank + 1)
+        # params[2] has no gradient on any rank -> zeros
+        flat = allreduce_gradients(params)
+        mean = sum(range(1, world + 1)) / world
+        ok = torch.allclose(params[0].grad, torch.full((7, 3), mean)) and torch.allclose(params[1].grad, torch.arange(5.0) * mean)
+        ok = ok and params[2].grad is not None and params[2].grad.abs().max().item() == 0 and flat.numel() == 21 + 5 + 4
+        out[rank] = int(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo():
+    port = _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_grad_worker, args=(2, port, out), nprocs=2, join=True)
+    assert [out[r] for r in range(2)] == [1, 1]
+    from giga_b200.training import allreduce_gradients
+    assert allreduce_gradients([torch.nn.Parameter(torch.zeros(3))]) is None   # single process: no-op

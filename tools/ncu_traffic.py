@@ -13,6 +13,8 @@ def unit_scale(u):
 
 def bench_name(kname, order):
     if "conv_in_planes" in kname: return "conv_in_planes"
+    if "conv_in_tc" in kname: return "conv_in_tc"
+    if "yz_finish" in kname: return "yz_finish"
     if "xz_finish" in kname: return "xz_finish"
     if "nchw_to_tall" in kname: return "nchw_to_tall:pre"
     if "scene_argmax" in kname: return "scene_argmax"
