@@ -16,4 +16,20 @@ __host__ __device__ constexpr int round_up(int a, int b) { return ceil_div(a, b)
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 
+// Packed fp32 pair arithmetic (sm_100: FFMA2 / FADD2).  Each component is an IEEE fp32 fma / add, so the
+// results are bit-identical to the scalar instructions; the pair form halves the issue slots of FMA-bound loops.
+__device__ __forceinline__ void fma2(float2& d, const float2 a, const float s) {   // d += a * (s, s)
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  const float2 ss = make_float2(s, s);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(dd)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&ss)));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+__device__ __forceinline__ void add2(float2& d, const float2 a) {                   // d += a
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(dd) : "l"(*reinterpret_cast<const unsigned long long*>(&a)));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+
 }  // namespace giga

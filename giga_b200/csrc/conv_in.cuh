@@ -20,17 +20,17 @@
 namespace giga {
 
 struct ConvInParams {
-  float w[27][32];  // [tap = dx*9 + dy*3 + dz][cout]   (cross-correlation, voxels.py:36)
-  float b[32];
+  float2 w[27][16];  // [tap = dx*9 + dy*3 + dz][cout pair]   (cross-correlation, voxels.py:36)
+  float2 b[16];
 };
 
 constexpr int CI_TY = 5;            // iy rows per CTA
 constexpr int CI_NT = G / CI_TY;    // 8 CTAs per scene
 constexpr int CI_THREADS = CI_TY * G;  // 200
-constexpr int CI_RED_STRIDE = 41;
-constexpr int CI_RED = C * CI_TY * CI_RED_STRIDE;          // 6560 floats
-constexpr int CI_XYACC = C * CI_TY * CI_RED_STRIDE;        // 6560 floats
-constexpr int CI_SMEM_BYTES = (CI_RED + CI_XYACC) * 4;     // 52,480 B
+constexpr int CI_RED_STRIDE = 44;   // 16-byte aligned rows; float4 reads are bank-conflict free (44 = 12 mod 32)
+constexpr int CI_RED = C * CI_TY * CI_RED_STRIDE;          // 7040 floats
+constexpr int CI_XYACC = C * CI_TY * CI_RED_STRIDE;        // 7040 floats
+constexpr int CI_SMEM_BYTES = (CI_RED + CI_XYACC) * 4;     // 56,320 B
 
 // grid (CI_NT, B), block CI_THREADS
 __global__ void __launch_bounds__(CI_THREADS, 2)
@@ -39,8 +39,8 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
                       float* __restrict__ xz_part,   // [B][CI_NT][40 ix][32][40 iz]
                       int B, const __grid_constant__ ConvInParams P) {
   extern __shared__ __align__(16) float smem[];
-  float* red = smem;                // [32*TY][41]
-  float* xyacc = red + CI_RED;      // [32*TY][41]  (col = ix)
+  float* red = smem;                // [32*TY][44]
+  float* xyacc = red + CI_RED;      // [32*TY][44]  (col = ix)
 
   const int tile = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -62,9 +62,9 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
       off[dy * 3 + dz] = ok[dy * 3 + dz] ? gy * G + gz : 0;
     }
 
-  float yz[C];
+  float2 yz[C / 2];   // channel pairs (FFMA2 / FADD2: half the issue slots of the scalar loop, same bits)
 #pragma unroll
-  for (int c = 0; c < C; ++c) yz[c] = 0.f;
+  for (int c = 0; c < C / 2; ++c) yz[c] = make_float2(0.f, 0.f);
 
   float win[3][9];  // [dx][dy*3+dz]; win[dx] holds slab ix+dx-1
   float nxt[9];     // prefetched slab
@@ -91,40 +91,47 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
 #pragma unroll
       for (int t = 0; t < 9; ++t) nxt[t] = 0.f;              // slab 40 (padding)
     }
-    float f[C];
+    float2 f[C / 2];
 #pragma unroll
-    for (int c = 0; c < C; ++c) f[c] = P.b[c];
+    for (int c = 0; c < C / 2; ++c) f[c] = P.b[c];
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const float v = win[dx][t];
 #pragma unroll
-        for (int c = 0; c < C; ++c) f[c] = fmaf(P.w[dx * 9 + t][c], v, f[c]);
+        for (int c = 0; c < C / 2; ++c) fma2(f[c], P.w[dx * 9 + t][c], v);
       }
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float r = fmaxf(f[c], 0.f);
-      yz[c] += r;
-      red[(c * CI_TY + iyl) * CI_RED_STRIDE + iz] = r;
+    for (int c = 0; c < C / 2; ++c) {
+      const float2 r = make_float2(fmaxf(f[c].x, 0.f), fmaxf(f[c].y, 0.f));
+      add2(yz[c], r);
+      red[((2 * c) * CI_TY + iyl) * CI_RED_STRIDE + iz] = r.x;
+      red[((2 * c + 1) * CI_TY + iyl) * CI_RED_STRIDE + iz] = r.y;
     }
     __syncthreads();
     // xy[c][iy][ix] = sum over iz (ascending, the reference's scatter order)
     if (tid < C * CI_TY) {
       const float* r = red + tid * CI_RED_STRIDE;
       float s = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < G; ++k) s += r[k];
+#pragma unroll
+      for (int k = 0; k < G; k += 4) {
+        const float4 q = ld4(r + k);
+        s += q.x; s += q.y; s += q.z; s += q.w;
+      }
       xyacc[tid * CI_RED_STRIDE + ix] = s;
     }
     // xz partial[ix][c][iz] = sum over this CTA's TY rows
     float* part = xz_part + (((size_t)b * CI_NT + tile) * G + ix) * (C * G);
-    for (int o = tid; o < C * G; o += CI_THREADS) {
-      const int c = o / G, z = o % G;
-      float s = 0.f;
+    for (int o = tid; o < C * (G / 4); o += CI_THREADS) {   // four iz per thread
+      const int c = o / (G / 4), z = (o % (G / 4)) * 4;
+      float4 s = ld4(red + (c * CI_TY) * CI_RED_STRIDE + z);
 #pragma unroll
-      for (int r = 0; r < CI_TY; ++r) s += red[(c * CI_TY + r) * CI_RED_STRIDE + z];
-      part[o] = s;
+      for (int r = 1; r < CI_TY; ++r) {
+        const float4 q = ld4(red + (c * CI_TY + r) * CI_RED_STRIDE + z);
+        s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+      }
+      st4(part + c * G + z, s);
     }
     __syncthreads();
   }
@@ -132,7 +139,7 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
   // yz[c][iz][iy]: transpose through smem so that rows of TY consecutive iy are written together
   float* stage = red;  // [32][40][TY] = 6400 floats <= CI_RED
 #pragma unroll
-  for (int c = 0; c < C; ++c) stage[(c * G + iz) * CI_TY + iyl] = yz[c] / 40.0f;
+  for (int c = 0; c < C; ++c) stage[(c * G + iz) * CI_TY + iyl] = ((c & 1) ? yz[c / 2].y : yz[c / 2].x) / 40.0f;
   __syncthreads();
   float* pre_yz = pre + ((size_t)(2 * B + b) * C) * G2;
   for (int o = tid; o < C * G * CI_TY; o += CI_THREADS) {

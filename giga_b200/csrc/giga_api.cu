@@ -441,8 +441,8 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
     if (!get(ctx, "encoder.conv_in.weight", 32 * 27, &w) || !get(ctx, "encoder.conv_in.bias", 32, &b))
       return fail(GIGA_ESTATE, "encoder.conv_in.{weight,bias}: missing or wrong size");
     for (int c = 0; c < 32; ++c) {
-      for (int t = 0; t < 27; ++t) ctx->conv_in.w[t][c] = w[c * 27 + t];  // [co][0][dx][dy][dz] -> [tap][co]
-      ctx->conv_in.b[c] = b[c];
+      for (int t = 0; t < 27; ++t) (&ctx->conv_in.w[t][0].x)[c] = w[c * 27 + t];  // [co][0][dx][dy][dz] -> [tap][co]
+      (&ctx->conv_in.b[0].x)[c] = b[c];
     }
     std::vector<float> blob(ctx->el.total, 0.f);
     for (int c = 0; c < 32; ++c)

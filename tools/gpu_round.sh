@@ -17,11 +17,11 @@ if [ -z "$2" ]; then
   echo "== ncu launch list"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --log-file $OUT/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1
-  echo "== ncu full: conv3x3 (10 layers of one step)"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3x3_kernel -s 30 -c 10 -o $OUT/prof_conv3x3 -f \
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_conv.log 2>&1
-  echo "== ncu full: decoder + conv_in + convT"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'decode_points|conv_in_planes|convT2x2|conv1x1|xz_finish' -s 21 -c 7 -o $OUT/prof_misc -f \
+  echo "== ncu full: U-Net kernels of one step (tcgen05 convs, pools, layout)"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'conv_tall_persistent|pool_tall|nchw_to_tall' -s 45 -c 15 -o $OUT/prof_unet -f \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_unet.log 2>&1
+  echo "== ncu full: conv_in + decoder + argmax of one step"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'decode_points|conv_in_planes|xz_finish|scene_argmax' -s 15 -c 5 -o $OUT/prof_misc -f \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_misc.log 2>&1
   ls -la $OUT
 fi
