@@ -205,10 +205,8 @@ def main():
 
     def step(i):
         k = i % POOL
-        c = net.encode_inputs(xs[k])
-        qual, rot, width = net.decode(ps[k], c)
-        occ = net.decoder_tsdf(pts[k], c)   # as forward() does (models/__init__.py:64)
-        net.scene_argmax(qual, gather_val[rank], gather_idx[rank])
+        # net(x, p, p_tsdf=...) plus the per-scene arg-max, one C-ABI call (giga_forward)
+        (qual, rot, width, occ), _ = net.forward_with_argmax(xs[k], ps[k], pts[k], gather_val[rank], gather_idx[rank])
         if world > 1:
             dist.all_gather_into_tensor(gather_val, gather_val[rank].clone())
             dist.all_gather_into_tensor(gather_idx, gather_idx[rank].clone())

@@ -151,6 +151,8 @@ struct giga_ctx {
   float* d_pre = nullptr;      // [3][B][32][1600]
   float* d_xzpart = nullptr;   // [B][CI_NT][40][32][40]
   float* d_yzpart = nullptr;   // [B][CT_NG][40][32][40]  (tensor-core conv_in)
+  float* d_planes = nullptr;   // [3][B][40][40][32] plane features of giga_forward calls that pass planes = NULL
+  int planes_cap = 0;
   float* d_act[kNumActs] = {};
   float* d_tall[kNumActs + 1] = {};   // TALL pre-split activations ([0] = pre, [1+i] = kActs[i]) for the tensor-core encoder
   long tall_ps[kNumActs + 1] = {};
@@ -392,7 +394,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_yzpart};
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_yzpart, ctx->d_planes};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : ctx->slot) {
@@ -784,6 +786,38 @@ int giga_scene_argmax(giga_ctx* ctx, const float* qual, int B, int N, float* bes
     scene_argmax_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(qual, N, best_val, best_idx);
   }
   CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+int giga_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, int Ng, const float* p_tsdf, int No, float* planes,
+                 float* qual, float* rot, float* width, float* occ, float* best_val, int* best_idx, void* stream) {
+  if (!ctx || !tsdf || B <= 0) return fail(GIGA_EINVAL, "giga_forward: bad argument");
+  const bool grasp = p && Ng > 0, geo = p_tsdf && No > 0;
+  if (!grasp && !geo) return fail(GIGA_EINVAL, "giga_forward: no query points");
+  if ((best_val || best_idx) && !(grasp && best_val && best_idx && qual))
+    return fail(GIGA_EINVAL, "giga_forward: the arg-max needs the grasp heads and both best_val and best_idx");
+  if (!planes) {
+    if (int r = set_device(ctx)) return r;
+    if (B > ctx->planes_cap) {
+      CU_TRY(cudaDeviceSynchronize());
+      if (ctx->d_planes) cudaFree(ctx->d_planes);
+      ctx->d_planes = nullptr;
+      ctx->planes_cap = 0;
+      CU_TRY(cudaMalloc(&ctx->d_planes, sizeof(float) * 3 * (size_t)B * G2 * C));
+      ctx->planes_cap = B;
+    }
+    planes = ctx->d_planes;
+  }
+  if (int r = giga_encode(ctx, tsdf, B, planes, stream)) return r;
+  if (grasp) {
+    const unsigned hm = ctx->heads & (GIGA_HEAD_QUAL | GIGA_HEAD_ROT | GIGA_HEAD_WIDTH);
+    if (!hm) return fail(GIGA_ESTATE, "giga_forward: no grasp head committed (pass p = NULL for giga_geo)");
+    if (int r = giga_decode(ctx, planes, B, p, Ng, hm, qual, rot, width, nullptr, stream)) return r;
+  }
+  if (geo)
+    if (int r = giga_decode(ctx, planes, B, p_tsdf, No, GIGA_HEAD_TSDF, nullptr, nullptr, nullptr, occ, stream)) return r;
+  if (best_val)
+    if (int r = giga_scene_argmax(ctx, qual, B, Ng, best_val, best_idx, stream)) return r;
   return GIGA_OK;
 }
 

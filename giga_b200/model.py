@@ -25,6 +25,7 @@ import weakref
 
 from ._lib import HEAD_GRASP, HEAD_QUAL, HEAD_RAW, HEAD_ROT, HEAD_TSDF, HEAD_WIDTH, check, lib
 
+_STRUCT_VERSION = [0]   # bumped whenever any weight/bias attribute is (re)bound
 PLANES = ("xz", "xy", "yz")
 GRID = 40
 CDIM = 32
@@ -44,6 +45,10 @@ class _Affine(nn.Module):
         bound = 1.0 / math.sqrt(fan_in)
         nn.init.uniform_(self.weight, -bound, bound)  # kaiming_uniform_(a=sqrt(5)) == U(+-1/sqrt(fan_in))
         nn.init.uniform_(self.bias, -bound, bound)
+
+    def __setattr__(self, name, value):   # a re-bound Parameter object invalidates the engine's cached tensor list
+        _STRUCT_VERSION[0] += 1
+        super().__setattr__(name, value)
 
 
 def _linear(n_in, n_out):
@@ -145,6 +150,9 @@ class _Engine:
               "giga_ctx_create")
         self.h = h
         self.param_key = None
+        self.param_names = None
+        self.tensors = []
+        self.struct_version = -1
 
     def __del__(self):
         try:
@@ -155,10 +163,17 @@ class _Engine:
             pass
 
     def sync_params(self, module: nn.Module):
-        params = list(module.state_dict(keep_vars=True).items())
-        key = tuple((k, v.data_ptr(), v._version) for k, v in params)
-        if key == self.param_key:
+        # fast path (every call): the cached tensor objects still hold the committed storage and version
+        if self.struct_version == _STRUCT_VERSION[0] and self.param_key == tuple((v.data_ptr(), v._version) for v in self.tensors):
             return
+        params = list(module.state_dict(keep_vars=True).items())
+        self.tensors = [v for _, v in params]
+        self.struct_version = _STRUCT_VERSION[0]
+        key = tuple((v.data_ptr(), v._version) for v in self.tensors)
+        names = tuple(k for k, _ in params)
+        if key == self.param_key and names == self.param_names:
+            return
+        self.param_names = names
         for k, v in params:
             t = v.detach()
             if t.dtype != torch.float32 or not t.is_contiguous():
@@ -396,13 +411,49 @@ class ConvolutionalOccupancyNetwork(_GigaBase):
         if device is not None:
             self.to(device)
 
-    def _forward_native(self, inputs, p, p_tsdf=None):
-        c = self.encode_inputs(inputs)
-        qual, rot, width = self.decode(p, c)
+    def _forward_native(self, inputs, p, p_tsdf=None, best=None):
+        """One C-ABI call (giga_forward): encode + grasp heads at p + TSDF head at p_tsdf [+ per-scene arg-max into
+        best = (val f32[B], idx i32[B])]; the plane features stay in a library-owned buffer."""
+        eng = self._engine()
+        x = _prep(inputs, eng.device)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (GRID, GRID, GRID):
+            raise _lib.GigaError(f"inputs must be (B,{GRID},{GRID},{GRID}), got {tuple(inputs.shape)}")
+        B = x.shape[0]
+        pts = _prep(p, eng.device)
+        if pts.dim() != 3 or pts.shape[2] != 3 or pts.shape[0] != B:
+            raise _lib.GigaError(f"points must be (B,N,3) with B={B}, got {tuple(p.shape)}")
+        N = pts.shape[1]
+        mk = lambda *s: torch.empty(s, device=eng.device, dtype=torch.float32)
+        qual, rot, width = mk(B, N), mk(B, N, 4), mk(B, N)
+        pt = occ = None
+        No = 0
         if p_tsdf is not None:
-            tsdf = self.decoder_tsdf(p_tsdf, c)
-            return qual, rot, width, tsdf
+            if not hasattr(self, "decoder_tsdf"):
+                raise AttributeError("this model has no decoder_tsdf")   # as the reference (models/__init__.py:64)
+            pt = _prep(p_tsdf, eng.device)
+            if pt.dim() != 3 or pt.shape[2] != 3 or pt.shape[0] != B:
+                raise _lib.GigaError(f"p_tsdf must be (B,N,3) with B={B}, got {tuple(p_tsdf.shape)}")
+            No = pt.shape[1]
+            occ = mk(B, No)
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        bv, bi = best if best is not None else (None, None)
+        check(lib.giga_forward(eng.h, ptr(x), B, ptr(pts), N, ptr(pt), No, C.c_void_p(0), ptr(qual), ptr(rot), ptr(width), ptr(occ),
+                               ptr(bv), ptr(bi), _stream(eng.device)), "giga_forward")
+        if p_tsdf is not None:
+            return qual, rot, width, occ
         return qual, rot, width
+
+    def forward_with_argmax(self, inputs, p, p_tsdf=None, out_val=None, out_idx=None):
+        """forward() plus the final grasp-score reduction (per-scene max quality, first arg-max) in the same call;
+        out_val / out_idx may be this rank's slices of the all-gather buffers."""
+        dev = next(self.parameters()).device
+        B = inputs.shape[0]
+        if out_val is None:
+            out_val = torch.empty(B, device=dev, dtype=torch.float32)
+        if out_idx is None:
+            out_idx = torch.empty(B, device=dev, dtype=torch.int32)
+        assert out_val.is_contiguous() and out_idx.is_contiguous() and out_idx.dtype == torch.int32
+        return self._forward_native(inputs, p, p_tsdf, best=(out_val, out_idx)), (out_val, out_idx)
 
     def forward(self, inputs, p, p_tsdf=None, sample=True, **kwargs):
         """models/__init__.py:42-67"""

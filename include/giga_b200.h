@@ -96,6 +96,16 @@ int giga_sample_feature(giga_ctx *ctx, const float *planes, int B, const float *
  * best_val[b], best_idx[b]; the multi-GPU path points these into the all-gather buffer. */
 int giga_scene_argmax(giga_ctx *ctx, const float *qual, int B, int N, float *best_val, int *best_idx, void *stream);
 
+/* whole forward with DEVICE buffers in ONE call: replaces `net(inputs, p, p_tsdf=...)`
+ * (`ConvolutionalOccupancyNetwork.forward`, models/__init__.py:42-67): giga_encode, giga_decode of the
+ * committed grasp heads at `p` (Ng points; p may be NULL/0 for giga_geo), giga_decode of the TSDF head
+ * at `p_tsdf` (No points; may be NULL/0) and, when best_val/best_idx are non-NULL, giga_scene_argmax of
+ * qual.  `planes` receives the plane features ([3][B][40][40][32]); NULL keeps them in a ctx-owned
+ * buffer.  Nothing synchronises. */
+int giga_forward(giga_ctx *ctx, const float *tsdf, int B, const float *p, int Ng, const float *p_tsdf, int No,
+                 float *planes, float *qual, float *rot, float *width, float *occ, float *best_val, int *best_idx,
+                 void *stream);
+
 /* end-to-end host entry: replaces `predict()` (detection_implicit.py:99-113) /
  * `net(x, pos, p_tsdf=pos_occ)` (scripts/train_giga.py:204) with HOST buffers: H2D of
  * tsdf/points, encode, decode of the grasp heads at `p` (Ng pts) and of the TSDF head at

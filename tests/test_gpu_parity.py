@@ -354,3 +354,26 @@ def test_training_bridge_matches_reference_gradients(oracle_sd):
     with torch.no_grad():
         out2 = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
     assert not torch.equal(out2[3], out[3].detach())
+
+
+def test_single_call_forward_equals_staged_calls(net, oracle_sd):
+    """forward() is one C-ABI call (giga_forward); encode_inputs -> decode -> decoder_tsdf -> scene_argmax as
+    separate calls must give the same bits.  Re-bound / replaced parameters are picked up."""
+    x, p, pt = O.seeded_inputs(3, 257, seed=71)
+    xd, pd, ptd = x.to(DEV), p.to(DEV), pt.to(DEV)
+    with torch.no_grad():
+        c = net.encode_inputs(xd)
+        q, r, w = net.decode(pd, c)
+        occ = torch.sigmoid(net.decode_occ(ptd, c).logits) * 0 + net.decoder_tsdf(ptd, c)
+        v, i = net.scene_argmax(q)
+        (q2, r2, w2, o2), (v2, i2) = net.forward_with_argmax(xd, pd, ptd)
+        for a, b in zip((q, r, w, occ, v, i), (q2, r2, w2, o2, v2, i2)):
+            assert torch.equal(a, b)
+        q3, r3, w3 = net(xd, pd)
+        assert torch.equal(q3, q) and torch.equal(r3, r) and torch.equal(w3, w)
+    other = make_net("giga", oracle_sd)
+    with torch.no_grad():
+        base = other(xd, pd)
+        other.decoder_width.fc_out.bias = torch.nn.Parameter(other.decoder_width.fc_out.bias.detach() + 2.0)   # new Parameter object
+        moved = other(xd, pd)
+    assert torch.allclose(moved[2], base[2] + 2.0, atol=1e-6) and torch.equal(moved[0], base[0])
