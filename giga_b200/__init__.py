@@ -10,5 +10,7 @@ from ._lib import GigaError, LIB_PATH, HEAD_QUAL, HEAD_ROT, HEAD_WIDTH, HEAD_TSD
 from .model import (ConvolutionalOccupancyNetwork, ConvolutionalOccupancyNetworkGeometry, LocalDecoder,  # noqa: F401
                     LocalVoxelEncoder, PlaneFeatures, UNet)
 from .networks import get_network, load_network  # noqa: F401
+from . import detection_implicit  # noqa: F401
+from .detection_implicit import VGNImplicit  # noqa: F401
 
 __version__ = "0.1.0"

@@ -36,12 +36,28 @@ SYMBOLS = {
     "giga_forward_host_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_forward_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "giga_select_params_default": (None, [C.c_void_p]),
+    "giga_gaussian_kernel1d": (C.c_int, [C.c_double, C.c_int, C.POINTER(C.c_double)]),
+    "giga_select_grasps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_ctx_set_lattice": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "giga_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_detect_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_ctx_launch_count": (C.c_long, [C.c_void_p]),
     "giga_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "giga_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "giga_ctx_timing_report": (C.c_long, [C.c_void_p, C.c_char_p, C.c_long]),
     "giga_debug_copy": (C.c_long, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p]),
 }
+
+
+class SelectParams(C.Structure):
+    """giga_select_params (include/giga_b200.h)"""
+    _fields_ = [("gaussian_sigma", C.c_double), ("min_width", C.c_float), ("max_width", C.c_float), ("out_th", C.c_float),
+                ("lim_x", C.c_int), ("lim_y", C.c_int), ("lim_z", C.c_int), ("low_th", C.c_float), ("threshold", C.c_float),
+                ("force_detection", C.c_int), ("max_filter_size", C.c_int)]
 
 
 class GigaError(RuntimeError):

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -15,6 +16,7 @@
 #include "conv_in_tc.cuh"
 #include "decoder.cuh"
 #include "decoder_tc.cuh"
+#include "planner.cuh"
 #include "unet.cuh"
 #include "unet_tall.cuh"
 
@@ -166,6 +168,15 @@ struct giga_ctx {
   };
   HostSlot slot[3];   // [0],[1]: pipelined submit/wait; [2]: the synchronous giga_forward_host
   cudaStream_t st_h2d = nullptr, st_compute = nullptr, st_d2h = nullptr;   // pipelined host path
+  // planner post-processing (planner.cuh)
+  int pl_cap_B = 0;
+  float *d_pl_a = nullptr, *d_pl_b = nullptr, *d_pl_qlow = nullptr, *d_pl_cval = nullptr;   // [B][64000] each
+  int *d_pl_cidx = nullptr, *d_pl_flag = nullptr;                                           // [B][64000], [2B] (flag | count)
+  float* d_lattice = nullptr;    // [64000][3] as set by giga_ctx_set_lattice
+  int det_cap_B = 0, det_cap_K = 0, det_lat_B = 0;
+  float *d_det_pts = nullptr, *d_det_qual = nullptr, *d_det_rot = nullptr, *d_det_width = nullptr;   // [B][64000](x3|x4)
+  float *d_det_tsdf = nullptr, *d_det_tsdfp = nullptr;                                       // host-entry staging
+  int* d_det_out = nullptr;      // [B][K][4] rot | [B][K] score | [B][K] width | [B][K] index | [B] count (words)
   long launches = 0;
   bool attrs_set = false;
   // optional per-kernel CUDA-event timing (bench.py roofline): events recorded on the launch stream
@@ -409,6 +420,10 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (ctx->st_compute) cudaStreamDestroy(ctx->st_compute);
   if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
   if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+  void* pl[] = {ctx->d_pl_a, ctx->d_pl_b, ctx->d_pl_qlow, ctx->d_pl_cval, ctx->d_pl_cidx, ctx->d_pl_flag, ctx->d_lattice, ctx->d_det_pts,
+                ctx->d_det_qual, ctx->d_det_rot, ctx->d_det_width, ctx->d_det_tsdf, ctx->d_det_tsdfp, ctx->d_det_out};
+  for (void* p : pl)
+    if (p) cudaFree(p);
   for (float* p : ctx->d_act)
     if (p) cudaFree(p);
   for (float* p : ctx->d_tall)
@@ -934,6 +949,203 @@ int giga_forward_host_wait(giga_ctx* ctx, int slot) {
   if (!s.pending) return fail(GIGA_ESTATE, "giga_forward_host_wait: nothing submitted on this slot");
   CU_TRY(cudaEventSynchronize(s.ev_done));
   s.pending = false;
+  return GIGA_OK;
+}
+
+// ---- planner post-processing ---------------------------------------------------------------------------
+void giga_select_params_default(giga_select_params* p) {
+  if (!p) return;
+  p->gaussian_sigma = 1.0;
+  p->min_width = 0.033f;
+  p->max_width = 0.233f;
+  p->out_th = 0.5f;
+  const double voxel_size = 0.3 / 40;
+  p->lim_x = (int)(0.02 / voxel_size);
+  p->lim_y = (int)(0.02 / voxel_size);
+  p->lim_z = (int)(0.055 / voxel_size);
+  p->low_th = 0.5f;
+  p->threshold = 0.9f;
+  p->force_detection = 0;
+  p->max_filter_size = 4;
+}
+
+int giga_gaussian_kernel1d(double sigma, int radius, double* out) {
+  if (!(sigma > 0) || radius < 0 || radius > PL_MAXR || !out) return fail(GIGA_EINVAL, "giga_gaussian_kernel1d: bad argument");
+  const int n = 2 * radius + 1;
+  const double sigma2 = sigma * sigma, f = -0.5 / sigma2;
+  double a[2 * PL_MAXR + 1];
+  for (int i = 0; i < n; ++i) {
+    const long x = i - radius;
+    a[i] = exp(f * (double)(x * x));
+  }
+  // numpy's pairwise sum (what `phi_x.sum()` does): plain loop below 8 elements, 8 accumulators from there on
+  double sum;
+  if (n < 8) {
+    sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += a[i];
+  } else {
+    double r[8];
+    for (int k = 0; k < 8; ++k) r[k] = a[k];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+      for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+    sum = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) sum += a[i];
+  }
+  for (int i = 0; i < n; ++i) out[i] = a[i] / sum;
+  return GIGA_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int make_select(const giga_select_params* prm, SelectParams& S) {
+  if (!prm) return fail(GIGA_EINVAL, "giga_select_params is null");
+  if (!(prm->gaussian_sigma > 0)) return fail(GIGA_EINVAL, "giga_select_params: gaussian_sigma must be > 0");
+  const int radius = (int)(4.0 * prm->gaussian_sigma + 0.5);   // scipy: int(truncate * sd + 0.5), truncate = 4
+  if (radius > PL_MAXR) return fail(GIGA_EINVAL, "giga_select_params: gaussian_sigma too large (radius > 8)");
+  if (prm->max_filter_size < 1 || prm->max_filter_size > G) return fail(GIGA_EINVAL, "giga_select_params: bad max_filter_size");
+  if (prm->lim_x < 0 || prm->lim_y < 0 || prm->lim_z < 0) return fail(GIGA_EINVAL, "giga_select_params: negative bound limit");
+  if (int r = giga_gaussian_kernel1d(prm->gaussian_sigma, radius, S.w)) return r;   // symmetric: reversing it (scipy correlates) is a no-op
+  S.radius = radius;
+  S.min_width = prm->min_width; S.max_width = prm->max_width; S.out_th = prm->out_th;
+  S.lim_x = prm->lim_x; S.lim_y = prm->lim_y; S.lim_z = prm->lim_z;
+  S.low_th = prm->low_th; S.threshold = prm->threshold;
+  S.force_detection = prm->force_detection; S.max_filter_size = prm->max_filter_size;
+  return GIGA_OK;
+}
+
+int ensure_planner_ws(giga_ctx* ctx, int B) {
+  if (B <= ctx->pl_cap_B) return GIGA_OK;
+  CU_TRY(cudaDeviceSynchronize());
+  void** ptrs[] = {(void**)&ctx->d_pl_a, (void**)&ctx->d_pl_b, (void**)&ctx->d_pl_qlow, (void**)&ctx->d_pl_cval, (void**)&ctx->d_pl_cidx,
+                   (void**)&ctx->d_pl_flag};
+  for (void** q : ptrs) { if (*q) cudaFree(*q); *q = nullptr; }
+  ctx->pl_cap_B = 0;
+  const size_t vol = sizeof(float) * (size_t)B * G3;
+  CU_TRY(cudaMalloc(&ctx->d_pl_a, vol));
+  CU_TRY(cudaMalloc(&ctx->d_pl_b, vol));
+  CU_TRY(cudaMalloc(&ctx->d_pl_qlow, vol));
+  CU_TRY(cudaMalloc(&ctx->d_pl_cval, vol));
+  CU_TRY(cudaMalloc(&ctx->d_pl_cidx, vol));
+  CU_TRY(cudaMalloc(&ctx->d_pl_flag, sizeof(int) * 2 * (size_t)B));
+  ctx->pl_cap_B = B;
+  return GIGA_OK;
+}
+
+int ensure_detect_ws(giga_ctx* ctx, int B, int K) {
+  if (B > ctx->det_cap_B) {
+    CU_TRY(cudaDeviceSynchronize());
+    void** ptrs[] = {(void**)&ctx->d_det_pts, (void**)&ctx->d_det_qual, (void**)&ctx->d_det_rot, (void**)&ctx->d_det_width,
+                     (void**)&ctx->d_det_tsdf, (void**)&ctx->d_det_tsdfp};
+    for (void** q : ptrs) { if (*q) cudaFree(*q); *q = nullptr; }
+    ctx->det_cap_B = ctx->det_lat_B = 0;
+    const size_t vol = sizeof(float) * (size_t)B * G3;
+    CU_TRY(cudaMalloc(&ctx->d_det_pts, vol * 3));
+    CU_TRY(cudaMalloc(&ctx->d_det_qual, vol));
+    CU_TRY(cudaMalloc(&ctx->d_det_rot, vol * 4));
+    CU_TRY(cudaMalloc(&ctx->d_det_width, vol));
+    CU_TRY(cudaMalloc(&ctx->d_det_tsdf, vol));
+    CU_TRY(cudaMalloc(&ctx->d_det_tsdfp, vol));
+    ctx->det_cap_B = B;
+  }
+  if ((long)B * K > (long)ctx->det_cap_K) {
+    CU_TRY(cudaDeviceSynchronize());
+    if (ctx->d_det_out) cudaFree(ctx->d_det_out);
+    ctx->d_det_out = nullptr;
+    ctx->det_cap_K = 0;
+    CU_TRY(cudaMalloc(&ctx->d_det_out, sizeof(int) * ((size_t)B + 7 * (size_t)B * K)));
+    ctx->det_cap_K = B * K;
+  }
+  return GIGA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int giga_select_grasps(giga_ctx* ctx, const float* tsdf, const float* qual, const float* rot, const float* width, int B,
+                       const giga_select_params* prm, int K, int* count, float* score, int* index, float* out_rot, float* out_width,
+                       float* qual_vol, void* stream) {
+  if (!ctx || !tsdf || !qual || !rot || !width || B <= 0 || K <= 0 || !count || !score || !index || !out_rot || !out_width)
+    return fail(GIGA_EINVAL, "giga_select_grasps: bad argument");
+  if ((reinterpret_cast<uintptr_t>(rot) | reinterpret_cast<uintptr_t>(out_rot)) & 15)
+    return fail(GIGA_EINVAL, "giga_select_grasps: rot / out_rot must be 16-byte aligned (quaternions move as float4)");
+  SelectParams S;
+  if (int r = make_select(prm, S)) return r;
+  if (int r = set_device(ctx)) return r;
+  if (int r = ensure_planner_ws(ctx, B)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ceil_div(B * G3, 256);
+  int *flag = ctx->d_pl_flag, *cnt = ctx->d_pl_flag + B;
+  CU_TRY(cudaMemsetAsync(flag, 0, sizeof(int) * 2 * B, st));
+  { LaunchScope ls(ctx, "planner:gauss_x", st); gauss_axis_kernel<0><<<blocks, 256, 0, st>>>(qual, ctx->d_pl_a, B, S); }
+  { LaunchScope ls(ctx, "planner:gauss_y", st); gauss_axis_kernel<1><<<blocks, 256, 0, st>>>(ctx->d_pl_a, ctx->d_pl_b, B, S); }
+  { LaunchScope ls(ctx, "planner:gauss_z+mask", st);
+    gauss_z_mask_kernel<<<blocks, 256, 0, st>>>(ctx->d_pl_b, tsdf, width, qual_vol, ctx->d_pl_qlow, flag, B, S); }
+  { LaunchScope ls(ctx, "planner:nms", st);
+    grasp_nms_kernel<<<blocks, 256, 0, st>>>(ctx->d_pl_qlow, flag, cnt, ctx->d_pl_cval, ctx->d_pl_cidx, B, S); }
+  { LaunchScope ls(ctx, "planner:rank", st);
+    grasp_rank_kernel<<<dim3(G3 / 256, B), 256, 0, st>>>(cnt, flag, ctx->d_pl_cval, ctx->d_pl_cidx, rot, width, K, count, score, index,
+                                                        out_rot, out_width, S); }
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+int giga_ctx_set_lattice(giga_ctx* ctx, const float* pos, int N) {
+  if (!ctx || !pos || N != G3) return fail(GIGA_EINVAL, "giga_ctx_set_lattice: the planner lattice is [64000][3] (40^3 volumes)");
+  if (int r = set_device(ctx)) return r;
+  CU_TRY(cudaDeviceSynchronize());
+  if (!ctx->d_lattice) CU_TRY(cudaMalloc(&ctx->d_lattice, sizeof(float) * 3 * G3));
+  CU_TRY(cudaMemcpy(ctx->d_lattice, pos, sizeof(float) * 3 * G3, cudaMemcpyHostToDevice));
+  ctx->det_lat_B = 0;   // re-broadcast on the next giga_detect
+  return GIGA_OK;
+}
+
+int giga_detect(giga_ctx* ctx, const float* tsdf, const float* tsdf_process, int B, const giga_select_params* prm, int K, int* count,
+                float* score, int* index, float* out_rot, float* out_width, void* stream) {
+  if (!ctx || !tsdf || B <= 0 || K <= 0) return fail(GIGA_EINVAL, "giga_detect: bad argument");
+  if (!ctx->d_lattice) return fail(GIGA_ESTATE, "giga_detect: no query lattice (call giga_ctx_set_lattice first)");
+  if (int r = set_device(ctx)) return r;
+  if (int r = ensure_detect_ws(ctx, B, K)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->det_lat_B < B) {
+    LaunchScope ls(ctx, "planner:broadcast_lattice", st);
+    broadcast_points_kernel<<<ceil_div(3 * G3, 256), 256, 0, st>>>(ctx->d_lattice, ctx->d_det_pts, 3 * G3, ctx->det_cap_B);
+    ctx->det_lat_B = ctx->det_cap_B;
+  }
+  if (int r = giga_forward(ctx, tsdf, B, ctx->d_det_pts, G3, nullptr, 0, nullptr, ctx->d_det_qual, ctx->d_det_rot, ctx->d_det_width, nullptr,
+                           nullptr, nullptr, stream))
+    return r;
+  return giga_select_grasps(ctx, tsdf_process ? tsdf_process : tsdf, ctx->d_det_qual, ctx->d_det_rot, ctx->d_det_width, B, prm, K, count,
+                            score, index, out_rot, out_width, nullptr, stream);
+}
+
+int giga_detect_host(giga_ctx* ctx, const float* tsdf, const float* tsdf_process, int B, const giga_select_params* prm, int K, int* count,
+                     float* score, int* index, float* out_rot, float* out_width, void* stream) {
+  if (!ctx || !tsdf || B <= 0 || K <= 0 || !count || !score || !index || !out_rot || !out_width)
+    return fail(GIGA_EINVAL, "giga_detect_host: bad argument");
+  if (int r = set_device(ctx)) return r;
+  if (int r = ensure_detect_ws(ctx, B, K)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t vol = sizeof(float) * (size_t)B * G3, bk = (size_t)B * K;
+  CU_TRY(cudaMemcpyAsync(ctx->d_det_tsdf, tsdf, vol, cudaMemcpyHostToDevice, st));
+  if (tsdf_process) CU_TRY(cudaMemcpyAsync(ctx->d_det_tsdfp, tsdf_process, vol, cudaMemcpyHostToDevice, st));
+  float* d_rot = reinterpret_cast<float*>(ctx->d_det_out);   // float4 stores: keep the quaternions 16-byte aligned
+  float* d_score = d_rot + 4 * bk;
+  float* d_width = d_score + bk;
+  int* d_index = reinterpret_cast<int*>(d_width + bk);
+  int* d_count = d_index + bk;
+  if (int r = giga_detect(ctx, ctx->d_det_tsdf, tsdf_process ? ctx->d_det_tsdfp : nullptr, B, prm, K, d_count, d_score, d_index, d_rot,
+                          d_width, stream))
+    return r;
+  CU_TRY(cudaMemcpyAsync(count, d_count, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(index, d_index, sizeof(int) * bk, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(score, d_score, sizeof(float) * bk, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(out_rot, d_rot, sizeof(float) * 4 * bk, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(out_width, d_width, sizeof(float) * bk, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
   return GIGA_OK;
 }
 

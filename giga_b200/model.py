@@ -340,6 +340,27 @@ class _GigaBase(nn.Module):
                                     C.c_void_p(out_idx.data_ptr()), _stream(eng.device)), "giga_scene_argmax")
         return out_val, out_idx
 
+    def select_grasps(self, tsdf, qual, rot, width, params=None, K: int = 512, return_qual_vol: bool = False):
+        """process() + bound() + select() of the reference planner (detection_implicit.py:115-143, 87-97, 146-174) on
+        DEVICE volumes of B scenes (giga_select_grasps): tsdf (B,40,40,40), qual/width (B,64000), rot (B,64000,4) ->
+        count (B,) int32, score (B,K), index (B,K) int32, rot (B,K,4), width (B,K) [, processed quality volume (B,40,40,40)]."""
+        from .detection_implicit import select_params
+        eng = self._engine()
+        t, q, r, w = (_prep(a, eng.device) for a in (tsdf, qual, rot, width))
+        B = t.shape[0]
+        if tuple(t.shape) != (B, GRID, GRID, GRID) or q.numel() != B * GRID ** 3 or r.numel() != 4 * B * GRID ** 3 or w.numel() != B * GRID ** 3:
+            raise _lib.GigaError("select_grasps takes 40^3 volumes: tsdf (B,40,40,40), qual/width (B,64000), rot (B,64000,4)")
+        params = params or select_params()
+        mk = lambda shape, dt: torch.zeros(shape, device=eng.device, dtype=dt)
+        count, score, index = mk((B,), torch.int32), mk((B, K), torch.float32), mk((B, K), torch.int32)
+        orot, owidth = mk((B, K, 4), torch.float32), mk((B, K), torch.float32)
+        qvol = mk((B, GRID, GRID, GRID), torch.float32) if return_qual_vol else None
+        ptr = lambda a: C.c_void_p(a.data_ptr()) if a is not None else C.c_void_p(0)
+        check(lib.giga_select_grasps(eng.h, ptr(t), ptr(q), ptr(r), ptr(w), B, C.byref(params), K, ptr(count), ptr(score), ptr(index),
+                                     ptr(orot), ptr(owidth), ptr(qvol), _stream(eng.device)), "giga_select_grasps")
+        out = (count, score, index, orot, owidth)
+        return out + (qvol,) if return_qual_vol else out
+
     def debug_activation(self, name: str, B: int) -> torch.Tensor:
         """Copy an intermediate activation of the last encode (tests only)."""
         eng = self._engine()

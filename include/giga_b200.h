@@ -123,6 +123,48 @@ int giga_forward_host_submit(giga_ctx *ctx, int slot, const float *tsdf, int B, 
                              float *qual, float *rot, float *width, float *occ);
 int giga_forward_host_wait(giga_ctx *ctx, int slot);
 
+/* planner post-processing ------------------------------------------------
+ * What detection_implicit.py does on the host with scipy.ndimage between predict() and the Grasp
+ * list, on the device for B scenes at once.  Volumes are [B][40][40][40] fp32 with flat voxel index
+ * v = (ix*40 + iy)*40 + iz = index of the lattice query point (VGNImplicit.__init__ :28-31). */
+typedef struct giga_select_params {
+  double gaussian_sigma;      /* process(gaussian_filter_sigma=1.0)                  :119,128-130 */
+  float  min_width, max_width;/* process(min_width=0.033, max_width=0.233)           :120-121,141 */
+  float  out_th;              /* process(out_th=0.5): surface mask from the TSDF     :122,133-138 */
+  int    lim_x, lim_y, lim_z; /* bound(): int(limit / voxel_size) = 2, 2, 7          :87-97       */
+  float  low_th;              /* LOW_TH = 0.5                                        :15,148      */
+  float  threshold;           /* select(threshold=qual_th=0.9)                       :146,153     */
+  int    force_detection;     /* keep only the best grasp when nothing passes        :149-150,169 */
+  int    max_filter_size;     /* NMS window of ndimage.maximum_filter, 4 (8 to visualise) :156    */
+} giga_select_params;
+/* the reference's defaults for the 0.3 m workspace (voxel_size 0.3/40) */
+void giga_select_params_default(giga_select_params *p);
+/* scipy's fp64 gaussian kernel (exp(-x^2/(2 sigma^2)) / sum, x = -radius..radius) as the device passes use it;
+ * out has 2*radius+1 entries.  Host-only helper (no GPU needed) so the weights can be checked against numpy. */
+int giga_gaussian_kernel1d(double sigma, int radius, double *out);
+/* process() + bound() + select() (detection_implicit.py:115-143, 87-97, 146-174) on DEVICE volumes:
+ * tsdf = the `tsdf_process` grid, qual/width [B][64000], rot [B][64000][4] = the three predicted volumes.
+ * Outputs (device): count[b] = number of grasps found for scene b (may exceed K); the first min(count,K)
+ * entries of score/index/out_rot/out_width [B][K](x4) are the grasps sorted by descending score (ties:
+ * larger voxel index first): score = smoothed quality, index = flat voxel index, out_rot = the raw predicted
+ * quaternion, out_width = predicted width.  qual_vol (optional, [B][64000]) receives the processed quality
+ * volume (what process()+bound() return).  rot and out_rot must be 16-byte aligned.  Nothing synchronises. */
+int giga_select_grasps(giga_ctx *ctx, const float *tsdf, const float *qual, const float *rot, const float *width, int B,
+                       const giga_select_params *prm, int K, int *count, float *score, int *index, float *out_rot,
+                       float *out_width, float *qual_vol, void *stream);
+/* the query lattice of the planner (`self.pos`, detection_implicit.py:28-31), HOST pointer [64000][3];
+ * copied to the device once and broadcast over the scenes of giga_detect calls (synchronous). */
+int giga_ctx_set_lattice(giga_ctx *ctx, const float *pos, int N);
+/* the whole planner, DEVICE buffers: replaces VGNImplicit.__call__ (detection_implicit.py:33-58) from the
+ * TSDF to the sorted grasps = giga_forward at the lattice (grasp heads only) + giga_select_grasps.
+ * tsdf_process may be NULL (= tsdf).  Outputs as giga_select_grasps. */
+int giga_detect(giga_ctx *ctx, const float *tsdf, const float *tsdf_process, int B, const giga_select_params *prm, int K,
+                int *count, float *score, int *index, float *out_rot, float *out_width, void *stream);
+/* same with HOST buffers in and out (H2D of the TSDFs, giga_detect, D2H of B*(1 + 7K) words); returns
+ * after the stream has drained.  This is the call a simulation loop makes per planning step. */
+int giga_detect_host(giga_ctx *ctx, const float *tsdf, const float *tsdf_process, int B, const giga_select_params *prm, int K,
+                     int *count, float *score, int *index, float *out_rot, float *out_width, void *stream);
+
 /* introspection ------------------------------------------------------------------- */
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 long giga_ctx_launch_count(const giga_ctx *ctx);
