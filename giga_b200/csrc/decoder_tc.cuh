@@ -1,4 +1,4 @@
-// Tensor-core implicit decoder (tcgen05 / TMEM, 3xTF32 operand splitting -> fp32-level accuracy).
+// Tensor-core implicit decoder (tcgen05 / TMEM, 3xFP16 operand splitting -> fp32-level accuracy).
 //
 // Same function as decode_points_kernel (decoder.cuh) -- tri-plane gather + LocalDecoder heads
 // (conv_onet/models/decoder.py:117-176, layers.py:39-47, models/__init__.py:119-123) -- but every
@@ -14,8 +14,13 @@
 //     five blocks, [160,256) = three partial accumulators (hi*hi, lo*hi, hi*lo) of the current 32x32 layer;
 //   * epilogues (bias, residual, ReLU, hi/lo split, write next A operand) run thread-per-point
 //     straight out of TMEM (tcgen05.ld 32x32b.x32), fc_p (K=3) and fc_out (N<=4) stay on CUDA cores;
-//   * 3xTF32: x*y ~= xh*yh + xl*yh + xh*yl with xh = rn_tf32(x), xl = x - xh (exact); measured
-//     error vs fp64 ~1e-6 relative (profiles/r01_tc_probe.txt), i.e. fp32-class.
+//   * 3xFP16: x*y ~= xh*yh + xl*yh + xh*yl with xh = fp16_rn(x), xl = fp16_rn(x - xh) (x - xh is exact in fp32); fp16 has
+//     tf32's 11-bit significand, so this is the 3xTF32 scheme at twice the K per MMA and half the operand bytes
+//     (tools/tc_f16_probe.cu: 2e-7 relative vs fp64).  fp16's narrow exponent is handled by a per-head power-of-two
+//     pre-scale 2^s of the weights chosen on the host (max |w| 2^s in [512, 1024)): the lo halves of all but
+//     negligible weights stay normal fp16 numbers; accumulators come out scaled by 2^s and the epilogues multiply by
+//     2^-s (exact).  Activations are O(1..50): their lo halves underflow gracefully below 2^-3 (absolute error
+//     <= 2^-25, fp32-class relative to the activation scale).  Activations are clamped to fp16's +-65504.
 #pragma once
 #include "common.cuh"
 #include "decoder.cuh"
@@ -26,58 +31,40 @@ namespace giga {
 
 // ---- packed per-head parameter blob for the tensor-core path (floats) ----
 constexpr int TW_FCP = 0;                         // Wt[3][32] + b[32]                      (128)
-constexpr int TW_FCC = 128;                       // [plane 3][hi,lo][ (k/4)*640 + n*4 + k%4 ], n = blk*32+j  (3*2*5120)
-constexpr int TW_FCC_SLICE = 5120;                //   one (plane, hi|lo) operand: N=160 x K=32
-constexpr int TW_BC = TW_FCC + 6 * TW_FCC_SLICE;  // 30848: fc_c biases [5][32]
-constexpr int TW_BLK = TW_BC + 160;               // 31008: per block W0hi W0lo W1hi W1lo (1024 each, (k/4)*128 + n*4 + k%4), b0[32], b1[32]
-constexpr int TW_BLK_SIZE = 4 * 1024 + 64;        // 4160
-constexpr int TW_OUT = TW_BLK + 5 * TW_BLK_SIZE;  // 51808: Wt[32][4] + b[4]
-constexpr int TW_HEAD = TW_OUT + 132;             // 51940 floats per head
+constexpr int TW_FCC = 128;                       // [plane 3][hi,lo] fp16 operands, halfs at (k/8)*1280 + n*8 + k%8, n = blk*32+j
+constexpr int TW_FCC_SLICE = 2560;                //   one (plane, hi|lo) operand: N=160 x K=32 halfs = 10240 B (in floats)
+constexpr int TW_BC = TW_FCC + 6 * TW_FCC_SLICE;  // 15488: fc_c biases [5][32]
+constexpr int TW_BLK = TW_BC + 160;               // 15648: per block W0hi W0lo W1hi W1lo (2048 B each, halfs at (k/8)*256 + n*8 + k%8), b0[32], b1[32]
+constexpr int TW_BLK_SIZE = 4 * 512 + 64;         // 2112
+constexpr int TW_OUT = TW_BLK + 5 * TW_BLK_SIZE;  // 26208: Wt[32][4] + b[4]
+constexpr int TW_INV = TW_OUT + 132;              // 2^-s: undoes the head's weight pre-scale
+constexpr int TW_HEAD = TW_INV + 4;               // 26344 floats per head
 
 constexpr int TD_PTS = 128;
 constexpr int TD_KS_A = TD_PTS * 16 + 16;         // A k-chunk stride (bytes), +16 keeps the gather stores conflict free
-constexpr int TD_A_BYTES = 8 * TD_KS_A;           // one A operand (K=32): 16512 B
-constexpr int TD_W_BYTES = 2 * TW_FCC_SLICE * 4;  // staged weights: fc_c plane slice hi+lo = 40960 B (chain stage uses 16.9 KB of it)
+constexpr int TD_A_BYTES = 4 * TD_KS_A;           // one A operand (K=32 = 4 k-chunks of 8 halfs): 8256 B
+constexpr int TD_W_BYTES = 2 * TW_FCC_SLICE * 4;  // staged weights: fc_c plane slice hi+lo = 20480 B (chain stage uses 8.4 KB of it)
 constexpr int TD_OFF_ALO = TD_A_BYTES;
-constexpr int TD_OFF_W = 2 * TD_A_BYTES;          // 33024
-constexpr int TD_OFF_TINFO = TD_OFF_W + TD_W_BYTES;          // 73984
-constexpr int TD_OFF_WB0 = TD_OFF_TINFO + TD_PTS * 24 * 4;   // 86272: dedicated chain-weight buffer 0 (buffer 1 aliases sW)
-constexpr int TD_WB_BYTES = TW_BLK_SIZE * 4;                 // 16640
-constexpr int TD_OFF_BAR = TD_OFF_WB0 + TD_WB_BYTES;         // 102912
-constexpr int TD_SMEM_BYTES = TD_OFF_BAR + 48;               // 102960  (2 CTAs / SM)
+constexpr int TD_OFF_W = 2 * TD_A_BYTES;          // 16512
+constexpr int TD_OFF_TINFO = TD_OFF_W + TD_W_BYTES;          // 36992
+constexpr int TD_OFF_WB0 = TD_OFF_TINFO + TD_PTS * 24 * 4;   // 49280: dedicated chain-weight buffer 0 (buffer 1 aliases sW)
+constexpr int TD_WB_BYTES = TW_BLK_SIZE * 4;                 // 8448
+constexpr int TD_OFF_BAR = TD_OFF_WB0 + TD_WB_BYTES;         // 57728
+constexpr int TD_SMEM_BYTES = TD_OFF_BAR + 48;               // 57776  (TMEM keeps it at 2 CTAs / SM)
 constexpr int TD_TMEM_COLS = 256;
 constexpr uint32_t TD_KS_WC = 160 * 16;           // fc_c B operand k-chunk stride (N=160)
 constexpr uint32_t TD_KS_W = 32 * 16;             // 32x32 B operand k-chunk stride
 
-__device__ __forceinline__ float tf32_rn(float v) {  // round-to-nearest tf32 (top 19 bits)
-  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-}
-
-// 32x32 layer: the three 3xTF32 products go to three INDEPENDENT accumulators (d, d+32, d+64) so that only
-// 4 dependent MMAs (the k-steps) chain on each -- dependent MMAs into one TMEM tile cost ~100 cycles each.
-__device__ __forceinline__ void issue_k32_split3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                 uint32_t b_kstride, uint32_t idesc) {
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    const uint64_t ah = tc::make_desc(a_hi + ks * 2 * TD_KS_A, TD_KS_A, 128);
-    const uint64_t al = tc::make_desc(a_lo + ks * 2 * TD_KS_A, TD_KS_A, 128);
-    const uint64_t bh = tc::make_desc(b_hi + ks * 2 * b_kstride, b_kstride, 128);
-    const uint64_t bl = tc::make_desc(b_lo + ks * 2 * b_kstride, b_kstride, 128);
-    tc::mma_tf32(d_tmem, ah, bh, idesc, ks > 0 ? 1u : 0u);
-    tc::mma_tf32(d_tmem + 32, al, bh, idesc, ks > 0 ? 1u : 0u);
-    tc::mma_tf32(d_tmem + 64, ah, bl, idesc, ks > 0 ? 1u : 0u);
-  }
-}
-
-// one of the three 3xTF32 products of a 32x32 layer (kind 0: hi*hi, 1: lo*hi, 2: hi*lo) -> accumulator d_tmem + 32*kind.
-// Issued by three different warps concurrently: a single thread only issues one small MMA every ~85 cycles.
+// one of the three 3xFP16 products of a 32x32 layer (kind 0: hi*hi, 1: lo*hi, 2: hi*lo) -> accumulator d_tmem + 32*kind
+// (independent accumulators: dependent MMAs into one TMEM tile cost ~100 cycles each).  Issued by three different warps
+// concurrently: a single thread only issues one small MMA every ~85 cycles.  K = 32 = 2 MMAs of K = 16.
 __device__ __forceinline__ void issue_k32_one(int kind, uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                               uint32_t b_kstride, uint32_t idesc) {
   const uint32_t a = kind == 1 ? a_lo : a_hi, b = kind == 2 ? b_lo : b_hi;
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    tc::mma_tf32(d_tmem + 32 * kind, tc::make_desc(a + ks * 2 * TD_KS_A, TD_KS_A, 128), tc::make_desc(b + ks * 2 * b_kstride, b_kstride, 128),
-                 idesc, ks > 0 ? 1u : 0u);
+  for (int ks = 0; ks < 2; ++ks)
+    tc::mma_f16(d_tmem + 32 * kind, tc::make_desc(a + ks * 2 * TD_KS_A, TD_KS_A, 128), tc::make_desc(b + ks * 2 * b_kstride, b_kstride, 128),
+                idesc, ks > 0 ? 1u : 0u);
 }
 
 // sum of the three partial accumulators of a 32x32 layer for this thread's row
@@ -92,34 +79,43 @@ __device__ __forceinline__ void tmem_ld32_sum3(uint32_t taddr, float* v) {
   for (int j = 0; j < 32; ++j) v[j] += a[j];
 }
 
-// issue the K=32 contraction  D[128 x N] (+)= (Ahi+Alo)[128x32] . (Bhi+Blo)[N x 32]^T  as 4 k-steps x 3 MMAs
+// issue the K=32 contraction  D[128 x N] (+)= (Ahi+Alo)[128x32] . (Bhi+Blo)[N x 32]^T  as 2 k-steps x 3 MMAs
 __device__ __forceinline__ void issue_k32_x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                              uint32_t b_kstride, uint32_t idesc, bool accumulate_first) {
   uint32_t acc = accumulate_first ? 1u : 0u;
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
+  for (int ks = 0; ks < 2; ++ks) {
     const uint64_t ah = tc::make_desc(a_hi + ks * 2 * TD_KS_A, TD_KS_A, 128);
     const uint64_t al = tc::make_desc(a_lo + ks * 2 * TD_KS_A, TD_KS_A, 128);
     const uint64_t bh = tc::make_desc(b_hi + ks * 2 * b_kstride, b_kstride, 128);
     const uint64_t bl = tc::make_desc(b_lo + ks * 2 * b_kstride, b_kstride, 128);
-    tc::mma_tf32(d_tmem, ah, bh, idesc, acc);
-    tc::mma_tf32(d_tmem, al, bh, idesc, 1u);
-    tc::mma_tf32(d_tmem, ah, bl, idesc, 1u);
+    tc::mma_f16(d_tmem, ah, bh, idesc, acc);
+    tc::mma_f16(d_tmem, al, bh, idesc, 1u);
+    tc::mma_f16(d_tmem, ah, bl, idesc, 1u);
     acc = 1u;
   }
+}
+
+// unscaled fp16 split of an activation (clamped to fp16's range): hi = rn(v), lo = rn(v - hi)
+__device__ __forceinline__ void split_act2(float v0, float v1, uint32_t& h, uint32_t& l) {
+  v0 = fminf(fmaxf(v0, -H_MAX), H_MAX);
+  v1 = fminf(fmaxf(v1, -H_MAX), H_MAX);
+  const __half2 hh = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+  h = *reinterpret_cast<const uint32_t*>(&hh);
+  l = *reinterpret_cast<const uint32_t*>(&ll);
 }
 
 // thread t writes row t of the A operand (hi and lo) from 32 fp32 values
 __device__ __forceinline__ void store_a_row(uint8_t* a_hi, uint8_t* a_lo, int row, const float* v) {
 #pragma unroll
-  for (int kc = 0; kc < 8; ++kc) {
-    float4 h, l;
-    h.x = tf32_rn(v[4 * kc + 0]); l.x = v[4 * kc + 0] - h.x;
-    h.y = tf32_rn(v[4 * kc + 1]); l.y = v[4 * kc + 1] - h.y;
-    h.z = tf32_rn(v[4 * kc + 2]); l.z = v[4 * kc + 2] - h.z;
-    h.w = tf32_rn(v[4 * kc + 3]); l.w = v[4 * kc + 3] - h.w;
-    *reinterpret_cast<float4*>(a_hi + kc * TD_KS_A + row * 16) = h;
-    *reinterpret_cast<float4*>(a_lo + kc * TD_KS_A + row * 16) = l;
+  for (int kc = 0; kc < 4; ++kc) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_act2(v[8 * kc + 2 * i], v[8 * kc + 2 * i + 1], h[i], l[i]);
+    *reinterpret_cast<uint4*>(a_hi + kc * TD_KS_A + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_lo + kc * TD_KS_A + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -213,8 +209,8 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
   const uint32_t a_hi = tc::smem_u32(sAhi), a_lo = tc::smem_u32(sAlo), w_s = tc::smem_u32(sW);
-  constexpr uint32_t IDESC_160 = tc::make_idesc_tf32(128, 160);
-  constexpr uint32_t IDESC_32 = tc::make_idesc_tf32(128, 32);
+  constexpr uint32_t IDESC_160 = tc::make_idesc_f16(128, 160);
+  constexpr uint32_t IDESC_32 = tc::make_idesc_f16(128, 32);
   uint32_t phase = 0, phase3 = 0;
 
   // Weight staging is asynchronous (cp.async.bulk + mbarrier, issued by one elected lane of warp 0):
@@ -237,6 +233,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   for (int head = 0; head < 4; ++head) {
     if (!(heads & (1u << head))) continue;
     const float* W = tw + (size_t)head * TW_HEAD;
+    const float winv = __ldg(W + TW_INV);   // 2^-s of this head's weight pre-scale
     int next_head = -1;
     for (int hh = head + 1; hh < 4; ++hh)
       if (heads & (1u << hh)) { next_head = hh; break; }
@@ -248,14 +245,14 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       if (!(pl == 0 && plane0_prefetched)) issue_bulk(sW, W + TW_FCC + pl * 2 * TW_FCC_SLICE, TD_W_BYTES, pbar);
       if (pl == 0) issue_bulk(sWB0, W + TW_BLK, TD_WB_BYTES, &wbar[0]);   // chain block 0 -> dedicated buffer
       // A operand from the register-resident features: element (row = warp*32+q, k = lane)
-      uint8_t* ah = sAhi + (lane >> 2) * TD_KS_A + (lane & 3) * 4 + (warp * 32) * 16;
-      uint8_t* al = sAlo + (lane >> 2) * TD_KS_A + (lane & 3) * 4 + (warp * 32) * 16;
+      uint8_t* ah = sAhi + (lane >> 3) * TD_KS_A + (lane & 7) * 2 + (warp * 32) * 16;
+      uint8_t* al = sAlo + (lane >> 3) * TD_KS_A + (lane & 7) * 2 + (warp * 32) * 16;
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
-        const float v = F[pl][q];
-        const float h = tf32_rn(v);
-        *reinterpret_cast<float*>(ah + q * 16) = h;
-        *reinterpret_cast<float*>(al + q * 16) = v - h;
+        const float v = fminf(fmaxf(F[pl][q], -H_MAX), H_MAX);
+        const __half h = __float2half_rn(v);
+        *reinterpret_cast<__half*>(ah + q * 16) = h;
+        *reinterpret_cast<__half*>(al + q * 16) = __float2half_rn(v - __half2float(h));
       }
       tc::fence_smem_to_async();
       tc::fence_before_sync();
@@ -299,7 +296,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       tc::tmem_ld32(tmem_row + blk * 32, v);           // fc_c[blk] output for this point
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        h[j] += v[j] + __ldg(W + TW_BC + blk * 32 + j);  // net = net + fc_c[blk](c)
+        h[j] += fmaf(v[j], winv, __ldg(W + TW_BC + blk * 32 + j));  // net = net + fc_c[blk](c)
         v[j] = fmaxf(h[j], 0.f);
       }
       store_a_row(sAhi, sAlo, tid, v);
@@ -311,7 +308,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       if (warp < 3) {
         tc::fence_after_sync();
         if (tc::elect_one()) {
-          issue_k32_one(warp, tmem + 160, a_hi, a_lo, w_b, w_b + 4096, TD_KS_W, IDESC_32);   // fc_0
+          issue_k32_one(warp, tmem + 160, a_hi, a_lo, w_b, w_b + 2048, TD_KS_W, IDESC_32);   // fc_0
           tc::mma_commit(bar3);
         }
         __syncwarp();
@@ -319,10 +316,10 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       tc::mbar_wait(bar3, phase3);
       phase3 ^= 1u;
       tc::fence_after_sync();
-      const float* bs = reinterpret_cast<const float*>(wbuf) + 4096;   // b0[32], b1[32]
+      const float* bs = reinterpret_cast<const float*>(wbuf) + 2048;   // b0[32], b1[32]
       tmem_ld32_sum3(tmem_row + 160, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bs[j], 0.f);
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(v[j], winv, bs[j]), 0.f);
       store_a_row(sAhi, sAlo, tid, v);
       tc::fence_smem_to_async();
       tc::fence_before_sync();
@@ -330,7 +327,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       if (warp < 3) {
         tc::fence_after_sync();
         if (tc::elect_one()) {
-          issue_k32_one(warp, tmem + 160, a_hi, a_lo, w_b + 8192, w_b + 12288, TD_KS_W, IDESC_32);   // fc_1
+          issue_k32_one(warp, tmem + 160, a_hi, a_lo, w_b + 4096, w_b + 6144, TD_KS_W, IDESC_32);   // fc_1
           tc::mma_commit(bar3);
         }
         __syncwarp();
@@ -340,7 +337,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
       tc::fence_after_sync();
       tmem_ld32_sum3(tmem_row + 160, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) h[j] += v[j] + bs[32 + j];     // x + fc_1(relu(fc_0(relu(x))))
+      for (int j = 0; j < 32; ++j) h[j] += fmaf(v[j], winv, bs[32 + j]);     // x + fc_1(relu(fc_0(relu(x))))
       tc::fence_before_sync();
       __syncthreads();   // everyone has read b0/b1 and T before this weight buffer / T are overwritten
       stamp();   // per head: 5 block rounds

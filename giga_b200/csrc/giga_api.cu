@@ -7,13 +7,13 @@
 #include <cstdint>
 #include <cmath>
 #include <cstring>
+#include <cuda_fp16.h>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
 #include "conv_in.cuh"
-#include "conv_in_tc.cuh"
 #include "decoder.cuh"
 #include "decoder_tc.cuh"
 #include "planner.cuh"
@@ -64,7 +64,7 @@ using T_u1up = TallCfg<20, 64, 0, 32, 32, 2, 1, false>;
 using T_u1c1 = TallCfg<40, 32, 32, 32, 32, 2, 0, false>;
 using T_u1c2 = TallCfg<40, 32, 0, 32, 32, 2, 0, true>;
 
-// persistent variants (one CTA per SM): <cfg, stages, resident weights>
+// persistent kernels (one CTA per SM): <cfg, stages, resident weights, N-concat>
 using P_c40 = PersistCfg<T_c40, 4, true, true>;
 using P_d1c1 = PersistCfg<T_d1c1, 4, false>;
 using P_c20 = PersistCfg<T_c20, 4, false>;
@@ -87,11 +87,9 @@ struct EncLayout {
   long bias[10];
   long up_w[2], up_b[2];
   long fin_w, fin_b;
-  long tc_conv[10];  // tensor-core operand-layout weights (hi/lo tf32 splits) per conv layer
-  long tc_up[2];     // transpose convs, [ab][chunk][hi|lo][kc][co][4]
-  long tc_fin;       // conv_final as a 32x32 B operand [hi,lo][kc 8][n 32][4]
-  long cin_b;        // conv_in bias (device copy for the tensor-core conv_in)
-  long tc_cin;       // conv_in as 9 (dx,dy) taps x [kc 2][hi|lo][n 32][4] with k = dz (conv_in_tc.cuh)
+  long tc_conv[10];  // tensor-core operand-layout weights (hi/lo fp16 splits) per conv layer
+  long tc_up[2];     // transpose convs, [ab][chunk][kc][hi|lo][co][8 halfs]
+  long tc_fin;       // conv_final as a 32x32 B operand [hi,lo][kc 4][n 32][8 halfs]
   long total;
 };
 const int kConvCin[10] = {32, 32, 32, 64, 64, 128, 128, 64, 64, 32};
@@ -109,11 +107,10 @@ EncLayout make_enc_layout() {
   for (int i = 0; i < 2; ++i) { L.up_w[i] = o; o += (long)kUpCin[i] * kUpCout[i] * 4; L.up_b[i] = o; o += kUpCout[i]; }
   L.fin_w = o; o += 32 * 32;
   L.fin_b = o; o += 32;
-  for (int i = 0; i < 10; ++i) { L.tc_conv[i] = o; o += (long)kConvCin[i] * kConvCout[i] * 9 * 2; }
-  for (int i = 0; i < 2; ++i) { L.tc_up[i] = o; o += (long)kUpCin[i] * kUpCout[i] * 4 * 2; }
-  L.tc_fin = o; o += 2 * 1024;
-  L.tc_cin = o; o += CT_WEIGHT_FLOATS;
-  L.cin_b = o; o += 32;
+  // hi + lo fp16 = one 4-byte word per weight
+  for (int i = 0; i < 10; ++i) { L.tc_conv[i] = o; o += (long)kConvCin[i] * kConvCout[i] * 9; }
+  for (int i = 0; i < 2; ++i) { L.tc_up[i] = o; o += (long)kUpCin[i] * kUpCout[i] * 4; }
+  L.tc_fin = o; o += 1024;
   L.total = o;
   return L;
 }
@@ -140,9 +137,7 @@ struct giga_ctx {
   float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo tf32 splits)
   int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int encoder_impl = 1;      // U-Net convs: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
-  int conv_in_impl = 0;      // conv_in: 0 = fp32 FMA pipe (default), 1 = tcgen05 variant (experimental, not faster: DESIGN.md 5)
   int last_impl = 0;
-  bool last_cin_tc = false;
   int num_sms = 148;
   const char* timeline_layer = nullptr;   // debug (env GIGA_TIMELINE=<kernel name>): in-kernel phase timestamps
   unsigned long long* d_timeline = nullptr;
@@ -152,7 +147,6 @@ struct giga_ctx {
   int last_B = 0;
   float* d_pre = nullptr;      // [3][B][32][1600]
   float* d_xzpart = nullptr;   // [B][CI_NT][40][32][40]
-  float* d_yzpart = nullptr;   // [B][CT_NG][40][32][40]  (tensor-core conv_in)
   float* d_planes = nullptr;   // [3][B][40][40][32] plane features of giga_forward calls that pass planes = NULL
   int planes_cap = 0;
   float* d_act[kNumActs] = {};
@@ -220,7 +214,6 @@ struct LaunchScope {
 int ensure_attrs(giga_ctx* ctx) {
   if (ctx->attrs_set) return GIGA_OK;
   CU_TRY(cudaFuncSetAttribute(conv_in_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CI_SMEM_BYTES));
-  CU_TRY(cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(sample_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
@@ -228,10 +221,6 @@ int ensure_attrs(giga_ctx* ctx) {
   SET_CONV(K_d0c1); SET_CONV(K_d0c2); SET_CONV(K_d1c1); SET_CONV(K_d1c2); SET_CONV(K_d2c1);
   SET_CONV(K_d2c2); SET_CONV(K_u0c1); SET_CONV(K_u0c2); SET_CONV(K_u1c1); SET_CONV(K_u1c2);
 #undef SET_CONV
-#define SET_TC(K) CU_TRY(cudaFuncSetAttribute(conv_tall_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES))
-  SET_TC(T_c40); SET_TC(T_d1c1); SET_TC(T_c20); SET_TC(T_d2c1); SET_TC(T_d2c2); SET_TC(T_u0up); SET_TC(T_u0c1); SET_TC(T_u1up);
-  SET_TC(T_u1c1); SET_TC(T_u1c2);
-#undef SET_TC
 #define SET_P(P) CU_TRY(cudaFuncSetAttribute(conv_tall_persistent_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES))
   SET_P(P_c40); SET_P(P_d1c1); SET_P(P_c20); SET_P(P_d2c1); SET_P(P_d2c2); SET_P(P_u0up); SET_P(P_u0c1); SET_P(P_u1up); SET_P(P_u1c1);
   SET_P(P_u1c2);
@@ -253,9 +242,6 @@ int ensure_workspace(giga_ctx* ctx, int B) {
   ctx->cap_B = 0;
   CU_TRY(cudaMalloc(&ctx->d_pre, sizeof(float) * 3 * (size_t)B * C * G2));
   CU_TRY(cudaMalloc(&ctx->d_xzpart, sizeof(float) * (size_t)B * CI_NT * G * C * G));
-  if (ctx->d_yzpart) cudaFree(ctx->d_yzpart);
-  ctx->d_yzpart = nullptr;
-  CU_TRY(cudaMalloc(&ctx->d_yzpart, sizeof(float) * (size_t)B * CT_NG * G * C * G));
   for (int i = 0; i < kNumActs; ++i)
     CU_TRY(cudaMalloc(&ctx->d_act[i], sizeof(float) * 3 * (size_t)B * kActs[i].ch * kActs[i].hw * kActs[i].hw));
   for (int i = 0; i <= kNumActs; ++i) {   // zero-initialised once: padding positions are never written
@@ -288,24 +274,6 @@ void launch_conv(giga_ctx* ctx, const char* name, int n_img, const float* s0, co
 
 struct TallBuf { float* p = nullptr; long ps = 0; };
 
-template <class K>
-void launch_tall(giga_ctx* ctx, const char* name, int n_img, const TallBuf& s0, const TallBuf& s1, const float* w,
-                 const float* bias, const TallBuf& out, float* fin_out, cudaStream_t st) {
-  dim3 grid(K::num_ctas(n_img), K::NNT);
-  LaunchScope ls(ctx, name, st);
-  unsigned long long* tl = nullptr;
-  if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, name)) {   // debug: per-CTA phase timestamps of one layer
-    const size_t n = (size_t)grid.x * grid.y * 32;
-    if (ctx->d_timeline) cudaFree(ctx->d_timeline);
-    cudaMalloc(&ctx->d_timeline, n * 8);
-    cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
-    ctx->timeline_n = (long)n;
-    tl = ctx->d_timeline;
-  }
-  conv_tall_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(s0.p, s0.ps, s1.p, s1.ps, w, bias, out.p, out.ps,
-                                                                ctx->d_enc + ctx->el.tc_fin, ctx->d_enc + ctx->el.fin_b, fin_out, n_img, tl);
-}
-
 template <class P>
 void launch_persist(giga_ctx* ctx, const char* name, int n_img, const TallBuf& s0, const TallBuf& s1, const float* w,
                     const float* bias, const TallBuf& out, float* fin_out, cudaStream_t st) {
@@ -335,26 +303,34 @@ void launch_convT(giga_ctx* ctx, const char* name, int n_img, const float* src, 
                                                                ctx->d_enc + ctx->el.up_b[up], out);
 }
 
-float tf32_rn_host(float v);
+// fp16 hi / 2^11-scaled lo split of a weight (same split as unet_tall.cuh::split8)
+inline void split_half_host(float v, uint16_t& hi, uint16_t& lo, float lo_scale) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn((v - __half2float(h)) * lo_scale);
+  memcpy(&hi, &h, 2);
+  memcpy(&lo, &l, 2);
+}
 
-// [ntile][chunk][tap][kc 2][hi,lo][n NTILE][4]; MODE 0 from the reference's Conv2d [co][ci][3][3],
+// [ntile][chunk 16 ch][tap][kc 2][hi,lo][n NTILE][8 halfs]; MODE 0 from the reference's Conv2d [co][ci][3][3],
 // MODE 1 from ConvTranspose2d [ci][co][2][2] with ntile = a*2+b
 template <class K>
-void pack_conv_tc(const float* w, float* dst) {
+void pack_conv_tc(const float* w, float* dst_words) {
+  uint16_t* dst = reinterpret_cast<uint16_t*>(dst_words);
   for (int nt = 0; nt < K::NNT; ++nt)
     for (int c = 0; c < K::NC; ++c)
       for (int tap = 0; tap < K::NTAPS; ++tap)
         for (int kc = 0; kc < 2; ++kc)
           for (int n = 0; n < K::NTILE; ++n)
-            for (int j = 0; j < 4; ++j) {
-              const int ci = c * 8 + kc * 4 + j;
+            for (int j = 0; j < 8; ++j) {
+              const int ci = c * 16 + kc * 8 + j;
               float v;
               if (K::MODE == 0) v = w[((long)(nt * K::NTILE + n) * K::CIN + ci) * 9 + tap];
               else v = w[((long)ci * K::COUT + n) * 4 + nt];
-              const float hi = tf32_rn_host(v);
-              const long base = ((((long)nt * K::NC + c) * K::NTAPS + tap) * 2) * 2 * K::NTILE * 4;
-              dst[base + ((kc * 2 + 0) * K::NTILE + n) * 4 + j] = hi;     // [kc][hi|lo][n][4]
-              dst[base + ((kc * 2 + 1) * K::NTILE + n) * 4 + j] = v - hi;
+              uint16_t hi, lo;
+              split_half_host(v, hi, lo, LO_SCALE);
+              const long base = ((((long)nt * K::NC + c) * K::NTAPS + tap) * 2) * 2 * K::NTILE * 8;
+              dst[base + ((kc * 2 + 0) * K::NTILE + n) * 8 + j] = hi;     // [kc][hi|lo][n][8]
+              dst[base + ((kc * 2 + 1) * K::NTILE + n) * 8 + j] = lo;
             }
 }
 
@@ -405,7 +381,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_yzpart, ctx->d_planes};
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_planes};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : ctx->slot) {
@@ -462,19 +438,6 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       (&ctx->conv_in.b[0].x)[c] = b[c];
     }
     std::vector<float> blob(ctx->el.total, 0.f);
-    for (int c = 0; c < 32; ++c)
-      for (int tap = 0; tap < 9; ++tap)       // tap = dx*3 + dy ; k = dz
-        for (int dz = 0; dz < 3; ++dz) {
-          const float v = w[c * 27 + tap * 3 + dz], hi = tf32_rn_host(v);
-          blob[ctx->el.tc_cin + tap * 512 + (0 * 2 + 0) * 128 + c * 4 + dz] = hi;
-          blob[ctx->el.tc_cin + tap * 512 + (0 * 2 + 1) * 128 + c * 4 + dz] = v - hi;
-        }
-    for (int c = 0; c < 32; ++c) {   // bias rides on the centre tap (dx=1,dy=1): the A operand's 4th k is the constant 1
-      const float bv = b[c], hi = tf32_rn_host(bv);
-      blob[ctx->el.tc_cin + 4 * 512 + (0 * 2 + 0) * 128 + c * 4 + 3] = hi;
-      blob[ctx->el.tc_cin + 4 * 512 + (0 * 2 + 1) * 128 + c * 4 + 3] = bv - hi;
-    }
-    memcpy(blob.data() + ctx->el.cin_b, ctx->conv_in.b, sizeof(float) * 32);
     for (int i = 0; i < 10; ++i) {
       const int ci = kConvCin[i], co = kConvCout[i];
       std::string base = std::string("encoder.unet.") + kConvName[i];
@@ -498,12 +461,16 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
     for (int o = 0; o < 32; ++o)
       for (int c = 0; c < 32; ++c) blob[ctx->el.fin_w + c * 32 + o] = w[o * 32 + c];  // [ci][co]
     memcpy(blob.data() + ctx->el.fin_b, b, sizeof(float) * 32);
-    for (int k = 0; k < 32; ++k)
-      for (int n = 0; n < 32; ++n) {
-        const float v = w[n * 32 + k], hi = tf32_rn_host(v);
-        blob[ctx->el.tc_fin + ((k / 4) * 32 + n) * 4 + (k % 4)] = hi;
-        blob[ctx->el.tc_fin + 1024 + ((k / 4) * 32 + n) * 4 + (k % 4)] = v - hi;
-      }
+    {
+      uint16_t* fw = reinterpret_cast<uint16_t*>(blob.data() + ctx->el.tc_fin);   // [hi|lo][kc 4][n 32][8 halfs]
+      for (int k = 0; k < 32; ++k)
+        for (int n = 0; n < 32; ++n) {
+          uint16_t hi, lo;
+          split_half_host(w[n * 32 + k], hi, lo, LO_SCALE);
+          fw[((k / 8) * 32 + n) * 8 + (k % 8)] = hi;
+          fw[1024 + ((k / 8) * 32 + n) * 8 + (k % 8)] = lo;
+        }
+    }
     {
       const float* cw[10];
       for (int i = 0; i < 10; ++i) get(ctx, std::string("encoder.unet.") + kConvName[i] + ".weight", (long)kConvCout[i] * kConvCin[i] * 9, &cw[i]);
@@ -568,9 +535,30 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       for (int k = 0; k < 32; ++k) H[DW_OUT + k * 4 + m] = w[m * 32 + k];
       H[DW_OUT + 128 + m] = b[m];
     }
-    // tensor-core blob: the same parameters pre-split into tf32 hi/lo pairs in UMMA operand layout
+    // tensor-core blob: the same parameters, pre-scaled by 2^s and split into fp16 hi/lo pairs in UMMA operand layout
     float* T = tb.data() + (size_t)h * TW_HEAD;
     memcpy(T + TW_FCP, H + DW_FCP, sizeof(float) * 128);
+    float wmax = 0.f;
+    for (int i = 0; i < 5; ++i) {
+      const std::string si = std::to_string(i);
+      need("fc_c." + si + ".weight", 32 * 96, &w);
+      for (int e = 0; e < 32 * 96; ++e) wmax = fmaxf(wmax, fabsf(w[e]));
+      for (int f = 0; f < 2; ++f) {
+        need("blocks." + si + ".fc_" + std::to_string(f) + ".weight", 32 * 32, &w);
+        for (int e = 0; e < 32 * 32; ++e) wmax = fmaxf(wmax, fabsf(w[e]));
+      }
+    }
+    int sexp = 0;   // max |w| * 2^s in [512, 1024): hi/lo halves of every non-negligible weight are normal fp16 numbers
+    if (wmax > 0.f && std::isfinite(wmax)) {
+      int e;
+      frexpf(wmax, &e);           // wmax = m * 2^e, m in [0.5, 1)
+      sexp = 10 - e;
+      if (sexp < -14) sexp = -14;
+      if (sexp > 24) sexp = 24;
+    }
+    const float wscale = ldexpf(1.f, sexp);
+    T[TW_INV] = ldexpf(1.f, -sexp);
+    uint16_t* T16 = reinterpret_cast<uint16_t*>(T);
     for (int i = 0; i < 5; ++i) {
       const std::string si = std::to_string(i);
       need("fc_c." + si + ".weight", 32 * 96, &w);
@@ -578,25 +566,28 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       for (int j = 0; j < 32; ++j) {
         for (int k96 = 0; k96 < 96; ++k96) {
           const int pl = k96 / 32, k = k96 % 32, n = i * 32 + j;
-          const float v = w[j * 96 + k96], hi = tf32_rn_host(v);
-          float* S = T + TW_FCC + pl * 2 * TW_FCC_SLICE;
-          S[(k / 4) * 640 + n * 4 + (k % 4)] = hi;
-          S[TW_FCC_SLICE + (k / 4) * 640 + n * 4 + (k % 4)] = v - hi;
+          uint16_t hi, lo;
+          split_half_host(w[j * 96 + k96] * wscale, hi, lo, 1.f);
+          uint16_t* S = T16 + 2 * (TW_FCC + pl * 2 * TW_FCC_SLICE);      // halfs: [k/8][n 160][8]
+          S[(k / 8) * 1280 + n * 8 + (k % 8)] = hi;
+          S[2 * TW_FCC_SLICE + (k / 8) * 1280 + n * 8 + (k % 8)] = lo;
         }
         T[TW_BC + i * 32 + j] = b[j];
       }
       float* Bk = T + TW_BLK + i * TW_BLK_SIZE;
+      uint16_t* Bk16 = reinterpret_cast<uint16_t*>(Bk);                  // W0hi W0lo W1hi W1lo, 1024 halfs each: [k/8][n 32][8]
       for (int f = 0; f < 2; ++f) {
         const std::string fn = "blocks." + si + ".fc_" + std::to_string(f);
         need(fn + ".weight", 32 * 32, &w);
         need(fn + ".bias", 32, &b);
         for (int j = 0; j < 32; ++j) {
           for (int k = 0; k < 32; ++k) {
-            const float v = w[j * 32 + k], hi = tf32_rn_host(v);
-            Bk[f * 2048 + (k / 4) * 128 + j * 4 + (k % 4)] = hi;
-            Bk[f * 2048 + 1024 + (k / 4) * 128 + j * 4 + (k % 4)] = v - hi;
+            uint16_t hi, lo;
+            split_half_host(w[j * 32 + k] * wscale, hi, lo, 1.f);
+            Bk16[f * 2048 + (k / 8) * 256 + j * 8 + (k % 8)] = hi;
+            Bk16[f * 2048 + 1024 + (k / 8) * 256 + j * 8 + (k % 8)] = lo;
           }
-          Bk[4096 + f * 32 + j] = b[j];
+          Bk[2048 + f * 32 + j] = b[j];
         }
       }
     }
@@ -623,42 +614,20 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
   if (int r = ensure_workspace(ctx, B)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_img = 3 * B;
-  const bool cin_tc = ctx->encoder_impl >= 1 && ctx->conv_in_impl == 1;
-  if (cin_tc) {   // tensor-core conv_in writes the TALL pre-split planes directly
-    {
-      unsigned long long* tl = nullptr;
-      if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, "conv_in_tc")) {
-        const size_t n = (size_t)CT_NG * B * 32;
-        if (ctx->d_timeline) cudaFree(ctx->d_timeline);
-        cudaMalloc(&ctx->d_timeline, n * 8);
-        cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
-        ctx->timeline_n = (long)n;
-        tl = ctx->d_timeline;
-      }
-      LaunchScope ls(ctx, "conv_in_tc", st);
-      conv_in_tc_kernel<<<dim3(CT_NG, B), 256, CT_SMEM_BYTES, st>>>(tsdf, ctx->d_enc + ctx->el.tc_cin, ctx->d_enc + ctx->el.cin_b,
-                                                                     ctx->d_tall[0], ctx->tall_ps[0], ctx->d_yzpart, B, tl);
-    }
-    {
-      LaunchScope ls(ctx, "yz_finish", st);
-      yz_finish_tall_kernel<<<dim3(G, B), 320, 0, st>>>(ctx->d_yzpart, ctx->d_tall[0], ctx->tall_ps[0], B);
-    }
-  } else {
-    {
-      LaunchScope ls(ctx, "conv_in_planes", st);
-      conv_in_planes_kernel<<<dim3(CI_NT, B), CI_THREADS, CI_SMEM_BYTES, st>>>(tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
-    }
-    {
-      LaunchScope ls(ctx, "xz_finish", st);
-      xz_finish_kernel<<<dim3(C, B), 256, 0, st>>>(ctx->d_xzpart, ctx->d_pre, B);
-    }
+  {
+    LaunchScope ls(ctx, "conv_in_planes", st);
+    conv_in_planes_kernel<<<dim3(CI_NT, B), CI_THREADS, CI_SMEM_BYTES, st>>>(tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+  }
+  {
+    LaunchScope ls(ctx, "xz_finish", st);
+    xz_finish_kernel<<<dim3(C, B), 256, 0, st>>>(ctx->d_xzpart, ctx->d_pre, B);
   }
   float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"),
         *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),
         *u0 = act(ctx, "u0"), *u0c1 = act(ctx, "u0c1"), *u0c2 = act(ctx, "u0c2"), *u1 = act(ctx, "u1"),
         *u1c1 = act(ctx, "u1c1"), *u1c2 = act(ctx, "u1c2");
   if (ctx->encoder_impl >= 1) {
-    // tensor-core U-Net on TALL pre-split activations (unet_tall.cuh); 1 = persistent kernels, 2 = one CTA per tile
+    // tensor-core U-Net on TALL pre-split activations (unet_tall.cuh), persistent kernels
     auto tb = [&](const char* nm) {
       TallBuf t;
       if (!strcmp(nm, "pre")) { t.p = ctx->d_tall[0]; t.ps = ctx->tall_ps[0]; return t; }
@@ -669,22 +638,22 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
     const TallBuf none;
     const float* E = ctx->d_enc;
     const EncLayout& L = ctx->el;
-    if (!cin_tc) {
+    {
       LaunchScope ls(ctx, "nchw_to_tall:pre", st);
-      nchw_to_tall_kernel<40, 8><<<ceil_div(n_img * 8 * G2, 256), 256, 0, st>>>(ctx->d_pre, tb("pre").p, tb("pre").ps, n_img);
+      nchw_to_tall_kernel<40, 4><<<ceil_div(n_img * 4 * G2, 256), 256, 0, st>>>(ctx->d_pre, tb("pre").p, tb("pre").ps, n_img);
     }
-    if (ctx->encoder_impl == 1) {
+    {
       launch_persist<P_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st);
       launch_persist<P_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st);
       {
         LaunchScope ls(ctx, "maxpool:p0", st);
-        pool_tall_kernel<20, 8><<<ceil_div(n_img * 8 * 400, 256), 256, 0, st>>>(tb("d0c2").p, tb("d0c2").ps, tb("p0").p, tb("p0").ps, n_img);
+        pool_tall_kernel<20, 4><<<ceil_div(n_img * 4 * 400, 256), 256, 0, st>>>(tb("d0c2").p, tb("d0c2").ps, tb("p0").p, tb("p0").ps, n_img);
       }
       launch_persist<P_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st);
       launch_persist<P_c20>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st);
       {
         LaunchScope ls(ctx, "maxpool:p1", st);
-        pool_tall_kernel<10, 16><<<ceil_div(n_img * 16 * 100, 256), 256, 0, st>>>(tb("d1c2").p, tb("d1c2").ps, tb("p1").p, tb("p1").ps, n_img);
+        pool_tall_kernel<10, 8><<<ceil_div(n_img * 8 * 100, 256), 256, 0, st>>>(tb("d1c2").p, tb("d1c2").ps, tb("p1").p, tb("p1").ps, n_img);
       }
       launch_persist<P_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st);
       launch_persist<P_d2c2>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st);
@@ -694,36 +663,13 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
       launch_persist<P_u1up>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st);
       launch_persist<P_u1c1>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st);
       launch_persist<P_u1c2>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st);
-    } else {
-      launch_tall<T_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st);
-      launch_tall<T_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st);
-      {
-        LaunchScope ls(ctx, "maxpool:p0", st);
-        pool_tall_kernel<20, 8><<<ceil_div(n_img * 8 * 400, 256), 256, 0, st>>>(tb("d0c2").p, tb("d0c2").ps, tb("p0").p, tb("p0").ps, n_img);
-      }
-      launch_tall<T_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st);
-      launch_tall<T_c20>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st);
-      {
-        LaunchScope ls(ctx, "maxpool:p1", st);
-        pool_tall_kernel<10, 16><<<ceil_div(n_img * 16 * 100, 256), 256, 0, st>>>(tb("d1c2").p, tb("d1c2").ps, tb("p1").p, tb("p1").ps, n_img);
-      }
-      launch_tall<T_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st);
-      launch_tall<T_d2c2>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st);
-      launch_tall<T_u0up>(ctx, "convT:u0", n_img, tb("d2c2"), none, E + L.tc_up[0], E + L.up_b[0], tb("u0"), nullptr, st);
-      launch_tall<T_u0c1>(ctx, "conv3x3:u0c1", n_img, tb("u0"), tb("d1c2"), E + L.tc_conv[6], E + L.bias[6], tb("u0c1"), nullptr, st);
-      launch_tall<T_c20>(ctx, "conv3x3:u0c2", n_img, tb("u0c1"), none, E + L.tc_conv[7], E + L.bias[7], tb("u0c2"), nullptr, st);
-      launch_tall<T_u1up>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st);
-      launch_tall<T_u1c1>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st);
-      launch_tall<T_u1c2>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st);
     }
     ctx->last_B = B;
     ctx->last_impl = ctx->encoder_impl;
-    ctx->last_cin_tc = cin_tc;
     CU_TRY(cudaGetLastError());
     return GIGA_OK;
   }
   ctx->last_impl = 0;
-  ctx->last_cin_tc = false;
   launch_conv<K_d0c1>(ctx, "conv3x3:d0c1", n_img, ctx->d_pre, nullptr, 0, d0c1, nullptr, st);
   launch_conv<K_d0c2>(ctx, "conv3x3:d0c2", n_img, d0c1, nullptr, 1, d0c2, p0, st);
   launch_conv<K_d1c1>(ctx, "conv3x3:d1c1", n_img, p0, nullptr, 2, d1c1, nullptr, st);
@@ -1158,13 +1104,8 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
     ctx->decoder_impl = value;
     return GIGA_OK;
   }
-  if (!strcmp(key, "conv_in_impl")) {
-    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "conv_in_impl must be 0 (fp32 FMA) or 1 (tcgen05, experimental)");
-    ctx->conv_in_impl = value;
-    return GIGA_OK;
-  }
   if (!strcmp(key, "encoder_impl")) {
-    if (value < 0 || value > 2) return fail(GIGA_EINVAL, "encoder_impl must be 0 (fp32 FMA), 1 (tcgen05 persistent) or 2 (tcgen05 per-tile)");
+    if (value < 0 || value > 1) return fail(GIGA_EINVAL, "encoder_impl must be 0 (fp32 FMA pipe) or 1 (tcgen05 3xFP16, persistent)");
     ctx->encoder_impl = value;
     return GIGA_OK;
   }
@@ -1228,10 +1169,6 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
       }
   }
   if (!src) return fail(GIGA_EINVAL, std::string("giga_debug_copy: unknown buffer '") + name + "'");
-  if (ctx->last_cin_tc && !strcmp(name, "pre")) {   // tensor-core conv_in: planes exist only in the TALL layout
-    const int n_img = 3 * ctx->last_B;
-    tall_to_nchw_kernel<40, 8><<<ceil_div(n_img * 8 * G2, 256), 256, 0, (cudaStream_t)stream>>>(ctx->d_tall[0], ctx->d_pre, ctx->tall_ps[0], n_img);
-  }
   if (ctx->last_impl >= 1 && strcmp(name, "pre")) {
     if (!strcmp(name, "u1c2"))
       return fail(GIGA_ESTATE, "giga_debug_copy: 'u1c2' is fused away by the tensor-core encoder (encoder_impl=1)");
@@ -1239,17 +1176,17 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
     int idx = -1;
     for (int i = 0; i < kNumActs; ++i)
       if (!strcmp(kActs[i].name, name)) idx = i;
-    const int n_img = 3 * ctx->last_B, hw = kActs[idx].hw, c4 = kActs[idx].ch / 4;
+    const int n_img = 3 * ctx->last_B, hw = kActs[idx].hw, c8 = kActs[idx].ch / 8;
     const float* tsrc = ctx->d_tall[1 + idx];
     const long ps = ctx->tall_ps[1 + idx];
     float* scratch = ctx->d_act[idx];
     cudaStream_t st = (cudaStream_t)stream;
-    const int blocks = ceil_div(n_img * c4 * hw * hw, 256);
-    if (hw == 40 && c4 == 8) tall_to_nchw_kernel<40, 8><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
-    else if (hw == 20 && c4 == 8) tall_to_nchw_kernel<20, 8><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
-    else if (hw == 20 && c4 == 16) tall_to_nchw_kernel<20, 16><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
-    else if (hw == 10 && c4 == 16) tall_to_nchw_kernel<10, 16><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
-    else if (hw == 10 && c4 == 32) tall_to_nchw_kernel<10, 32><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    const int blocks = ceil_div(n_img * c8 * hw * hw, 256);
+    if (hw == 40 && c8 == 4) tall_to_nchw_kernel<40, 4><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    else if (hw == 20 && c8 == 4) tall_to_nchw_kernel<20, 4><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    else if (hw == 20 && c8 == 8) tall_to_nchw_kernel<20, 8><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    else if (hw == 10 && c8 == 8) tall_to_nchw_kernel<10, 8><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
+    else if (hw == 10 && c8 == 16) tall_to_nchw_kernel<10, 16><<<blocks, 256, 0, st>>>(tsrc, scratch, ps, n_img);
     else return fail(GIGA_EINVAL, "giga_debug_copy: unexpected activation shape");
   }
   if (numel > capacity) return fail(GIGA_EINVAL, "giga_debug_copy: destination too small");

@@ -3,12 +3,12 @@
 // below were validated on a B200 with tools/tc_probe.cu (profiles/r01_tc_probe.txt).
 //
 // Operand layout used everywhere (canonical K-major, SWIZZLE_NONE): an operand with R rows (M or N)
-// and K fp32 columns is stored as 16-byte "k-chunks" of 4 consecutive k for one row:
-//     byte address(r, k) = (k/4) * KSTRIDE + r*16 + (k%4)*4
+// and K columns is stored as 16-byte "k-chunks" of E consecutive k for one row (E = 4 for tf32/fp32 words, 8 for fp16):
+//     byte address(r, k) = (k/E) * KSTRIDE + r*16 + (k%E)*(16/E)
 // so an 8-row x 16-byte core matrix is 128 contiguous bytes, SBO (next 8 rows) = 128 B and
 // LBO (next k-chunk) = KSTRIDE (any multiple of 16 B; R*16 + 16 keeps thread-issued stores
-// bank-conflict free).  One MMA consumes K = 8 (two k-chunks); advancing K by 8 advances the
-// start address by 2*KSTRIDE.  Advancing the start by 16*s bytes shifts the operand by s rows --
+// bank-conflict free).  One MMA consumes two k-chunks (K = 8 tf32 or K = 16 fp16); advancing by one MMA's K
+// advances the start address by 2*KSTRIDE.  Advancing the start by 16*s bytes shifts the operand by s rows --
 // the "flattened shift" the implicit-GEMM convolution uses for its 9 taps.
 #pragma once
 #include <cuda_runtime.h>
@@ -43,6 +43,17 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+               "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+// kind::f16: fp16 A/B (format code 0), fp32 accumulate, both operands K-major; one MMA consumes K = 16 = two 16-byte
+// k-chunks of 8 halfs per row -- the SAME shared-memory bytes per MMA as kind::tf32 (K = 8), i.e. twice the K per
+// operand fetch (tools/tc_f16_probe.cu: identical cycles per MMA, half the cycles per unit of K)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
                "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
                : "memory");
 }

@@ -3,9 +3,11 @@
 // TALL layout of an activation with C channels at resolution HW (all 3B plane images stacked):
 //   rows: 0 = zero pad; image i at rows 1+i*(HW+1) .. i*(HW+1)+HW; one zero row after every image;
 //   cols: 0 and HW+1 are zero pad (WP = HW+2);  flattened position f = row*WP + col;
-//   memory: [hi|lo][C/4 k-chunks][PS positions][4 channels] fp32, position f stored at MARGIN+f;
-//   hi = rn_tf32(v), lo = v - hi (exact), so hi+lo == v bit-exactly and each 16-byte element is one
-//   row of one k-chunk of a K-major SWIZZLE_NONE UMMA operand (tc.cuh).
+//   memory: [hi|lo][C/8 k-chunks][PS positions][8 channels] fp16, position f stored at MARGIN+f, i.e. 16-byte
+//   elements (the code addresses them as 4 floats);  hi = fp16_rn(v), lo = fp16_rn((v - hi) * 2^11): v - hi is exact
+//   in fp32 and the 2^11 scale keeps lo a NORMAL fp16 over the whole fp16 range of v, so hi + lo*2^-11 carries 22
+//   significant bits (fp32-class) at every magnitude.  Each 16-byte element is one row of one k-chunk of a K-major
+//   SWIZZLE_NONE UMMA operand (tc.cuh).
 // Consequences:
 //   * the operand window a CTA needs (its 128*NT output positions plus a one-row/one-column halo, for
 //     one k-chunk) is ONE contiguous byte range in global memory -> a single cp.async.bulk
@@ -13,94 +15,122 @@
 //   * the 9 taps of a 3x3 conv are the same staged window advanced by (dy*WP+dx) rows = a start-address
 //     offset in the matrix descriptor (hardware-validated: tools/tc_probe.cu T5/T6);
 //   * producers write the split in their epilogue (the values are in registers anyway).
-// Accuracy: 3xTF32 (hi*hi + lo*hi + hi*lo).  Tensor-core accumulation truncates, so error grows with
-// the accumulate chain; the hi*hi products therefore go to one of two alternating TMEM accumulator
-// sets that are drained into fp32 REGISTERS every G chunks (<= 18 MMAs per chain, round-to-nearest
-// adds on the CUDA cores), while the ~2^-12-scaled correction products accumulate in two further sets.
-//
-// CTA = 160 threads: warps 0-3 own TMEM lanes 0..127 (drain + epilogue, thread t <-> position f0+t),
-// warp 4 lane 0 is the control thread (bulk copies + MMA issue).  No __syncthreads in the main loop;
-// everything is mbarrier-driven: full[s] (bytes landed) / empty[s] (tcgen05.commit) per stage,
-// acc_full[set] (commit) / acc_empty[set] (128 drainer arrivals) per accumulator set.
+// Accuracy: 3xFP16 operand splitting, x*y ~= xh*yh + xl*yh + xh*yl (fp16 has tf32's 11-bit significand, so this is the
+// 3xTF32 scheme at twice the K per MMA and half the operand bytes: tools/tc_f16_probe.cu, profiles/r01s_tc_f16_probe.txt;
+// measured 2e-7 relative vs fp64).  Tensor-core accumulation truncates, so error grows with the accumulate chain; the
+// hi*hi products therefore go to one of two alternating TMEM accumulator sets that are drained into fp32 REGISTERS after
+// every 16-channel chunk (<= 9 MMAs per chain, round-to-nearest adds on the CUDA cores), while the 2^11-scaled
+// correction products accumulate in separate sets and are folded in with one FMA (x 2^-11) at the end of the tile.
+// Range: activations and weights must stay inside fp16's +-65504 (conv outputs are clamped there; GIGA's are O(10)).
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace giga {
 
 constexpr int TALL_MARGIN = 640;   // zero positions before/after the image stack (>= WP+1 + 2*128 + slack)
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+constexpr float H_MAX = 65504.f;
 
 __host__ __device__ constexpr int tall_wp(int hw) { return hw + 2; }
 __host__ __device__ constexpr int tall_rows(int hw, int n_img) { return 1 + n_img * (hw + 1); }
 __host__ __device__ constexpr long tall_positions(int hw, int n_img) { return (long)tall_rows(hw, n_img) * tall_wp(hw); }
 // plane stride (positions) of a TALL tensor sized for n_img images
 __host__ __device__ constexpr long tall_ps(int hw, int n_img) { return 2 * TALL_MARGIN + ((tall_positions(hw, n_img) + 255) / 256) * 256; }
-__host__ __device__ constexpr long tall_floats(int hw, int n_img, int ch) { return 2L * (ch / 4) * tall_ps(hw, n_img) * 4; }
+// storage in floats (= 4-byte words): [hi|lo][ch/8][ps] 16-byte elements
+__host__ __device__ constexpr long tall_floats(int hw, int n_img, int ch) { return 2L * (ch / 8) * tall_ps(hw, n_img) * 4; }
 
-__device__ __forceinline__ float rn_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
-__device__ __forceinline__ void split4(const float4& v, float4& h, float4& l) {
-  h.x = rn_tf32(v.x); l.x = v.x - h.x;
-  h.y = rn_tf32(v.y); l.y = v.y - h.y;
-  h.z = rn_tf32(v.z); l.z = v.z - h.z;
-  h.w = rn_tf32(v.w); l.w = v.w - h.w;
+// 8 fp32 values -> one 16-byte hi element and one 16-byte (scaled) lo element
+__device__ __forceinline__ void split8(const float* v, uint4& h, uint4& l) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn((v[2 * i] - hf.x) * LO_SCALE, (v[2 * i + 1] - hf.y) * LO_SCALE);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    lw[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  h = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
+// the value a (hi, lo) pair stands for
+__device__ __forceinline__ void join8(const uint4& h, const uint4& l, float* v) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+    v[2 * i] = fmaf(lf.x, LO_INV, hf.x);
+    v[2 * i + 1] = fmaf(lf.y, LO_INV, hf.y);
+  }
+}
+__device__ __forceinline__ uint4 ldu4(const float* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void stu4(float* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 __device__ __forceinline__ long tall_pos(int hw, int img, int y, int x) { return (long)(1 + img * (hw + 1) + y) * (hw + 2) + x + 1; }
 
-// ---- layout conversion / pooling (thread = one valid pixel x one k-chunk) --------------------------
-// grid: ceil(n_img*HW*HW*(C/4) / 256), block 256
-template <int HW, int C4>   // C4 = channels / 4
+// ---- layout conversion / pooling (thread = one valid pixel x one 8-channel k-chunk) --------------------------
+// grid: ceil(n_img*HW*HW*C8 / 256), block 256
+template <int HW, int C8>   // C8 = channels / 8
 __global__ void __launch_bounds__(256) nchw_to_tall_kernel(const float* __restrict__ src, float* __restrict__ dst, long ps, int n_img) {
   const long t = (long)blockIdx.x * 256 + threadIdx.x;
-  const long total = (long)n_img * C4 * HW * HW;
+  const long total = (long)n_img * C8 * HW * HW;
   if (t >= total) return;
   const int pix = (int)(t % (HW * HW));
-  const int kc = (int)((t / (HW * HW)) % C4);
-  const int img = (int)(t / ((long)HW * HW * C4));
-  const float* p = src + ((size_t)img * (4 * C4) + 4 * kc) * (HW * HW) + pix;
-  float4 v = make_float4(__ldg(p), __ldg(p + HW * HW), __ldg(p + 2 * HW * HW), __ldg(p + 3 * HW * HW)), h, l;
-  split4(v, h, l);
+  const int kc = (int)((t / (HW * HW)) % C8);
+  const int img = (int)(t / ((long)HW * HW * C8));
+  const float* p = src + ((size_t)img * (8 * C8) + 8 * kc) * (HW * HW) + pix;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = fminf(fmaxf(__ldg(p + j * HW * HW), -H_MAX), H_MAX);
+  uint4 h, l;
+  split8(v, h, l);
   const long pos = TALL_MARGIN + tall_pos(HW, img, pix / HW, pix % HW);
-  st4(dst + ((size_t)kc * ps + pos) * 4, h);
-  st4(dst + ((size_t)(C4 + kc) * ps + pos) * 4, l);
+  stu4(dst + ((size_t)kc * ps + pos) * 4, h);
+  stu4(dst + ((size_t)(C8 + kc) * ps + pos) * 4, l);
 }
 
-template <int HW, int C4>
+template <int HW, int C8>
 __global__ void __launch_bounds__(256) tall_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, long ps, int n_img) {
   const long t = (long)blockIdx.x * 256 + threadIdx.x;
-  const long total = (long)n_img * C4 * HW * HW;
+  const long total = (long)n_img * C8 * HW * HW;
   if (t >= total) return;
   const int pix = (int)(t % (HW * HW));
-  const int kc = (int)((t / (HW * HW)) % C4);
-  const int img = (int)(t / ((long)HW * HW * C4));
+  const int kc = (int)((t / (HW * HW)) % C8);
+  const int img = (int)(t / ((long)HW * HW * C8));
   const long pos = TALL_MARGIN + tall_pos(HW, img, pix / HW, pix % HW);
-  const float4 h = ld4(src + ((size_t)kc * ps + pos) * 4), l = ld4(src + ((size_t)(C4 + kc) * ps + pos) * 4);
-  float* p = dst + ((size_t)img * (4 * C4) + 4 * kc) * (HW * HW) + pix;
-  p[0] = h.x + l.x; p[HW * HW] = h.y + l.y; p[2 * HW * HW] = h.z + l.z; p[3 * HW * HW] = h.w + l.w;
+  float v[8];
+  join8(ldu4(src + ((size_t)kc * ps + pos) * 4), ldu4(src + ((size_t)(C8 + kc) * ps + pos) * 4), v);
+  float* p = dst + ((size_t)img * (8 * C8) + 8 * kc) * (HW * HW) + pix;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j * HW * HW] = v[j];
 }
 
-// MaxPool2d(2,2) (unet.py:64): TALL(2*HW) -> TALL(HW); hi+lo reconstructs the fp32 value exactly
-template <int HW, int C4>   // HW = OUTPUT resolution
+// MaxPool2d(2,2) (unet.py:64): TALL(2*HW) -> TALL(HW) on the values the (hi, lo) pairs stand for
+template <int HW, int C8>   // HW = OUTPUT resolution
 __global__ void __launch_bounds__(256) pool_tall_kernel(const float* __restrict__ src, long ps_in, float* __restrict__ dst, long ps_out, int n_img) {
   const long t = (long)blockIdx.x * 256 + threadIdx.x;
-  const long total = (long)n_img * C4 * HW * HW;
+  const long total = (long)n_img * C8 * HW * HW;
   if (t >= total) return;
   const int pix = (int)(t % (HW * HW));
-  const int kc = (int)((t / (HW * HW)) % C4);
-  const int img = (int)(t / ((long)HW * HW * C4));
+  const int kc = (int)((t / (HW * HW)) % C8);
+  const int img = (int)(t / ((long)HW * HW * C8));
   const int y = pix / HW, x = pix % HW;
-  float4 m;
+  float m[8];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const long pos = TALL_MARGIN + tall_pos(2 * HW, img, 2 * y + (q >> 1), 2 * x + (q & 1));
-    const float4 h = ld4(src + ((size_t)kc * ps_in + pos) * 4), l = ld4(src + ((size_t)(C4 + kc) * ps_in + pos) * 4);
-    const float4 v = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
-    m = q == 0 ? v : make_float4(fmaxf(m.x, v.x), fmaxf(m.y, v.y), fmaxf(m.z, v.z), fmaxf(m.w, v.w));
+    float v[8];
+    join8(ldu4(src + ((size_t)kc * ps_in + pos) * 4), ldu4(src + ((size_t)(C8 + kc) * ps_in + pos) * 4), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = q == 0 ? v[j] : fmaxf(m[j], v[j]);
   }
-  float4 h, l;
-  split4(m, h, l);
+  uint4 h, l;
+  split8(m, h, l);
   const long pos = TALL_MARGIN + tall_pos(HW, img, y, x);
-  st4(dst + ((size_t)kc * ps_out + pos) * 4, h);
-  st4(dst + ((size_t)(C4 + kc) * ps_out + pos) * 4, l);
+  stu4(dst + ((size_t)kc * ps_out + pos) * 4, h);
+  stu4(dst + ((size_t)(C8 + kc) * ps_out + pos) * 4, l);
 }
 
 // ---- mbarrier / bulk-copy helpers (beyond tc.cuh) ----------------------------------------------------
@@ -129,7 +159,7 @@ struct TallCfg {
   static constexpr bool FUSE_FINAL = FUSE_FINAL_;
   static constexpr int WP = HW + 2, HP1 = HW + 1;
   static constexpr int NTAPS = MODE == 0 ? 9 : 1;
-  static constexpr int NC = CIN / 8;                         // 8-channel chunks (one K=8 MMA step per tap)
+  static constexpr int NC = CIN / 16;                        // 16-channel chunks (one K=16 fp16 MMA step per tap)
   static constexpr int G = MODE == 0 ? 1 : NC;               // chunks per accumulator group (drain period)
   static constexpr int NG = NC / G;
   static constexpr int MT = NT * 128;
@@ -137,7 +167,7 @@ struct TallCfg {
   static constexpr int ROWS_WIN = MT + 2 * HALO;
   static constexpr int KS_A = ROWS_WIN * 16;                 // bytes per staged k-chunk
   static constexpr int A_BYTES = 4 * KS_A;                   // hi kc0, hi kc1, lo kc0, lo kc1
-  static constexpr int B_BYTES = NTAPS * 2 * 2 * NTILE * 16; // [tap][kc][hi|lo][n][4]
+  static constexpr int B_BYTES = NTAPS * 2 * 2 * NTILE * 16; // [tap][kc][hi|lo][n][8 halfs]
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NNT = MODE == 0 ? COUT / NTILE : 4;   // grid.y
   static constexpr int ACC = NT * NTILE;                     // columns per accumulator set
@@ -147,286 +177,18 @@ struct TallCfg {
   static constexpr int OFF_BIAS = OFF_BAR + 96;
   static constexpr int SMEM_BYTES = OFF_BIAS + 64 * 4;
   static constexpr int FIN_KS = 128 * 16 + 16;
-  static constexpr int FIN_A_BYTES = 8 * FIN_KS;
+  static constexpr int FIN_A_BYTES = 4 * FIN_KS;             // conv_final A operand: K = 32 = 4 k-chunks of 8 halfs
   static constexpr int NTHREADS = 160;
-  static_assert(CIN0 % 8 == 0 && CIN1 % 8 == 0 && NTILE % 32 == 0 && NTILE <= 64 && NC % G == 0 && NC >= 2, "tiling");
+  static_assert(CIN0 % 16 == 0 && CIN1 % 16 == 0 && NTILE % 32 == 0 && NTILE <= 64 && NC % G == 0 && NC >= 2, "tiling");
   static_assert(MODE == 1 || COUT % NTILE == 0, "N tiling");
   static_assert(MODE == 0 || NTILE == COUT, "transpose conv: one (a,b) parity class per N tile");
   static_assert(TMEM_NEED <= 256, "TMEM budget (2 CTAs/SM)");
-  static_assert(!FUSE_FINAL || (MODE == 0 && COUT == 32 && NTILE == 32 && 2 * FIN_A_BYTES + 8192 <= 2 * STAGE_BYTES), "fused conv_final");
+  static_assert(!FUSE_FINAL || (MODE == 0 && COUT == 32 && NTILE == 32 && 2 * FIN_A_BYTES + 4096 <= 2 * STAGE_BYTES), "fused conv_final");
   static_assert(HALO + MT + 128 <= TALL_MARGIN, "margin");
   static int num_ctas(int n_img) { return ceil_div((int)ceil_div((long)tall_positions(HW, n_img), 128L), NT); }
-  // packed weights: [ntile][chunk][tap][kc 2][hi|lo][n NTILE][4]
+  // packed weights: [ntile][chunk][tap][kc 2][hi|lo][n NTILE][8 halfs]
   static constexpr long weight_floats() { return (long)NNT * NC * (B_BYTES / 4); }
 };
-
-// grid (num_ctas, NNT), block 160, dynamic smem SMEM_BYTES
-template <class K>
-__global__ void __launch_bounds__(160, 2)
-conv_tall_kernel(const float* __restrict__ src0, long ps0,   // TALL [2][CIN0/4][ps0][4]
-                 const float* __restrict__ src1, long ps1,   // TALL [2][CIN1/4][ps1][4] or null
-                 const float* __restrict__ wt,               // packed weights (see TallCfg)
-                 const float* __restrict__ bias,             // [COUT]
-                 float* __restrict__ out, long pso,          // TALL [2][COUT/4][pso][4] at HW (MODE 0) or 2*HW (MODE 1)
-                 const float* __restrict__ fin_w, const float* __restrict__ fin_b, float* __restrict__ fin_out,  // FUSE_FINAL
-                 int n_img, unsigned long long* __restrict__ tl) {   // tl: optional per-CTA timeline (32 x u64), debug only
-  constexpr int HW = K::HW, WP = K::WP, HP1 = K::HP1, NTILE = K::NTILE, NT = K::NT, ACC = K::ACC;
-  extern __shared__ __align__(128) uint8_t smem_tall[];
-  uint8_t* smem = smem_tall;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);  // [2]
-  uint64_t* empty = full + 2;                                        // [2]
-  uint64_t* acc_full = full + 4;                                     // [2]
-  uint64_t* acc_empty = full + 6;                                    // [2]
-  uint64_t* fin_bar = full + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + K::OFF_BAR + 80);
-  float* sbias = reinterpret_cast<float*>(smem + K::OFF_BIAS);   // this CTA's NTILE biases (first touch costs an L2 round trip)
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int f0 = blockIdx.x * K::MT;
-  const int nt_idx = blockIdx.y;
-  const int total_rows = tall_rows(HW, n_img);
-  unsigned long long* tlc = tl ? tl + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
-  auto stamp = [&](int slot) {
-    if (tlc) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      tlc[slot] = t;
-    }
-  };
-  if (tid == 0) stamp(0);
-
-  if (warp == 4) tc::tmem_alloc(tmem_slot, K::TMEM_COLS);
-  if (tid < NTILE) sbias[tid] = __ldg(bias + (K::MODE == 0 ? blockIdx.y * NTILE : 0) + tid);
-  if (tid == 0) {
-    tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1);
-    tc::mbar_init(&empty[0], 1); tc::mbar_init(&empty[1], 1);
-    tc::mbar_init(&acc_full[0], 1); tc::mbar_init(&acc_full[1], 1);
-    tc::mbar_init(&acc_empty[0], 128); tc::mbar_init(&acc_empty[1], 128);
-    tc::mbar_init(fin_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  tc::fence_smem_to_async();
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 4) {
-    // ===================== control warp: bulk copies + MMA issue by one elected lane =====================
-    // (the whole warp runs the loop so that addresses/descriptors stay warp-uniform -> uniform registers)
-    constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NTILE);
-    const float* wt_cta = wt + (size_t)nt_idx * K::NC * (K::B_BYTES / 4);
-    auto loads = [&](int c) {
-      const int s = c & 1;
-      uint8_t* stA = smem + s * K::STAGE_BYTES;
-      if (c >= 2) tc::mbar_wait(&empty[s], (uint32_t)(((c - 2) >> 1) & 1));   // MMAs of chunk c-2 have consumed the stage
-      const int ch0 = c * 8;
-      const float* sp; long ps; int kch, kcn;
-      if (ch0 < K::CIN0) { sp = src0; ps = ps0; kch = ch0 / 4; kcn = K::CIN0 / 4; }
-      else { sp = src1; ps = ps1; kch = (ch0 - K::CIN0) / 4; kcn = K::CIN1 / 4; }
-      const long pos0 = TALL_MARGIN + f0 - K::HALO;
-      if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)K::STAGE_BYTES);
-#pragma unroll
-        for (int hl = 0; hl < 2; ++hl)
-#pragma unroll
-          for (int kc = 0; kc < 2; ++kc)
-            tc::bulk_g2s(stA + (hl * 2 + kc) * K::KS_A, sp + ((size_t)(hl * kcn + kch + kc) * ps + pos0) * 4, K::KS_A, &full[s]);
-        tc::bulk_g2s(stA + K::A_BYTES, wt_cta + (size_t)c * (K::B_BYTES / 4), K::B_BYTES, &full[s]);
-      }
-      __syncwarp();
-    };
-    if ((tid & 31) == 0) stamp(1);
-    loads(0);
-    loads(1);
-#pragma unroll 1
-    for (int c = 0; c < K::NC; ++c) {
-      const int s = c & 1, g = c / K::G, set = g & 1;
-      const bool group_first = (c % K::G) == 0, group_last = (c % K::G) == K::G - 1;
-      tc::mbar_wait(&full[s], (uint32_t)((c >> 1) & 1));
-      if ((tid & 31) == 0 && c < 4) stamp(2 + 2 * c);
-      if (group_first && g >= 2) tc::mbar_wait(&acc_empty[set], (uint32_t)(((g - 2) >> 1) & 1));
-      tc::fence_after_sync();
-      const uint32_t a_hi = tc::smem_u32(smem + s * K::STAGE_BYTES), a_lo = a_hi + 2 * K::KS_A, b0 = a_hi + K::A_BYTES;
-      if (tc::elect_one()) {
-        // Dependent MMAs into one TMEM accumulator serialise on its ~100-cycle read-modify-write latency
-        // (measured: profiles/r01_conv_timeline.txt), far longer than a 128xNTILEx8 MMA executes (NTILE/2
-        // cycles).  So consecutive MMAs go round-robin over 3*NT independent accumulator chains.
-#pragma unroll
-        for (int tap = 0; tap < K::NTAPS; ++tap) {
-          const int dy = tap / 3, dx = tap - dy * 3;
-          const uint32_t bb = b0 + tap * (4 * NTILE * 16);          // [kc][hi|lo][n][4]: k-chunk stride 2*NTILE*16
-          const uint64_t bh = tc::make_desc(bb, 2 * NTILE * 16, 128);
-          const uint64_t bl = tc::make_desc(bb + NTILE * 16, 2 * NTILE * 16, 128);
-#pragma unroll
-          for (int mt = 0; mt < NT; ++mt) {   // hi*hi -> the drained set
-            const uint32_t aoff = (uint32_t)(mt * 128 + (K::MODE == 0 ? dy * WP + dx : 0)) * 16;
-            tc::mma_tf32(tmem + set * ACC + mt * NTILE, tc::make_desc(a_hi + aoff, K::KS_A, 128), bh, IDESC, (group_first && tap == 0) ? 0u : 1u);
-          }
-#pragma unroll
-          for (int mt = 0; mt < NT; ++mt) {   // lo*hi
-            const uint32_t aoff = (uint32_t)(mt * 128 + (K::MODE == 0 ? dy * WP + dx : 0)) * 16;
-            tc::mma_tf32(tmem + 2 * ACC + mt * NTILE, tc::make_desc(a_lo + aoff, K::KS_A, 128), bh, IDESC, (c == 0 && tap == 0) ? 0u : 1u);
-          }
-#pragma unroll
-          for (int mt = 0; mt < NT; ++mt) {   // hi*lo
-            const uint32_t aoff = (uint32_t)(mt * 128 + (K::MODE == 0 ? dy * WP + dx : 0)) * 16;
-            tc::mma_tf32(tmem + 3 * ACC + mt * NTILE, tc::make_desc(a_hi + aoff, K::KS_A, 128), bl, IDESC, (c == 0 && tap == 0) ? 0u : 1u);
-          }
-        }
-        tc::mma_commit(&empty[s]);
-        if (group_last) tc::mma_commit(&acc_full[set]);
-      }
-      __syncwarp();
-      if ((tid & 31) == 0 && c < 4) stamp(3 + 2 * c);
-      if (c >= 1 && c + 1 < K::NC) loads(c + 1);
-    }
-    if ((tid & 31) == 0) stamp(10);
-  } else {
-    // =============================== drain + epilogue warps (thread t <-> TMEM lane t) ===============================
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
-    float acc[NT][NTILE];
-#pragma unroll
-    for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-      for (int j = 0; j < NTILE; ++j) acc[mt][j] = 0.f;
-#pragma unroll 1
-    for (int g = 0; g < K::NG; ++g) {
-      const int set = g & 1;
-      tc::mbar_wait(&acc_full[set], (uint32_t)((g >> 1) & 1));
-      tc::fence_after_sync();
-      if (tid == 0 && g < 4) stamp(12 + g);
-#pragma unroll
-      for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-        for (int n0 = 0; n0 < NTILE; n0 += 32) {
-          float v[32];
-          tc::tmem_ld32(tmem_row + set * ACC + mt * NTILE + n0, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[mt][n0 + j] += v[j];
-        }
-      tc::fence_before_sync();
-      tc::mbar_arrive(&acc_empty[set]);
-    }
-    if (tid == 0) stamp(20);
-    // the last group's commit covers every MMA, including the correction set
-#pragma unroll
-    for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-      for (int n0 = 0; n0 < NTILE; n0 += 32) {
-        float v[32], w[32];
-        tc::tmem_ld32(tmem_row + 2 * ACC + mt * NTILE + n0, v);
-        tc::tmem_ld32(tmem_row + 3 * ACC + mt * NTILE + n0, w);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[mt][n0 + j] += v[j] + w[j];
-      }
-
-#pragma unroll
-    for (int mt = 0; mt < NT; ++mt) {
-      const int f = f0 + mt * 128 + tid;
-      const int r = f / WP, cc = f - r * WP;
-      const int rr = r - 1, img = rr / HP1, y = rr - img * HP1, x = cc - 1;
-      const bool valid = cc >= 1 && cc <= HW && r >= 1 && r < total_rows && y < HW;
-      if constexpr (K::MODE == 0 && !K::FUSE_FINAL) {
-        if (valid) {
-          const long pos = TALL_MARGIN + f;
-#pragma unroll
-          for (int kc = 0; kc < NTILE / 4; ++kc) {
-            const int co = nt_idx * NTILE + 4 * kc;
-            const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * kc);
-            const float4 v = make_float4(fmaxf(acc[mt][4 * kc + 0] + bv.x, 0.f), fmaxf(acc[mt][4 * kc + 1] + bv.y, 0.f),
-                                         fmaxf(acc[mt][4 * kc + 2] + bv.z, 0.f), fmaxf(acc[mt][4 * kc + 3] + bv.w, 0.f));
-            float4 h, l;
-            split4(v, h, l);
-            st4(out + ((size_t)(co / 4) * pso + pos) * 4, h);
-            st4(out + ((size_t)(K::COUT / 4 + co / 4) * pso + pos) * 4, l);
-          }
-        }
-      } else if constexpr (K::MODE == 1) {
-        if (valid) {
-          const int a = nt_idx >> 1, b = nt_idx & 1;
-          const long pos = TALL_MARGIN + tall_pos(2 * HW, img, 2 * y + a, 2 * x + b);
-#pragma unroll
-          for (int kc = 0; kc < NTILE / 4; ++kc) {
-            const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * kc);
-            const float4 v = make_float4(acc[mt][4 * kc + 0] + bv.x, acc[mt][4 * kc + 1] + bv.y, acc[mt][4 * kc + 2] + bv.z, acc[mt][4 * kc + 3] + bv.w);
-            float4 h, l;
-            split4(v, h, l);
-            st4(out + ((size_t)kc * pso + pos) * 4, h);
-            st4(out + ((size_t)(K::COUT / 4 + kc) * pso + pos) * 4, l);
-          }
-        }
-      } else {
-        // conv_final (1x1, no activation) fused: relu(conv) -> A operand -> 32x32 3xTF32 MMA -> +bias -> channels-last
-        uint8_t* fa_hi = smem;
-        uint8_t* fa_lo = smem + K::FIN_A_BYTES;
-        uint8_t* fw = smem + 2 * K::FIN_A_BYTES;   // [hi|lo][kc 8][n 32][4]
-#pragma unroll
-        for (int kc = 0; kc < 8; ++kc) {
-          const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * kc);
-          const float4 v = make_float4(fmaxf(acc[mt][4 * kc + 0] + bv.x, 0.f), fmaxf(acc[mt][4 * kc + 1] + bv.y, 0.f),
-                                       fmaxf(acc[mt][4 * kc + 2] + bv.z, 0.f), fmaxf(acc[mt][4 * kc + 3] + bv.w, 0.f));
-          float4 h, l;
-          split4(v, h, l);
-          *reinterpret_cast<float4*>(fa_hi + kc * K::FIN_KS + tid * 16) = h;
-          *reinterpret_cast<float4*>(fa_lo + kc * K::FIN_KS + tid * 16) = l;
-        }
-        if (mt == 0) {
-          const float4* wsrc = reinterpret_cast<const float4*>(fin_w);
-          float4* wdst = reinterpret_cast<float4*>(fw);
-          for (int e = tid; e < 512; e += 128) wdst[e] = __ldg(wsrc + e);
-        }
-        tc::fence_smem_to_async();
-        tc::fence_before_sync();
-        tc::named_bar_sync(1, 128);
-        if (warp == 0) {
-          tc::fence_after_sync();
-          const uint32_t ah0 = tc::smem_u32(fa_hi), al0 = tc::smem_u32(fa_lo), w0 = tc::smem_u32(fw);
-          constexpr uint32_t ID32 = tc::make_idesc_tf32(128, 32);
-          if (tc::elect_one()) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ah = tc::make_desc(ah0 + ks * 2 * K::FIN_KS, K::FIN_KS, 128);
-              const uint64_t al = tc::make_desc(al0 + ks * 2 * K::FIN_KS, K::FIN_KS, 128);
-              const uint64_t bh = tc::make_desc(w0 + ks * 2 * 512, 512, 128);
-              const uint64_t bl = tc::make_desc(w0 + 4096 + ks * 2 * 512, 512, 128);
-              tc::mma_tf32(tmem, ah, bh, ID32, ks > 0 ? 1u : 0u);
-              tc::mma_tf32(tmem, al, bh, ID32, 1u);
-              tc::mma_tf32(tmem, ah, bl, ID32, 1u);
-            }
-            tc::mma_commit(fin_bar);
-          }
-          __syncwarp();
-        }
-        tc::mbar_wait(fin_bar, (uint32_t)(mt & 1));
-        tc::fence_after_sync();
-        float v[32];
-        tc::tmem_ld32(tmem_row, v);
-        if (valid) {
-          float* op = fin_out + ((size_t)img * (HW * HW) + y * HW + x) * 32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            st4(op + j, make_float4(v[j] + __ldg(fin_b + j), v[j + 1] + __ldg(fin_b + j + 1), v[j + 2] + __ldg(fin_b + j + 2),
-                                    v[j + 3] + __ldg(fin_b + j + 3)));
-        }
-        tc::fence_before_sync();
-        tc::named_bar_sync(1, 128);   // fa_* / final accumulator free for the next M tile
-      }
-    }
-  }
-  if (tid == 0) stamp(21);
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem, K::TMEM_COLS);
-  if (tid == 0) {
-    stamp(22);
-    if (tlc) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      tlc[31] = smid;
-    }
-  }
-}
-
 
 // =====================================================================================================
 // Persistent variant: one CTA per SM walks a strided list of work items (M-tile group x N tile) so that
@@ -454,7 +216,7 @@ struct PersistCfg {
   static constexpr int STAGE_BYTES = K::A_BYTES + (WRES ? 0 : K::B_BYTES);
   static constexpr int OFF_STAGES = W_BYTES;
   static constexpr int OFF_FIN = OFF_STAGES + S * STAGE_BYTES;                   // conv_final scratch (FUSE_FINAL)
-  static constexpr int FIN_BYTES = K::FUSE_FINAL ? 2 * K::FIN_A_BYTES + 8192 : 0;
+  static constexpr int FIN_BYTES = K::FUSE_FINAL ? 2 * K::FIN_A_BYTES + 4096 : 0;
   static constexpr int OFF_BIAS = OFF_FIN + FIN_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 64 * 4;
   static constexpr int NBAR = 2 * S + 10;                                        // full[S] empty[S] acc_full[2] acc_empty[2] z_full[2] z_empty[2] wbar fin
@@ -462,7 +224,7 @@ struct PersistCfg {
   static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
   static constexpr int ACC = K::ACC;
   static constexpr int TMEM_COLS = 512;                                          // X Y | Z1a Z2a | Z1b Z2b | final  (6*ACC + 32 <= 512)
-  static_assert(OFF_FINACC + 32 <= 512, "TMEM");
+  static_assert(OFF_FINACC + 64 <= 512, "TMEM");   // conv_final: hi*hi columns + scaled-correction columns
   static_assert(!NCONCAT || K::NTILE == 32, "N-concat doubles the MMA's N; kept for the NTILE=32 layers");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
   static_assert(!WRES || K::NNT == 1, "resident weights cover one N tile");
@@ -511,7 +273,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
   if (K::FUSE_FINAL && tid < 128) {   // conv_final weights: staged once per CTA
     const float4* wsrc = reinterpret_cast<const float4*>(fin_w);
     float4* wdst = reinterpret_cast<float4*>(smem + P::OFF_FIN + 2 * K::FIN_A_BYTES);
-    for (int e = tid; e < 512; e += 128) wdst[e] = __ldg(wsrc + e);
+    for (int e = tid; e < 256; e += 128) wdst[e] = __ldg(wsrc + e);
   }
   tc::fence_smem_to_async();
   tc::fence_before_sync();
@@ -546,10 +308,10 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
       const int grp = item / K::NNT, nt = item - grp * K::NNT;
       if (i >= S) twait(&empty[s], (uint32_t)(((i / S) - 1) & 1), w_a);   // all three MMA warps are done with the stage
       uint8_t* stA = smem + P::OFF_STAGES + s * P::STAGE_BYTES;
-      const int ch0 = c * 8;
+      const int ch0 = c * 16;
       const float* sp; long ps; int kch, kcn;
-      if (ch0 < K::CIN0) { sp = src0; ps = ps0; kch = ch0 / 4; kcn = K::CIN0 / 4; }
-      else { sp = src1; ps = ps1; kch = (ch0 - K::CIN0) / 4; kcn = K::CIN1 / 4; }
+      if (ch0 < K::CIN0) { sp = src0; ps = ps0; kch = ch0 / 8; kcn = K::CIN0 / 8; }
+      else { sp = src1; ps = ps1; kch = (ch0 - K::CIN0) / 8; kcn = K::CIN1 / 8; }
       const long pos0 = TALL_MARGIN + (long)grp * K::MT - K::HALO;
       if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(&full[s], (uint32_t)P::STAGE_BYTES);
@@ -568,7 +330,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
     // 3-product form: 5 = hi*hi, 6 = lo*hi, 7 = hi*lo.   N-concat form: 5 = Ahi.[Bhi;Blo]^T, 6 = Alo.Bhi^T.
     const int kind = warp - 5;
     constexpr int NMMA = (P::NCONCAT ? 2 : 1) * NTILE;             // N of warp 5's MMAs
-    const uint32_t idesc = (P::NCONCAT && kind == 0) ? tc::make_idesc_tf32(128, NMMA) : tc::make_idesc_tf32(128, NTILE);
+    const uint32_t idesc = (P::NCONCAT && kind == 0) ? tc::make_idesc_f16(128, NMMA) : tc::make_idesc_f16(128, NTILE);
     if (P::WRES && my_items > 0) tc::mbar_wait(wbar, 0u);
 #pragma unroll 1
     for (int i = 0; i < total_chunks; ++i) {
@@ -596,7 +358,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
 #pragma unroll
           for (int mt = 0; mt < NT; ++mt) {
             const uint32_t aoff = (uint32_t)(mt * 128 + (K::MODE == 0 ? dy * WP + dx : 0)) * 16;
-            tc::mma_tf32(d_base + mt * d_stride, tc::make_desc(a_base + aoff, K::KS_A, 128), bd, idesc, (fresh && tap == 0) ? 0u : 1u);
+            tc::mma_f16(d_base + mt * d_stride, tc::make_desc(a_base + aoff, K::KS_A, 128), bd, idesc, (fresh && tap == 0) ? 0u : 1u);
           }
         }
         tc::mma_commit(&empty[s]);
@@ -641,7 +403,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
               tc::tmem_ld32(tmem_row + set * P::ACC1 + mt * 2 * NTILE + n0, v);
               tc::tmem_ld32(tmem_row + set * P::ACC1 + mt * 2 * NTILE + NTILE + n0, w);
 #pragma unroll
-              for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q] + w[q];
+              for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += fmaf(w[q], LO_INV, v[q]);
             } else {
               tc::tmem_ld32(tmem_row + set * P::ACC1 + mt * NTILE + n0, v);
 #pragma unroll
@@ -663,11 +425,11 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           float v[32];
           tc::tmem_ld32(tmem_row + P::OFF_Z + zp * P::ZCOLS + mt * NTILE + n0, v);
 #pragma unroll
-          for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q];
+          for (int q = 0; q < 32; ++q) acc[mt][n0 + q] = fmaf(v[q], LO_INV, acc[mt][n0 + q]);
           if constexpr (!P::NCONCAT) {
             tc::tmem_ld32(tmem_row + P::OFF_Z + zp * P::ZCOLS + ACC + mt * NTILE + n0, v);
 #pragma unroll
-            for (int q = 0; q < 32; ++q) acc[mt][n0 + q] += v[q];
+            for (int q = 0; q < 32; ++q) acc[mt][n0 + q] = fmaf(v[q], LO_INV, acc[mt][n0 + q]);
           }
         }
       tc::fence_before_sync();
@@ -684,15 +446,15 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           if (valid) {
             const long pos = TALL_MARGIN + f;
 #pragma unroll
-            for (int kc = 0; kc < NTILE / 4; ++kc) {
-              const int co = nt_idx * NTILE + 4 * kc;
-              const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * kc);
-              const float4 v = make_float4(fmaxf(acc[mt][4 * kc + 0] + bv.x, 0.f), fmaxf(acc[mt][4 * kc + 1] + bv.y, 0.f),
-                                           fmaxf(acc[mt][4 * kc + 2] + bv.z, 0.f), fmaxf(acc[mt][4 * kc + 3] + bv.w, 0.f));
-              float4 h, l;
-              split4(v, h, l);
-              st4(out + ((size_t)(co / 4) * pso + pos) * 4, h);
-              st4(out + ((size_t)(K::COUT / 4 + co / 4) * pso + pos) * 4, l);
+            for (int kc = 0; kc < NTILE / 8; ++kc) {
+              const int co = nt_idx * NTILE + 8 * kc;
+              float v[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = fminf(fmaxf(acc[mt][8 * kc + q] + sbias[8 * kc + q], 0.f), H_MAX);
+              uint4 h, l;
+              split8(v, h, l);
+              stu4(out + ((size_t)(co / 8) * pso + pos) * 4, h);
+              stu4(out + ((size_t)(K::COUT / 8 + co / 8) * pso + pos) * 4, l);
             }
           }
         } else if constexpr (K::MODE == 1) {
@@ -700,13 +462,14 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
             const int a = nt_idx >> 1, b = nt_idx & 1;
             const long pos = TALL_MARGIN + tall_pos(2 * HW, img, 2 * y + a, 2 * x + b);
 #pragma unroll
-            for (int kc = 0; kc < NTILE / 4; ++kc) {
-              const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * kc);
-              const float4 v = make_float4(acc[mt][4 * kc + 0] + bv.x, acc[mt][4 * kc + 1] + bv.y, acc[mt][4 * kc + 2] + bv.z, acc[mt][4 * kc + 3] + bv.w);
-              float4 h, l;
-              split4(v, h, l);
-              st4(out + ((size_t)kc * pso + pos) * 4, h);
-              st4(out + ((size_t)(K::COUT / 4 + kc) * pso + pos) * 4, l);
+            for (int kc = 0; kc < NTILE / 8; ++kc) {
+              float v[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = fminf(fmaxf(acc[mt][8 * kc + q] + sbias[8 * kc + q], -H_MAX), H_MAX);
+              uint4 h, l;
+              split8(v, h, l);
+              stu4(out + ((size_t)kc * pso + pos) * 4, h);
+              stu4(out + ((size_t)(K::COUT / 8 + kc) * pso + pos) * 4, l);
             }
           }
         } else {
@@ -714,14 +477,14 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           uint8_t* fa_lo = fa_hi + K::FIN_A_BYTES;
           uint8_t* fw = fa_lo + K::FIN_A_BYTES;
 #pragma unroll
-          for (int kc = 0; kc < 8; ++kc) {
-            const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * kc);
-            const float4 v = make_float4(fmaxf(acc[mt][4 * kc + 0] + bv.x, 0.f), fmaxf(acc[mt][4 * kc + 1] + bv.y, 0.f),
-                                         fmaxf(acc[mt][4 * kc + 2] + bv.z, 0.f), fmaxf(acc[mt][4 * kc + 3] + bv.w, 0.f));
-            float4 h, l;
-            split4(v, h, l);
-            *reinterpret_cast<float4*>(fa_hi + kc * K::FIN_KS + tid * 16) = h;
-            *reinterpret_cast<float4*>(fa_lo + kc * K::FIN_KS + tid * 16) = l;
+          for (int kc = 0; kc < 4; ++kc) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fminf(fmaxf(acc[mt][8 * kc + q] + sbias[8 * kc + q], 0.f), H_MAX);
+            uint4 h, l;
+            split8(v, h, l);
+            *reinterpret_cast<uint4*>(fa_hi + kc * K::FIN_KS + tid * 16) = h;
+            *reinterpret_cast<uint4*>(fa_lo + kc * K::FIN_KS + tid * 16) = l;
           }
           tc::fence_smem_to_async();
           tc::fence_before_sync();
@@ -729,17 +492,17 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           if (warp == 0) {
             tc::fence_after_sync();
             const uint32_t ah0 = tc::smem_u32(fa_hi), al0 = tc::smem_u32(fa_lo), w0 = tc::smem_u32(fw);
-            constexpr uint32_t ID32 = tc::make_idesc_tf32(128, 32);
+            constexpr uint32_t ID32 = tc::make_idesc_f16(128, 32);
             if (tc::elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
+              for (int ks = 0; ks < 2; ++ks) {   // K = 32 = 2 MMAs of K = 16; weights [hi|lo][kc 4][n 32][8 halfs]
                 const uint64_t ah = tc::make_desc(ah0 + ks * 2 * K::FIN_KS, K::FIN_KS, 128);
                 const uint64_t al = tc::make_desc(al0 + ks * 2 * K::FIN_KS, K::FIN_KS, 128);
                 const uint64_t bh = tc::make_desc(w0 + ks * 2 * 512, 512, 128);
-                const uint64_t bl = tc::make_desc(w0 + 4096 + ks * 2 * 512, 512, 128);
-                tc::mma_tf32(tmem + P::OFF_FINACC, ah, bh, ID32, ks > 0 ? 1u : 0u);
-                tc::mma_tf32(tmem + P::OFF_FINACC, al, bh, ID32, 1u);
-                tc::mma_tf32(tmem + P::OFF_FINACC, ah, bl, ID32, 1u);
+                const uint64_t bl = tc::make_desc(w0 + 2048 + ks * 2 * 512, 512, 128);
+                tc::mma_f16(tmem + P::OFF_FINACC, ah, bh, ID32, ks > 0 ? 1u : 0u);
+                tc::mma_f16(tmem + P::OFF_FINACC + 32, al, bh, ID32, ks > 0 ? 1u : 0u);   // 2^11-scaled corrections
+                tc::mma_f16(tmem + P::OFF_FINACC + 32, ah, bl, ID32, 1u);
               }
               tc::mma_commit(fin_bar);
             }
@@ -748,8 +511,11 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           tc::mbar_wait(fin_bar, fin_use & 1u);
           ++fin_use;
           tc::fence_after_sync();
-          float v[32];
+          float v[32], z[32];
           tc::tmem_ld32(tmem_row + P::OFF_FINACC, v);
+          tc::tmem_ld32(tmem_row + P::OFF_FINACC + 32, z);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = fmaf(z[q], LO_INV, v[q]);
           if (valid) {
             float* op = fin_out + ((size_t)img * (HW * HW) + y * HW + x) * 32;
 #pragma unroll

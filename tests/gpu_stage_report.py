@@ -34,7 +34,7 @@ def main(B=2, N=300):
         cap = {}
         ref_planes = torch.stack([O.unet_forward(sd, pre_stack.reshape(3 * B, 32, 40, 40), capture=cap).reshape(3, B, 32, 40, 40)[i]
                                   for i in range(3)])
-        for eimpl, etag in ((0, "ffma"), (2, "tc2"), (1, "tc")):
+        for eimpl, etag in ((0, "ffma"), (1, "tc")):
             net._engine().set_option("encoder_impl", eimpl)
             c = net.encode_inputs(x.to(dev))
             torch.cuda.synchronize()

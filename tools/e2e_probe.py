@@ -14,7 +14,7 @@ hx = [torch.rand(B, 40, 40, 40).pin_memory() for _ in range(2)]
 hp = [(torch.rand(B, N, 3) - 0.5).pin_memory() for _ in range(2)]
 hpt = [(torch.rand(B, N, 3) - 0.5).pin_memory() for _ in range(2)]
 outs = [(pin(B, N), pin(B, N, 4), pin(B, N), pin(B, N)) for _ in range(2)]
-for impl in (2, 1, 0):
+for impl in (1, 0):
     net._engine().set_option("encoder_impl", impl)
     for i in range(4):
         net.forward_host(hx[i % 2], hp[i % 2], hpt[i % 2], out=outs[0])
