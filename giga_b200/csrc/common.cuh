@@ -13,6 +13,14 @@ constexpr int C = 32;          // plane feature channels / decoder hidden size
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ constexpr int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
+// Programmatic dependent launch (PDL): kernels on the fast path are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel may become resident -- and run its prologue (barrier
+// init, TMEM allocation, weight staging) -- while its predecessor in the stream is still draining.  pdl_launch() lets the
+// successor start early; pdl_wait() blocks until the predecessor grid has completed and its writes are visible, and must
+// precede the first access to anything a previous kernel wrote (or still reads).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 

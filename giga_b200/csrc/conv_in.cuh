@@ -39,6 +39,8 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
                       float* __restrict__ xz_part,   // [B][CI_NT][40 ix][32][40 iz]
                       int B, const __grid_constant__ ConvInParams P) {
   extern __shared__ __align__(16) float smem[];
+  pdl_launch();
+  pdl_wait();
   float* red = smem;                // [32*TY][44]
   float* xyacc = red + CI_RED;      // [32*TY][44]  (col = ix)
 
@@ -158,6 +160,8 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
 __global__ void __launch_bounds__(256)
 xz_finish_kernel(const float* __restrict__ xz_part, float* __restrict__ pre, int B) {
   __shared__ float tile[G * 41];
+  pdl_launch();
+  pdl_wait();
   const int c = blockIdx.x, b = blockIdx.y;
   for (int e = threadIdx.x; e < G2; e += 256) {
     const int ix = e / G, z = e % G;

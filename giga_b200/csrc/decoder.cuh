@@ -265,6 +265,8 @@ __global__ void __launch_bounds__(256)
 scene_argmax_kernel(const float* __restrict__ qual, int N, float* __restrict__ best_val, int* __restrict__ best_idx) {
   __shared__ float sv[8];
   __shared__ int si[8];
+  pdl_launch();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   float v = -INFINITY;
   int i = 0x7fffffff;

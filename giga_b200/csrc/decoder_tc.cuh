@@ -157,12 +157,14 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
     ++tslot;
   };
   stamp();   // 0: start
+  pdl_launch();
   if (warp == 0) tc::tmem_alloc(tmem_slot, TD_TMEM_COLS);
   if (tid == 0) {
     tc::mbar_init(bar, 1); tc::mbar_init(&wbar[0], 1); tc::mbar_init(&wbar[1], 1); tc::mbar_init(pbar, 1); tc::mbar_init(bar3, 3);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
+  pdl_wait();   // plane features (and points) of the preceding kernels are complete; outputs are only written below
   // ---- gather: the warp's 32 points, lane = channel; features stay in registers ----
   float F[3][32];
   {

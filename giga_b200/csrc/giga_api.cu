@@ -136,6 +136,7 @@ struct giga_ctx {
   float* d_heads = nullptr;  // [4][DW_HEAD]   fp32 FMA-pipe decoder
   float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo tf32 splits)
   int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
+  int pdl = 1;               // programmatic dependent launch between the fast-path kernels (1 = on)
   int encoder_impl = 1;      // U-Net convs: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int last_impl = 0;
   int num_sms = 148;
@@ -210,6 +211,23 @@ struct LaunchScope {
     ctx->launches++;
   }
 };
+
+// Launch on the fast path: with ctx->pdl the kernel carries the programmatic-stream-serialization attribute, i.e. it may
+// start (up to its griddepcontrol.wait) while the previous kernel in the stream is still running (common.cuh).
+template <typename... KArgs, typename... Args>
+void launch_k(const giga_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 int ensure_attrs(giga_ctx* ctx) {
   if (ctx->attrs_set) return GIGA_OK;
@@ -290,9 +308,8 @@ void launch_persist(giga_ctx* ctx, const char* name, int n_img, const TallBuf& s
     tl = ctx->d_timeline;
   }
   LaunchScope ls(ctx, name, st);
-  conv_tall_persistent_kernel<P><<<grid, P::NTHREADS, P::SMEM_BYTES, st>>>(s0.p, s0.ps, s1.p, s1.ps, w, bias, out.p, out.ps,
-                                                                           ctx->d_enc + ctx->el.tc_fin, ctx->d_enc + ctx->el.fin_b,
-                                                                           fin_out, n_img, n_groups, tl);
+  launch_k(ctx, conv_tall_persistent_kernel<P>, dim3(grid), dim3(P::NTHREADS), P::SMEM_BYTES, st, s0.p, s0.ps, s1.p, s1.ps, w, bias, out.p,
+           out.ps, ctx->d_enc + ctx->el.tc_fin, ctx->d_enc + ctx->el.fin_b, fin_out, n_img, n_groups, tl);
 }
 
 template <class K>
@@ -372,6 +389,7 @@ int giga_ctx_create(giga_ctx** out, int device) {
   giga_ctx* ctx = new giga_ctx();
   ctx->device = device;
   ctx->timeline_layer = getenv("GIGA_TIMELINE");
+  if (const char* e = getenv("GIGA_PDL")) ctx->pdl = atoi(e) != 0;   // A/B switch (same as giga_ctx_set_option("pdl"))
   ctx->el = make_enc_layout();
   *out = ctx;
   return GIGA_OK;
@@ -616,11 +634,11 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
   const int n_img = 3 * B;
   {
     LaunchScope ls(ctx, "conv_in_planes", st);
-    conv_in_planes_kernel<<<dim3(CI_NT, B), CI_THREADS, CI_SMEM_BYTES, st>>>(tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+    launch_k(ctx, conv_in_planes_kernel, dim3(CI_NT, B), dim3(CI_THREADS), CI_SMEM_BYTES, st, tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
   }
   {
     LaunchScope ls(ctx, "xz_finish", st);
-    xz_finish_kernel<<<dim3(C, B), 256, 0, st>>>(ctx->d_xzpart, ctx->d_pre, B);
+    launch_k(ctx, xz_finish_kernel, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, ctx->d_pre, B);
   }
   float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"),
         *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),
@@ -640,20 +658,23 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
     const EncLayout& L = ctx->el;
     {
       LaunchScope ls(ctx, "nchw_to_tall:pre", st);
-      nchw_to_tall_kernel<40, 4><<<ceil_div(n_img * 4 * G2, 256), 256, 0, st>>>(ctx->d_pre, tb("pre").p, tb("pre").ps, n_img);
+      launch_k(ctx, nchw_to_tall_kernel<40, 4>, dim3(ceil_div(n_img * 4 * G2, 256)), dim3(256), 0, st, (const float*)ctx->d_pre, tb("pre").p,
+               tb("pre").ps, n_img);
     }
     {
       launch_persist<P_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st);
       launch_persist<P_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st);
       {
         LaunchScope ls(ctx, "maxpool:p0", st);
-        pool_tall_kernel<20, 4><<<ceil_div(n_img * 4 * 400, 256), 256, 0, st>>>(tb("d0c2").p, tb("d0c2").ps, tb("p0").p, tb("p0").ps, n_img);
+        launch_k(ctx, pool_tall_kernel<20, 4>, dim3(ceil_div(n_img * 4 * 400, 256)), dim3(256), 0, st, (const float*)tb("d0c2").p, tb("d0c2").ps,
+                 tb("p0").p, tb("p0").ps, n_img);
       }
       launch_persist<P_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st);
       launch_persist<P_c20>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st);
       {
         LaunchScope ls(ctx, "maxpool:p1", st);
-        pool_tall_kernel<10, 8><<<ceil_div(n_img * 8 * 100, 256), 256, 0, st>>>(tb("d1c2").p, tb("d1c2").ps, tb("p1").p, tb("p1").ps, n_img);
+        launch_k(ctx, pool_tall_kernel<10, 8>, dim3(ceil_div(n_img * 8 * 100, 256)), dim3(256), 0, st, (const float*)tb("d1c2").p, tb("d1c2").ps,
+                 tb("p1").p, tb("p1").ps, n_img);
       }
       launch_persist<P_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st);
       launch_persist<P_d2c2>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st);
@@ -714,8 +735,8 @@ int giga_decode(giga_ctx* ctx, const float* planes, int B, const float* points, 
         ctx->timeline_n = (long)n;
         tl = ctx->d_timeline;
       }
-      decode_points_tc_kernel<<<dim3(ceil_div(N, TD_PTS), B), TD_PTS, TD_SMEM_BYTES, st>>>(planes, points, ctx->d_heads_tc, B,
-                                                                                           N, heads, qual, rot, width, occ, tl);
+      launch_k(ctx, decode_points_tc_kernel, dim3(ceil_div(N, TD_PTS), B), dim3(TD_PTS), TD_SMEM_BYTES, st, planes, points,
+               (const float*)ctx->d_heads_tc, B, N, heads, qual, rot, width, occ, tl);
     }
     else
       decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N,
@@ -744,7 +765,7 @@ int giga_scene_argmax(giga_ctx* ctx, const float* qual, int B, int N, float* bes
   if (int r = set_device(ctx)) return r;
   {
     LaunchScope ls(ctx, "scene_argmax", (cudaStream_t)stream);
-    scene_argmax_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(qual, N, best_val, best_idx);
+    launch_k(ctx, scene_argmax_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, qual, N, best_val, best_idx);
   }
   CU_TRY(cudaGetLastError());
   return GIGA_OK;
@@ -1102,6 +1123,11 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "decoder_impl")) {
     if (value != 0 && value != 1) return fail(GIGA_EINVAL, "decoder_impl must be 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
     ctx->decoder_impl = value;
+    return GIGA_OK;
+  }
+  if (!strcmp(key, "pdl")) {
+    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "pdl must be 0 or 1");
+    ctx->pdl = value;
     return GIGA_OK;
   }
   if (!strcmp(key, "encoder_impl")) {

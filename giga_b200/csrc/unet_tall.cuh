@@ -74,6 +74,8 @@ __device__ __forceinline__ long tall_pos(int hw, int img, int y, int x) { return
 // grid: ceil(n_img*HW*HW*C8 / 256), block 256
 template <int HW, int C8>   // C8 = channels / 8
 __global__ void __launch_bounds__(256) nchw_to_tall_kernel(const float* __restrict__ src, float* __restrict__ dst, long ps, int n_img) {
+  pdl_launch();
+  pdl_wait();
   const long t = (long)blockIdx.x * 256 + threadIdx.x;
   const long total = (long)n_img * C8 * HW * HW;
   if (t >= total) return;
@@ -93,6 +95,8 @@ __global__ void __launch_bounds__(256) nchw_to_tall_kernel(const float* __restri
 
 template <int HW, int C8>
 __global__ void __launch_bounds__(256) tall_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, long ps, int n_img) {
+  pdl_launch();
+  pdl_wait();
   const long t = (long)blockIdx.x * 256 + threadIdx.x;
   const long total = (long)n_img * C8 * HW * HW;
   if (t >= total) return;
@@ -110,6 +114,8 @@ __global__ void __launch_bounds__(256) tall_to_nchw_kernel(const float* __restri
 // MaxPool2d(2,2) (unet.py:64): TALL(2*HW) -> TALL(HW) on the values the (hi, lo) pairs stand for
 template <int HW, int C8>   // HW = OUTPUT resolution
 __global__ void __launch_bounds__(256) pool_tall_kernel(const float* __restrict__ src, long ps_in, float* __restrict__ dst, long ps_out, int n_img) {
+  pdl_launch();
+  pdl_wait();
   const long t = (long)blockIdx.x * 256 + threadIdx.x;
   const long total = (long)n_img * C8 * HW * HW;
   if (t >= total) return;
@@ -260,6 +266,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
   const int n_items = n_groups * K::NNT;
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x + j*gridDim.x
 
+  pdl_launch();   // the next layer may start its prologue (barriers, TMEM, weights) as soon as SM resources free up
   if (warp == 4) tc::tmem_alloc(tmem_slot, P::TMEM_COLS);
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], P::NMMAW); }   // every MMA warp releases a stage
@@ -301,6 +308,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
       }
       __syncwarp();
     }
+    pdl_wait();   // activations of the previous layer(s) are complete and visible; weights / biases above are constants
 #pragma unroll 1
     for (int i = 0; i < total_chunks; ++i) {   // i = flat chunk index of this CTA
       const int s = i % S, j = i / NC, c = i - j * NC;
