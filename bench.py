@@ -344,6 +344,8 @@ def main():
                 fl = 2.0 * GRID3 * 27 * 32 * B
             elif name == "decode_points:grasp":
                 fl = 2.0 * (HEAD_MAC["qual"] + HEAD_MAC["rot"] + HEAD_MAC["width"]) * B * N
+            elif name == "decode_points:grasp+tsdf":
+                fl = 2.0 * sum(HEAD_MAC.values()) * B * N
             elif name == "decode_points:tsdf":
                 fl = 2.0 * HEAD_MAC["tsdf"] * B * N
             else:

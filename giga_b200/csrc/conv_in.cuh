@@ -39,7 +39,6 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
                       float* __restrict__ xz_part,   // [B][CI_NT][40 ix][32][40 iz]
                       int B, const __grid_constant__ ConvInParams P) {
   extern __shared__ __align__(16) float smem[];
-  pdl_launch();
   pdl_wait();
   float* red = smem;                // [32*TY][44]
   float* xyacc = red + CI_RED;      // [32*TY][44]  (col = ix)
@@ -79,6 +78,9 @@ conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
 
 #pragma unroll 1
   for (int ix = 0; ix < G; ++ix) {
+    // Let the next kernel become resident only when this one is nearly done: its CTAs' shared memory comes out of the
+    // L1 carve-out this kernel's TSDF reads live in (an early trigger costs tens of us per step).
+    if (ix == G - 3) pdl_launch();
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       win[0][t] = win[1][t];

@@ -119,14 +119,19 @@ __device__ __forceinline__ void store_a_row(uint8_t* a_hi, uint8_t* a_lo, int ro
   }
 }
 
-// grid (ceil(N/128), B), block 128, dynamic smem TD_SMEM_BYTES, 2 CTAs/SM (2 x 256 TMEM columns)
+// grid (ceil(N/128) + ceil(N2/128), B), block 128, dynamic smem TD_SMEM_BYTES, 2 CTAs/SM (2 x 256 TMEM columns).
+// Two jobs can share one launch (forward(): the grasp heads at p and the TSDF head at p_tsdf): tiles [0, tiles1) evaluate
+// `heads` at pts, the rest `heads2` at pts2 -- the long (3-head) tiles are scheduled first and the short ones fill the tail
+// instead of paying a second launch and a second partial wave.
 __global__ void __launch_bounds__(TD_PTS, 2)
 decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
                         const float* __restrict__ pts,     // [B][N][3]
                         const float* __restrict__ tw,      // [4][TW_HEAD]
                         int B, int N, unsigned heads,
                         float* __restrict__ qual, float* __restrict__ rot, float* __restrict__ width,
-                        float* __restrict__ occ, unsigned long long* __restrict__ tl) {   // tl: optional debug timeline
+                        float* __restrict__ occ,
+                        const float* __restrict__ pts2, int N2, unsigned heads2, int tiles1,   // second job (N2 = 0: none)
+                        unsigned long long* __restrict__ tl) {   // tl: optional debug timeline
   extern __shared__ __align__(128) uint8_t smem_tc[];
   uint8_t* smem = smem_tc;
   uint8_t* sAhi = smem;
@@ -141,7 +146,9 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TD_OFF_BAR + 40);
 
   const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * TD_PTS;
+  int tile = blockIdx.x;
+  if (tile >= tiles1) { tile -= tiles1; pts = pts2; N = N2; heads = heads2; }
+  const int n0 = tile * TD_PTS;
   const int n = n0 + tid;
   const bool valid = n < N;
   const int nc = valid ? n : N - 1;
@@ -157,7 +164,6 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
     ++tslot;
   };
   stamp();   // 0: start
-  pdl_launch();
   if (warp == 0) tc::tmem_alloc(tmem_slot, TD_TMEM_COLS);
   if (tid == 0) {
     tc::mbar_init(bar, 1); tc::mbar_init(&wbar[0], 1); tc::mbar_init(&wbar[1], 1); tc::mbar_init(pbar, 1); tc::mbar_init(bar3, 3);
@@ -204,6 +210,7 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   const float* pp = pts + ((size_t)b * N + nc) * 3;
   const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
   stamp();   // 1: gather done
+  pdl_launch();   // after the gather: the successor's CTAs take shared memory out of the L1 carve-out the gather reads through
 
   tc::fence_before_sync();
   __syncthreads();   // TMEM address + mbarrier init visible

@@ -137,6 +137,7 @@ struct giga_ctx {
   float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo tf32 splits)
   int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int pdl = 1;               // programmatic dependent launch between the fast-path kernels (1 = on)
+  int merge_decode = 1;      // giga_forward: grasp heads + TSDF head in one decoder launch
   int encoder_impl = 1;      // U-Net convs: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int last_impl = 0;
   int num_sms = 148;
@@ -389,7 +390,8 @@ int giga_ctx_create(giga_ctx** out, int device) {
   giga_ctx* ctx = new giga_ctx();
   ctx->device = device;
   ctx->timeline_layer = getenv("GIGA_TIMELINE");
-  if (const char* e = getenv("GIGA_PDL")) ctx->pdl = atoi(e) != 0;   // A/B switch (same as giga_ctx_set_option("pdl"))
+  if (const char* e = getenv("GIGA_PDL")) ctx->pdl = atoi(e) != 0;   // A/B switches (debug)
+  if (const char* e = getenv("GIGA_MERGE_DECODE")) ctx->merge_decode = atoi(e) != 0;
   ctx->el = make_enc_layout();
   *out = ctx;
   return GIGA_OK;
@@ -712,6 +714,42 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
   return GIGA_OK;
 }
 
+}  // extern "C" (re-opened below)
+
+namespace {
+
+// one decoder launch for up to two jobs (heads at points / heads2 at points2); validation is the callers' job
+int launch_decode(giga_ctx* ctx, const float* planes, int B, const float* points, int N, unsigned heads, const float* points2, int N2,
+                  unsigned heads2, float* qual, float* rot, float* width, float* occ, cudaStream_t st) {
+  const bool two = points2 && N2 > 0;
+  if (two && ctx->decoder_impl != 1) return fail(GIGA_EINVAL, "launch_decode: merged jobs need the tensor-core decoder");
+  const char* name = two ? "decode_points:grasp+tsdf" : ((heads & 15u) == GIGA_HEAD_TSDF ? "decode_points:tsdf" : "decode_points:grasp");
+  LaunchScope ls(ctx, name, st);
+  if (ctx->decoder_impl == 1) {
+    const int tiles1 = ceil_div(N, TD_PTS), tiles2 = two ? ceil_div(N2, TD_PTS) : 0;
+    unsigned long long* tl = nullptr;
+    if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, "decode")) {
+      const size_t n = (size_t)(tiles1 + tiles2) * B * 32;
+      if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+      cudaMalloc(&ctx->d_timeline, n * 8);
+      cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
+      ctx->timeline_n = (long)n;
+      tl = ctx->d_timeline;
+    }
+    launch_k(ctx, decode_points_tc_kernel, dim3(tiles1 + tiles2, B), dim3(TD_PTS), TD_SMEM_BYTES, st, planes, points,
+             (const float*)ctx->d_heads_tc, B, N, heads, qual, rot, width, occ, points2, two ? N2 : 0, heads2, tiles1, tl);
+  } else {
+    decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N, heads, qual, rot,
+                                                                                         width, occ);
+  }
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int giga_decode(giga_ctx* ctx, const float* planes, int B, const float* points, int N, unsigned heads, float* qual,
                 float* rot, float* width, float* occ, void* stream) {
   if (!ctx || !planes || !points || B <= 0 || N <= 0 || !(heads & 15u) || (heads & ~31u))
@@ -722,28 +760,7 @@ int giga_decode(giga_ctx* ctx, const float* planes, int B, const float* points, 
       ((heads & GIGA_HEAD_TSDF) && !occ))
     return fail(GIGA_EINVAL, "giga_decode: output pointer of a requested head is null");
   if (int r = set_device(ctx)) return r;
-  cudaStream_t st = (cudaStream_t)stream;
-  {
-    LaunchScope ls(ctx, (heads & 15u) == GIGA_HEAD_TSDF ? "decode_points:tsdf" : "decode_points:grasp", st);
-    if (ctx->decoder_impl == 1) {
-      unsigned long long* tl = nullptr;
-      if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, "decode")) {
-        const size_t n = (size_t)ceil_div(N, TD_PTS) * B * 32;
-        if (ctx->d_timeline) cudaFree(ctx->d_timeline);
-        cudaMalloc(&ctx->d_timeline, n * 8);
-        cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
-        ctx->timeline_n = (long)n;
-        tl = ctx->d_timeline;
-      }
-      launch_k(ctx, decode_points_tc_kernel, dim3(ceil_div(N, TD_PTS), B), dim3(TD_PTS), TD_SMEM_BYTES, st, planes, points,
-               (const float*)ctx->d_heads_tc, B, N, heads, qual, rot, width, occ, tl);
-    }
-    else
-      decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N,
-                                                                                           heads, qual, rot, width, occ);
-  }
-  CU_TRY(cudaGetLastError());
-  return GIGA_OK;
+  return launch_decode(ctx, planes, B, points, N, heads, nullptr, 0, 0u, qual, rot, width, occ, (cudaStream_t)stream);
 }
 
 int giga_sample_feature(giga_ctx* ctx, const float* planes, int B, const float* points, int N, int mode, float* out,
@@ -791,13 +808,19 @@ int giga_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, int Ng
     planes = ctx->d_planes;
   }
   if (int r = giga_encode(ctx, tsdf, B, planes, stream)) return r;
-  if (grasp) {
-    const unsigned hm = ctx->heads & (GIGA_HEAD_QUAL | GIGA_HEAD_ROT | GIGA_HEAD_WIDTH);
-    if (!hm) return fail(GIGA_ESTATE, "giga_forward: no grasp head committed (pass p = NULL for giga_geo)");
-    if (int r = giga_decode(ctx, planes, B, p, Ng, hm, qual, rot, width, nullptr, stream)) return r;
+  const unsigned hm = ctx->heads & (GIGA_HEAD_QUAL | GIGA_HEAD_ROT | GIGA_HEAD_WIDTH);
+  if (grasp && !hm) return fail(GIGA_ESTATE, "giga_forward: no grasp head committed (pass p = NULL for giga_geo)");
+  if (grasp && geo && ctx->decoder_impl == 1 && ctx->merge_decode) {   // both point sets in ONE launch (long 3-head tiles first, TSDF tiles fill the tail)
+    if (!(ctx->heads & GIGA_HEAD_TSDF)) return fail(GIGA_ESTATE, "giga_forward: no TSDF head committed");
+    if (!occ || ((hm & GIGA_HEAD_QUAL) && !qual) || ((hm & GIGA_HEAD_ROT) && !rot) || ((hm & GIGA_HEAD_WIDTH) && !width))
+      return fail(GIGA_EINVAL, "giga_forward: output pointer of a requested head is null");
+    if (int r = launch_decode(ctx, planes, B, p, Ng, hm, p_tsdf, No, GIGA_HEAD_TSDF, qual, rot, width, occ, (cudaStream_t)stream)) return r;
+  } else {
+    if (grasp)
+      if (int r = giga_decode(ctx, planes, B, p, Ng, hm, qual, rot, width, nullptr, stream)) return r;
+    if (geo)
+      if (int r = giga_decode(ctx, planes, B, p_tsdf, No, GIGA_HEAD_TSDF, nullptr, nullptr, nullptr, occ, stream)) return r;
   }
-  if (geo)
-    if (int r = giga_decode(ctx, planes, B, p_tsdf, No, GIGA_HEAD_TSDF, nullptr, nullptr, nullptr, occ, stream)) return r;
   if (best_val)
     if (int r = giga_scene_argmax(ctx, qual, B, Ng, best_val, best_idx, stream)) return r;
   return GIGA_OK;
@@ -837,13 +860,9 @@ int enqueue_host_request(giga_ctx* ctx, giga_ctx::HostSlot& s, const float* tsdf
     CU_TRY(cudaEventRecord(s.ev_in, sin));
     CU_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
   }
-  if (int r = giga_encode(ctx, s.tsdf, B, s.planes, sc)) return r;
-  if (grasp) {
-    const unsigned hm = ctx->heads & (GIGA_HEAD_QUAL | GIGA_HEAD_ROT | GIGA_HEAD_WIDTH);
-    if (int r = giga_decode(ctx, s.planes, B, s.p, Ng, hm, s.qual, s.rot, s.width, nullptr, sc)) return r;
-  }
-  if (geo)
-    if (int r = giga_decode(ctx, s.planes, B, s.pt, No, GIGA_HEAD_TSDF, nullptr, nullptr, nullptr, s.occ, sc)) return r;
+  if (int r = giga_forward(ctx, s.tsdf, B, grasp ? s.p : nullptr, Ng, geo ? s.pt : nullptr, No, s.planes, s.qual, s.rot, s.width, s.occ, nullptr,
+                           nullptr, sc))
+    return r;
   if (sc != sout) {
     CU_TRY(cudaEventRecord(s.ev_compute, sc));
     CU_TRY(cudaStreamWaitEvent(sout, s.ev_compute, 0));
