@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstdint>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <cuda_fp16.h>
 #include <map>
@@ -138,6 +139,7 @@ struct giga_ctx {
   int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int pdl = 1;               // programmatic dependent launch between the fast-path kernels (1 = on)
   int merge_decode = 1;      // giga_forward: grasp heads + TSDF head in one decoder launch
+  int conv_in_split = 1;     // conv_in: output channels split over this many CTAs (1 or 2) at B >= 8 (2 measured 5 % slower)
   int encoder_impl = 1;      // U-Net convs: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int last_impl = 0;
   int num_sms = 148;
@@ -232,7 +234,7 @@ void launch_k(const giga_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 blo
 
 int ensure_attrs(giga_ctx* ctx) {
   if (ctx->attrs_set) return GIGA_OK;
-  CU_TRY(cudaFuncSetAttribute(conv_in_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CI_SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(conv_in_planes_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvInCfg<5, 1>::SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(sample_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
@@ -260,7 +262,11 @@ int ensure_workspace(giga_ctx* ctx, int B) {
   ctx->d_pre = ctx->d_xzpart = nullptr;
   ctx->cap_B = 0;
   CU_TRY(cudaMalloc(&ctx->d_pre, sizeof(float) * 3 * (size_t)B * C * G2));
-  CU_TRY(cudaMalloc(&ctx->d_xzpart, sizeof(float) * (size_t)B * CI_NT * G * C * G));
+  {
+    size_t units = 0;   // partial slabs: a later call with a smaller batch may use the finer tiling
+    for (int bb = 1; bb <= B; ++bb) units = std::max(units, (size_t)bb * (G / conv_in_ty(bb)));
+    CU_TRY(cudaMalloc(&ctx->d_xzpart, sizeof(float) * units * G * C * G));
+  }
   for (int i = 0; i < kNumActs; ++i)
     CU_TRY(cudaMalloc(&ctx->d_act[i], sizeof(float) * 3 * (size_t)B * kActs[i].ch * kActs[i].hw * kActs[i].hw));
   for (int i = 0; i <= kNumActs; ++i) {   // zero-initialised once: padding positions are never written
@@ -392,6 +398,7 @@ int giga_ctx_create(giga_ctx** out, int device) {
   ctx->timeline_layer = getenv("GIGA_TIMELINE");
   if (const char* e = getenv("GIGA_PDL")) ctx->pdl = atoi(e) != 0;   // A/B switches (debug)
   if (const char* e = getenv("GIGA_MERGE_DECODE")) ctx->merge_decode = atoi(e) != 0;
+  if (const char* e = getenv("GIGA_CONV_IN_SPLIT")) ctx->conv_in_split = atoi(e) == 2 ? 2 : 1;
   ctx->el = make_enc_layout();
   *out = ctx;
   return GIGA_OK;
@@ -636,11 +643,21 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
   const int n_img = 3 * B;
   {
     LaunchScope ls(ctx, "conv_in_planes", st);
-    launch_k(ctx, conv_in_planes_kernel, dim3(CI_NT, B), dim3(CI_THREADS), CI_SMEM_BYTES, st, tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+    if (conv_in_ty(B) == 1) {
+      using Cf = ConvInCfg<1, 4>;
+      launch_k(ctx, conv_in_planes_kernel<1, 4>, dim3(Cf::NT, B, 4), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+    } else if (ctx->conv_in_split == 2) {
+      using Cf = ConvInCfg<5, 2>;
+      launch_k(ctx, conv_in_planes_kernel<5, 2>, dim3(Cf::NT, B, 2), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+    } else {
+      using Cf = ConvInCfg<5, 1>;
+      launch_k(ctx, conv_in_planes_kernel<5, 1>, dim3(Cf::NT, B, 1), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+    }
   }
   {
     LaunchScope ls(ctx, "xz_finish", st);
-    launch_k(ctx, xz_finish_kernel, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, ctx->d_pre, B);
+    if (conv_in_ty(B) == 5) launch_k(ctx, xz_finish_kernel<G / 5>, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, ctx->d_pre, B);
+    else launch_k(ctx, xz_finish_kernel<G>, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, ctx->d_pre, B);
   }
   float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"),
         *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),

@@ -361,3 +361,19 @@ def test_single_call_forward_equals_staged_calls(net, oracle_sd):
         other.decoder_width.fc_out.bias = torch.nn.Parameter(other.decoder_width.fc_out.bias.detach() + 2.0)   # new Parameter object
         moved = other(xd, pd)
     assert torch.allclose(moved[2], base[2] + 2.0, atol=1e-6) and torch.equal(moved[0], base[0])
+
+
+def test_batch_invariance_across_tilings(net):
+    """A scene's outputs do not depend on the batch it is evaluated in -- including across the conv_in tiling switch
+    (B < 8: 40 CTAs per scene, B >= 8: 8 CTAs per scene; the xz sum keeps one canonical order)."""
+    x, p, pt = O.seeded_inputs(9, 130, seed=81)
+    xd, pd, ptd = x.to(DEV), p.to(DEV), pt.to(DEV)
+    with torch.no_grad():
+        full = net(xd, pd, p_tsdf=ptd)
+        pre9 = net.encode_inputs(xd) and net.debug_activation("pre", 9)
+        for sl in (slice(0, 1), slice(2, 5), slice(0, 8), slice(8, 9)):
+            part = net(xd[sl], pd[sl], p_tsdf=ptd[sl])
+            for a, b in zip(full, part):
+                assert torch.equal(a[sl], b)
+        net.encode_inputs(xd[4:5])
+        assert torch.equal(net.debug_activation("pre", 1), pre9[:, 4:5])
