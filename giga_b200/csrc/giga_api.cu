@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "conv_in.cuh"
+#include "conv_in_tc.cuh"
 #include "decoder.cuh"
 #include "decoder_tc.cuh"
 #include "planner.cuh"
@@ -91,6 +92,7 @@ struct EncLayout {
   long tc_conv[10];  // tensor-core operand-layout weights (hi/lo fp16 splits) per conv layer
   long tc_up[2];     // transpose convs, [ab][chunk][kc][hi|lo][co][8 halfs]
   long tc_fin;       // conv_final as a 32x32 B operand [hi,lo][kc 4][n 32][8 halfs]
+  long tc_cin;       // conv_in B operands [dx 3][mma 2][kc 2][n 64][8 halfs] + 2^-s (conv_in_tc.cuh)
   long total;
 };
 const int kConvCin[10] = {32, 32, 32, 64, 64, 128, 128, 64, 64, 32};
@@ -112,6 +114,7 @@ EncLayout make_enc_layout() {
   for (int i = 0; i < 10; ++i) { L.tc_conv[i] = o; o += (long)kConvCin[i] * kConvCout[i] * 9; }
   for (int i = 0; i < 2; ++i) { L.tc_up[i] = o; o += (long)kUpCin[i] * kUpCout[i] * 4; }
   L.tc_fin = o; o += 1024;
+  L.tc_cin = o; o += CT_W_WORDS;
   L.total = o;
   return L;
 }
@@ -138,6 +141,7 @@ struct giga_ctx {
   float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo tf32 splits)
   int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int pdl = 1;               // programmatic dependent launch between the fast-path kernels (1 = on)
+  int conv_in_impl = 0;      // fused Conv3d + plane means: 0 = fp32 FMA pipe (default), 1 = tcgen05 variant (parity-clean; shared-memory bound, not faster yet: DESIGN.md 5)
   int merge_decode = 1;      // giga_forward: grasp heads + TSDF head in one decoder launch
   int conv_in_split = 1;     // conv_in: output channels split over this many CTAs (1 or 2) at B >= 8 (2 measured 5 % slower)
   int encoder_impl = 1;      // U-Net convs: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
@@ -150,6 +154,7 @@ struct giga_ctx {
   int cap_B = 0;
   int last_B = 0;
   float* d_pre = nullptr;      // [3][B][32][1600]
+  float* d_elem = nullptr;     // conv_in_tc voxel elements [B][42][42][40] x 16 B (+ tail), padding zeroed once
   float* d_xzpart = nullptr;   // [B][CI_NT][40][32][40]
   float* d_planes = nullptr;   // [3][B][40][40][32] plane features of giga_forward calls that pass planes = NULL
   int planes_cap = 0;
@@ -235,6 +240,13 @@ void launch_k(const giga_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 blo
 int ensure_attrs(giga_ctx* ctx) {
   if (ctx->attrs_set) return GIGA_OK;
   CU_TRY(cudaFuncSetAttribute(conv_in_planes_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvInCfg<5, 1>::SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 4 CTAs / SM
+  {
+    int nb = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_in_tc_kernel, CT_THREADS, CT_SMEM_BYTES));
+    if (getenv("GIGA_VERBOSE")) fprintf(stderr, "[giga] conv_in_tc occupancy: %d CTAs/SM\n", nb);
+  }
   CU_TRY(cudaFuncSetAttribute(decode_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(sample_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
@@ -262,8 +274,12 @@ int ensure_workspace(giga_ctx* ctx, int B) {
   ctx->d_pre = ctx->d_xzpart = nullptr;
   ctx->cap_B = 0;
   CU_TRY(cudaMalloc(&ctx->d_pre, sizeof(float) * 3 * (size_t)B * C * G2));
+  if (ctx->d_elem) cudaFree(ctx->d_elem);
+  ctx->d_elem = nullptr;
+  CU_TRY(cudaMalloc(&ctx->d_elem, sizeof(float) * (size_t)ct_element_words(B)));
+  CU_TRY(cudaMemset(ctx->d_elem, 0, sizeof(float) * (size_t)ct_element_words(B)));
   {
-    size_t units = 0;   // partial slabs: a later call with a smaller batch may use the finer tiling
+    size_t units = (size_t)B * CT_NT;   // partial slabs: a later call with a smaller batch may use the finer FMA tiling
     for (int bb = 1; bb <= B; ++bb) units = std::max(units, (size_t)bb * (G / conv_in_ty(bb)));
     CU_TRY(cudaMalloc(&ctx->d_xzpart, sizeof(float) * units * G * C * G));
   }
@@ -398,6 +414,7 @@ int giga_ctx_create(giga_ctx** out, int device) {
   ctx->timeline_layer = getenv("GIGA_TIMELINE");
   if (const char* e = getenv("GIGA_PDL")) ctx->pdl = atoi(e) != 0;   // A/B switches (debug)
   if (const char* e = getenv("GIGA_MERGE_DECODE")) ctx->merge_decode = atoi(e) != 0;
+  if (const char* e = getenv("GIGA_CONV_IN_IMPL")) ctx->conv_in_impl = atoi(e) != 0;
   if (const char* e = getenv("GIGA_CONV_IN_SPLIT")) ctx->conv_in_split = atoi(e) == 2 ? 2 : 1;
   ctx->el = make_enc_layout();
   *out = ctx;
@@ -408,7 +425,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_planes};
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_planes, ctx->d_elem};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : ctx->slot) {
@@ -465,6 +482,36 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       (&ctx->conv_in.b[0].x)[c] = b[c];
     }
     std::vector<float> blob(ctx->el.total, 0.f);
+    {   // conv_in_tc B operands: weights and bias pre-scaled by 2^s, fp16 hi/lo, [dx 3][mma 2][kc 2][n 64][8 halfs]
+      float wmax = 0.f;
+      for (int e = 0; e < 32 * 27; ++e) wmax = fmaxf(wmax, fabsf(w[e]));
+      for (int e = 0; e < 32; ++e) wmax = fmaxf(wmax, fabsf(b[e]));
+      int sexp = 0;
+      if (wmax > 0.f && std::isfinite(wmax)) {
+        int e;
+        frexpf(wmax, &e);
+        sexp = std::min(24, std::max(-14, 10 - e));
+      }
+      const float wscale = ldexpf(1.f, sexp);
+      uint16_t* Wt = reinterpret_cast<uint16_t*>(blob.data() + ctx->el.tc_cin);
+      for (int dx = 0; dx < 3; ++dx)
+        for (int m = 0; m < 2; ++m)
+          for (int kc = 0; kc < 2; ++kc) {
+            const int dy = m == 0 ? kc : (kc == 0 ? -1 : 2);     // MMA 1's first k-chunk re-reads line dy 1 with zero weights
+            if (dy < 0) continue;
+            for (int n = 0; n < 64; ++n)
+              for (int j = 0; j < 8; ++j) {
+                const int c = n & 31;
+                float v = 0.f;
+                if (j < 6) v = w[c * 27 + dx * 9 + dy * 3 + (j % 3)] * wscale;   // slots 0-2: x hi, 3-5: x lo; same weight
+                else if (j == 6 && dx == 1 && dy == 1) v = b[c] * wscale;          // the element's constant 1 carries the bias
+                uint16_t hi, lo;
+                split_half_host(v, hi, lo, 1.f);
+                Wt[((((dx * 2 + m) * 2 + kc) * 64) + n) * 8 + j] = n < 32 ? hi : lo;
+              }
+          }
+      blob[ctx->el.tc_cin + CT_B_BYTES / 4] = ldexpf(1.f, -sexp);
+    }
     for (int i = 0; i < 10; ++i) {
       const int ci = kConvCin[i], co = kConvCout[i];
       std::string base = std::string("encoder.unet.") + kConvName[i];
@@ -641,7 +688,32 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
   if (int r = ensure_workspace(ctx, B)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_img = 3 * B;
-  {
+  if (ctx->conv_in_impl == 1) {
+    {
+      LaunchScope ls(ctx, "conv_in:elements", st);
+      launch_k(ctx, tsdf_elements_kernel, dim3(ceil_div(B * G3, 256)), dim3(256), 0, st, tsdf, ctx->d_elem, B);
+    }
+    {
+      unsigned long long* tl = nullptr;
+      if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, "conv_in_tc")) {   // debug: per-CTA stall accounting
+        const size_t n = (size_t)CT_NT * B * 32;
+        if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+        cudaMalloc(&ctx->d_timeline, n * 8);
+        cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
+        ctx->timeline_n = (long)n;
+        tl = ctx->d_timeline;
+      }
+      LaunchScope ls(ctx, "conv_in_tc", st);
+      launch_k(ctx, conv_in_tc_kernel, dim3(CT_NT, B), dim3(CT_THREADS), CT_SMEM_BYTES, st, (const float*)ctx->d_elem,
+               (const float*)(ctx->d_enc + ctx->el.tc_cin), ctx->d_pre, ctx->d_xzpart, B, tl);
+    }
+    {
+      LaunchScope ls(ctx, "xz_finish", st);
+      launch_k(ctx, xz_finish_tc_kernel, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, (const float*)(ctx->d_enc + ctx->el.tc_cin),
+               ctx->d_pre, B);
+    }
+  } else {
+    {
     LaunchScope ls(ctx, "conv_in_planes", st);
     if (conv_in_ty(B) == 1) {
       using Cf = ConvInCfg<1, 4>;
@@ -658,6 +730,7 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
     LaunchScope ls(ctx, "xz_finish", st);
     if (conv_in_ty(B) == 5) launch_k(ctx, xz_finish_kernel<G / 5>, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, ctx->d_pre, B);
     else launch_k(ctx, xz_finish_kernel<G>, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, ctx->d_pre, B);
+  }
   }
   float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"),
         *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),
@@ -1159,6 +1232,11 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "decoder_impl")) {
     if (value != 0 && value != 1) return fail(GIGA_EINVAL, "decoder_impl must be 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
     ctx->decoder_impl = value;
+    return GIGA_OK;
+  }
+  if (!strcmp(key, "conv_in_impl")) {
+    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "conv_in_impl must be 0 (fp32 FMA pipe) or 1 (tcgen05 3xFP16)");
+    ctx->conv_in_impl = value;
     return GIGA_OK;
   }
   if (!strcmp(key, "pdl")) {

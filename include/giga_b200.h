@@ -171,6 +171,8 @@ long giga_ctx_launch_count(const giga_ctx *ctx);
 /* implementation switches (A/B testing; defaults are the fastest parity-clean variants):
  *   "decoder_impl": 1 = tcgen05 tensor cores with 3xFP16 operand splitting (default), 0 = fp32 FMA pipe
  *   "encoder_impl": U-Net convolutions: 1 = tcgen05 3xFP16 with persistent CTAs (default), 0 = fp32 FMA pipe
+ *   "conv_in_impl": fused Conv3d + plane means: 0 = fp32 FMA pipe (default), 1 = tcgen05 3xFP16 variant (same parity bar;
+ *                   shared-memory-bandwidth bound, currently not faster)
  *   "pdl":          1 = programmatic dependent launch between the fast-path kernels (default), 0 = plain stream order */
 int giga_ctx_set_option(giga_ctx *ctx, const char *key, int value);
 /* per-kernel device timing for the roofline report: when enabled every kernel launch is bracketed

@@ -377,3 +377,20 @@ def test_batch_invariance_across_tilings(net):
                 assert torch.equal(a[sl], b)
         net.encode_inputs(xd[4:5])
         assert torch.equal(net.debug_activation("pre", 1), pre9[:, 4:5])
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_conv_in_implementations(oracle_sd, impl):
+    """conv_in_impl 1 = tcgen05 Conv3d + plane means (default; dz taps folded into 16-byte voxel elements, (dx,dy) taps as
+    descriptor shifts), 0 = fp32 FMA pipe: pre-U-Net planes within 1e-5, outputs within 1e-4, for both conv_in tilings."""
+    net = make_net("giga", oracle_sd)
+    net._engine().set_option("conv_in_impl", impl)
+    for B, seed in ((1, 1), (3, 2), (9, 3)):
+        x, p, pt = O.seeded_inputs(B, 64, seed=60 + seed)
+        with torch.no_grad():
+            pre = O.plane_features_pre_unet(oracle_sd, x)
+            ref = O.forward(oracle_sd, x, p, pt)
+            out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+            _close(net.debug_activation("pre", B), torch.stack([pre[k] for k in O.PLANES]), tol=1e-5, name=f"pre(impl{impl})")
+        for nme, a, b in zip(("qual", "rot", "width", "occ"), out, ref):
+            _close(a, b, name=f"cin{impl}.{nme}")
