@@ -83,6 +83,36 @@ def sharded_best_grasp(score_fn: Callable[[torch.Tensor, torch.Tensor], Tuple[to
     return gather_scene_best(v.float(), i.to(torch.int32), n, group=group)
 
 
+class SceneBestBuffer:
+    """The all-gather buffer of the final grasp-score reduction, packed so that ONE collective moves both fields:
+    buf[world][2][m] float32 with row 0 = best quality and row 1 = the arg-max index (int32 bits).  `val` / `idx` are
+    this rank's contiguous slices -- giga_scene_argmax (or giga_forward's fused arg-max) writes straight into them --
+    and gather() is a single in-place NCCL all-gather (8 bytes per scene)."""
+
+    def __init__(self, n_local_max: int, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.buf = torch.zeros((self.world, 2, n_local_max), dtype=torch.float32, device=device)
+
+    @property
+    def val(self) -> torch.Tensor:
+        return self.buf[self.rank, 0]
+
+    @property
+    def idx(self) -> torch.Tensor:
+        return self.buf[self.rank, 1].view(torch.int32)
+
+    def gather(self):
+        """-> (val (world, m) float32, idx (world, m) int32), identical on every rank."""
+        if self.world > 1:
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_gather_into_tensor(self.buf, self.buf[self.rank], group=self.group)   # in place: send = own slice
+            else:  # gloo (CPU tests): list form, no aliasing
+                dist.all_gather(list(self.buf.unbind(0)), self.buf[self.rank].clone(), group=self.group)
+        return self.buf[:, 0], self.buf[:, 1].view(torch.int32)
+
+
 class GigaScorer:
     """score_fn for the CUDA model: forward of the grasp heads + the fused per-scene arg-max kernel."""
 

@@ -57,6 +57,16 @@ def _worker(rank, world, port, n_scenes, out):
             ok = False
         except ValueError:
             pass
+        # packed single-collective buffer (what bench.py / the serving loop use): every rank fills its own slice
+        m = sharding.max_shard(n_scenes, world)
+        best = sharding.SceneBestBuffer(m, "cpu")
+        s0, e0 = sharding.shard_range(n_scenes, rank, world)
+        best.val[: e0 - s0] = rv[s0:e0]
+        best.idx[: e0 - s0] = ri[s0:e0]
+        gv, gi = best.gather()
+        for r in range(world):
+            rs, re = sharding.shard_range(n_scenes, r, world)
+            ok = ok and torch.equal(gv[r, : re - rs], rv[rs:re]) and torch.equal(gi[r, : re - rs], ri[rs:re])
         out[rank] = int(ok)
     finally:
         dist.destroy_process_group()

@@ -12,15 +12,23 @@ def unit_scale(u):
 
 
 def bench_name(kname, order):
+    """bench.py's kernel name for an ncu kernel name (launch order within one step for the repeated kernels)."""
     if "conv_in_planes" in kname: return "conv_in_planes"
     if "conv_in_tc" in kname: return "conv_in_tc"
-    if "yz_finish" in kname: return "yz_finish"
+    if "tsdf_elements" in kname: return "conv_in:elements"
     if "xz_finish" in kname: return "xz_finish"
     if "nchw_to_tall" in kname: return "nchw_to_tall:pre"
     if "scene_argmax" in kname: return "scene_argmax"
-    if "decode_points" in kname:
-        order["dec"] = order.get("dec", 0) + 1
-        return "decode_points:grasp" if order["dec"] % 2 == 1 else "decode_points:tsdf"
+    if "pool_tall" in kname:
+        order["pool"] = order.get("pool", 0) + 1
+        return "maxpool:p0" if order["pool"] % 2 == 1 else "maxpool:p1"
+    if "conv_tall_persistent" in kname:
+        names = ["conv3x3:d0c1", "conv3x3:d0c2", "conv3x3:d1c1", "conv3x3:d1c2", "conv3x3:d2c1", "conv3x3:d2c2", "convT:u0", "conv3x3:u0c1",
+                 "conv3x3:u0c2", "convT:u1", "conv3x3:u1c1", "conv3x3:u1c2+final"]
+        i = order.get("conv", 0)
+        order["conv"] = i + 1
+        return names[i % 12]
+    if "decode_points" in kname: return "decode_points:grasp+tsdf"
     return None
 
 
