@@ -245,8 +245,10 @@ class _GigaBase(nn.Module):
         self.__dict__["_train_bridge"] = bool(enabled)
         return self
 
-    def _bridge_active(self) -> bool:
-        return bool(self.__dict__.get("_train_bridge")) and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+    def _bridge_active(self, *inputs) -> bool:
+        if not (bool(self.__dict__.get("_train_bridge")) and torch.is_grad_enabled()):
+            return False
+        return any(p.requires_grad for p in self.parameters()) or any(t is not None and t.requires_grad for t in inputs)
 
     @property
     def gpu_launches(self) -> int:
@@ -478,7 +480,7 @@ class ConvolutionalOccupancyNetwork(_GigaBase):
 
     def forward(self, inputs, p, p_tsdf=None, sample=True, **kwargs):
         """models/__init__.py:42-67"""
-        if self._bridge_active():
+        if self._bridge_active(p):
             from .training import bridged_forward
             eng = self._engine()
             return bridged_forward(self, _prep(inputs, eng.device), _prep(p, eng.device),
@@ -502,8 +504,33 @@ class ConvolutionalOccupancyNetwork(_GigaBase):
                            "same failure as the reference for GIGA configs")
 
     def grad_refine(self, x, pos, bound_value=0.0125, lr=1e-6, num_step=1):
-        """models/__init__.py:136-164 needs d(qual)/d(pos); not called by any shipped script."""
-        raise NotImplementedError("grad_refine needs the position gradient of the fused decoder (not built yet)")
+        """models/__init__.py:136-164: SGD on the query positions to raise the predicted quality (not called by any
+        shipped script).  Forward values come from the CUDA library; d(qual)/d(pos) comes from the training bridge's
+        PyTorch recompute on the GPU (giga_b200/training.py) until the native backward kernels exist."""
+        was = bool(self.__dict__.get("_train_bridge"))
+        self.enable_training_bridge(True)
+        try:
+            pos_tmp = pos.clone()
+            l_bound = pos - bound_value
+            u_bound = pos + bound_value
+            pos_tmp.requires_grad = True
+            optimizer = torch.optim.SGD([pos_tmp], lr=lr)
+            self.eval()
+            with torch.enable_grad():
+                for _ in range(num_step):
+                    optimizer.zero_grad()
+                    qual_out, _, _ = self.forward(x, pos_tmp)
+                    loss = -qual_out.sum()
+                    loss.backward()
+                    optimizer.step()
+            for prm in self.parameters():   # the reference leaves parameter gradients behind as well; drop ours
+                prm.grad = None
+            with torch.no_grad():
+                pos_tmp = torch.maximum(torch.minimum(pos_tmp, u_bound), l_bound)
+                qual_out, rot_out, width_out = self.forward(x, pos_tmp)
+        finally:
+            self.enable_training_bridge(was)
+        return qual_out, pos_tmp, rot_out, width_out
 
 
 class ConvolutionalOccupancyNetworkGeometry(_GigaBase):

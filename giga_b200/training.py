@@ -100,6 +100,7 @@ class _Bridge(torch.autograd.Function):
         with torch.no_grad():
             outs = net._forward_native(x, p, p_tsdf)
         ctx.net, ctx.names, ctx.has_tsdf = net, names, p_tsdf is not None
+        ctx.p_grad = bool(p.requires_grad)
         ctx.save_for_backward(x, p, p_tsdf if p_tsdf is not None else x.new_empty(0), *params)
         return tuple(outs)
 
@@ -120,10 +121,13 @@ class _Bridge(torch.autograd.Function):
     @staticmethod
     def _backward_impl(ctx, leaves, sd, x, p, pt, grads):
         with torch.enable_grad():
-            outs = _forward_torch(sd, x, p, pt if ctx.has_tsdf else None, getattr(ctx.net, "detach_tsdf", False), hasattr(ctx.net, "decoder_qual"))
+            p_leaf = p.detach().requires_grad_(True) if ctx.p_grad else p      # grad_refine differentiates w.r.t. the query positions
+            outs = _forward_torch(sd, x, p_leaf, pt if ctx.has_tsdf else None, getattr(ctx.net, "detach_tsdf", False), hasattr(ctx.net, "decoder_qual"))
             pairs = [(o, g) for o, g in zip(outs, grads) if g is not None]
-            gp = torch.autograd.grad([o for o, _ in pairs], leaves, [g for _, g in pairs], allow_unused=True)
-        return (None, None, None, None, None) + tuple(gp)
+            wrt = list(leaves) + ([p_leaf] if ctx.p_grad else [])
+            gp = torch.autograd.grad([o for o, _ in pairs], wrt, [g for _, g in pairs], allow_unused=True)
+        gpos = gp[-1] if ctx.p_grad else None
+        return (None, None, gpos, None, None) + tuple(gp[:len(leaves)])
 
 
 def bridged_forward(net, x, p, p_tsdf):

@@ -394,3 +394,62 @@ def test_conv_in_implementations(oracle_sd, impl):
             _close(net.debug_activation("pre", B), torch.stack([pre[k] for k in O.PLANES]), tol=1e-5, name=f"pre(impl{impl})")
         for nme, a, b in zip(("qual", "rot", "width", "occ"), out, ref):
             _close(a, b, name=f"cin{impl}.{nme}")
+
+
+def test_other_baseline_configs(net, oracle_sd):
+    """BASELINE.json configs[2] (4096 grasp + 4096 occupancy points per scene, 32 scenes per GPU) and configs[4]
+    (64,000-point dense occupancy sweep, TSDF head only) at full size: oracle comparison on a subset of scenes (the CPU
+    oracle takes seconds per scene at these sizes) plus the size-independent properties on the whole batch."""
+    from oracle import planner_oracle as P
+    # ---- C3: B=32, 4096 + 4096 points, 4 heads ----
+    B, N = 32, 4096
+    x, p, pt = O.seeded_inputs(B, N, seed=91)
+    xd, pd, ptd = x.to(DEV), p.to(DEV), pt.to(DEV)
+    with torch.no_grad():
+        out = net(xd, pd, p_tsdf=ptd)
+        sub = [0, 13, 31]
+        ref = O.forward(oracle_sd, x[sub], p[sub], pt[sub])
+        for nme, a, b in zip(("qual", "rot", "width", "occ"), out, ref):
+            _close(a[sub], b, name=f"C3.{nme}")
+        assert torch.equal(out[0][sub].argmax(1).cpu(), ref[0].argmax(1))
+        lo, hi = net(xd[:11], pd[:11], p_tsdf=ptd[:11]), net(xd[11:], pd[11:], p_tsdf=ptd[11:])   # uneven shards
+        for a, l, h in zip(out, lo, hi):
+            assert torch.equal(a, torch.cat([l, h]))
+        assert all(torch.isfinite(o).all() for o in out)
+        assert ((out[1].norm(dim=2) - 1).abs() < 1e-5).all()
+    # ---- C5: dense occupancy sweep on the planner's 40^3 lattice, TSDF head only (infer_geo / giga_geo) ----
+    lattice = P.lattice_positions()                                     # (1, 64000, 3)
+    x5, _, _ = O.seeded_inputs(2, 8, seed=92)
+    pts5 = lattice.expand(2, -1, -1).contiguous()
+    with torch.no_grad():
+        occ = net.infer_geo(x5.to(DEV), pts5.to(DEV))
+        ref5 = O.infer_geo(oracle_sd, x5, pts5)
+        _close(occ, ref5, name="C5.occ")
+        geo = make_net("giga_geo", oracle_sd)
+        assert torch.equal(geo(x5.to(DEV), pts5.to(DEV), pts5.to(DEV)), occ)    # the geometry-only model runs the same kernels
+        # the three grasp heads on the same lattice (what VGNImplicit.predict evaluates)
+        q, r, w = net(x5[:1].to(DEV), lattice.to(DEV))
+        rq, rr, rw = O.forward(oracle_sd, x5[:1], lattice)
+        _close(q, rq, name="sim.qual"); _close(r, rr, name="sim.rot"); _close(w, rw, name="sim.width")
+        assert torch.equal(q.argmax(1).cpu(), rq.argmax(1))
+
+
+def test_grad_refine_matches_reference_semantics(oracle_sd):
+    """models/__init__.py:136-164: one SGD step on the query positions through d(qual)/d(pos), clamped to +-bound."""
+    net = make_net("giga", oracle_sd)
+    x, p, _ = O.seeded_inputs(2, 50, seed=95)
+    p = p * 0.8                                       # keep the +-bound box inside the cube
+    lr, bound = 1e-3, 0.0125
+    # reference semantics on the CPU oracle with autograd
+    pos = p.clone().requires_grad_(True)
+    sd = {k: v.clone() for k, v in oracle_sd.items()}
+    q = O.forward(sd, x, pos)[0]
+    (-q.sum()).backward()
+    ref_pos = torch.maximum(torch.minimum(p - lr * pos.grad, p + bound), p - bound)
+    with torch.no_grad():
+        ref_q, ref_r, ref_w = O.forward(sd, x, ref_pos)
+    qual, pos_new, rot, width = net.grad_refine(x.to(DEV), p.to(DEV), bound_value=bound, lr=lr, num_step=1)
+    assert (pos_new.cpu() - ref_pos).abs().max().item() < 1e-5
+    assert ((pos_new.cpu() - p).abs() <= bound + 1e-7).all()
+    _close(qual, ref_q, name="refine.qual"); _close(rot, ref_r, name="refine.rot"); _close(width, ref_w, name="refine.width")
+    assert not net.__dict__.get("_train_bridge") and all(prm.grad is None for prm in net.parameters())
