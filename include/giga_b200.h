@@ -161,7 +161,9 @@ int giga_ctx_set_lattice(giga_ctx *ctx, const float *pos, int N);
 int giga_detect(giga_ctx *ctx, const float *tsdf, const float *tsdf_process, int B, const giga_select_params *prm, int K,
                 int *count, float *score, int *index, float *out_rot, float *out_width, void *stream);
 /* same with HOST buffers in and out (H2D of the TSDFs, giga_detect, D2H of B*(1 + 7K) words); returns
- * after the stream has drained.  This is the call a simulation loop makes per planning step. */
+ * after the stream has drained.  This is the call a simulation loop makes per planning step: inputs and results are
+ * staged through pinned buffers owned by the ctx, and repeated calls of one configuration (B, K, parameters) replay a
+ * captured CUDA graph (one launch instead of ~25 API calls). */
 int giga_detect_host(giga_ctx *ctx, const float *tsdf, const float *tsdf_process, int B, const giga_select_params *prm, int K,
                      int *count, float *score, int *index, float *out_rot, float *out_width, void *stream);
 
@@ -173,6 +175,8 @@ long giga_ctx_launch_count(const giga_ctx *ctx);
  *   "encoder_impl": U-Net convolutions: 1 = tcgen05 3xFP16 with persistent CTAs (default), 0 = fp32 FMA pipe
  *   "conv_in_impl": fused Conv3d + plane means: 0 = fp32 FMA pipe (default), 1 = tcgen05 3xFP16 variant (same parity bar;
  *                   shared-memory-bandwidth bound, currently not faster)
+ *   "graph":        1 = giga_detect_host replays a captured CUDA graph of the whole call from its third invocation of a
+ *                   configuration on (default), 0 = always enqueue kernel by kernel
  *   "pdl":          1 = programmatic dependent launch between the fast-path kernels (default), 0 = plain stream order */
 int giga_ctx_set_option(giga_ctx *ctx, const char *key, int value);
 /* per-kernel device timing for the roofline report: when enabled every kernel launch is bracketed

@@ -151,3 +151,32 @@ def test_detect_host_batch_equals_single_scenes(net):
     # K too small: the wrapper re-runs with K = count
     c3, s3, i3, _, _ = detect_host(net, tsdfs, None, select_params(), K=1)
     assert s3.shape[1] >= int(c3.max())
+
+
+def test_detect_graph_replay_equals_eager(net):
+    """giga_detect_host replays a captured CUDA graph from the third call of a configuration on; results must be the bits
+    of the kernel-by-kernel path, also after parameters change (conv_in's weights are baked into the graph -> re-capture)."""
+    from giga_b200.detection_implicit import detect_host, select_params
+    tsdfs = [P.seeded_volumes(s)[0][None] for s in (5, 6, 7, 8)]
+    prm = select_params(force_detection=True)
+    eng = net._engine()
+    eng.set_option("graph", 0)
+    eager = [detect_host(net, t, None, prm, K=64) for t in tsdfs]
+    eng.set_option("graph", 1)
+    for rep in range(3):                               # eager registration, capture, replay
+        for t, ref in zip(tsdfs, eager):
+            got = detect_host(net, t, None, prm, K=64)
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b), rep
+    with torch.no_grad():
+        net.encoder.conv_in.bias.add_(0.05)            # new parameters: the stale graph must not be replayed
+    eng.set_option("graph", 0)
+    eager2 = detect_host(net, tsdfs[0], None, prm, K=64)
+    eng.set_option("graph", 1)
+    for rep in range(3):
+        got = detect_host(net, tsdfs[0], None, prm, K=64)
+        for a, b in zip(got, eager2):
+            assert np.array_equal(a, b), rep
+    assert not all(np.array_equal(a, b) for a, b in zip(eager2, eager[0]))
+    with torch.no_grad():
+        net.encoder.conv_in.bias.sub_(0.05)
