@@ -1262,6 +1262,7 @@ int giga_detect_host(giga_ctx* ctx, const float* tsdf, const float* tsdf_process
   auto enqueue = [&](cudaStream_t s) -> int {
     CU_TRY(cudaMemcpyAsync(ctx->d_det_tsdf, src, vol, cudaMemcpyHostToDevice, s));
     if (tsdf_process) CU_TRY(cudaMemcpyAsync(ctx->d_det_tsdfp, src_p, vol, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemsetAsync(ctx->d_det_out, 0, out_words * 4, s));   // entries past count[b] read as zero, not as the previous call's grasps
     if (int r = giga_detect(ctx, ctx->d_det_tsdf, tsdf_process ? ctx->d_det_tsdfp : nullptr, B, prm, K, d_count, d_score, d_index, d_rot, d_width, s))
       return r;
     CU_TRY(cudaMemcpyAsync(ctx->h_det_out, ctx->d_det_out, out_words * 4, cudaMemcpyDeviceToHost, s));

@@ -148,7 +148,8 @@ int giga_gaussian_kernel1d(double sigma, int radius, double *out);
  * entries of score/index/out_rot/out_width [B][K](x4) are the grasps sorted by descending score (ties:
  * larger voxel index first): score = smoothed quality, index = flat voxel index, out_rot = the raw predicted
  * quaternion, out_width = predicted width.  qual_vol (optional, [B][64000]) receives the processed quality
- * volume (what process()+bound() return).  rot and out_rot must be 16-byte aligned.  Nothing synchronises. */
+ * volume (what process()+bound() return).  Entries past min(count,K) are left untouched (giga_detect_host zeroes them).
+ * rot and out_rot must be 16-byte aligned.  Nothing synchronises. */
 int giga_select_grasps(giga_ctx *ctx, const float *tsdf, const float *qual, const float *rot, const float *width, int B,
                        const giga_select_params *prm, int K, int *count, float *score, int *index, float *out_rot,
                        float *out_width, float *qual_vol, void *stream);
