@@ -9,7 +9,7 @@
 //   * weights: staged by cp.async.bulk (UBLKCP) with mbarrier completion, prefetched one stage ahead;
 //   * gather: warp-cooperative (lane = channel, 12 coalesced 128 B texel reads per point); the
 //     96 features of the warp's 32 points stay in REGISTERS (F[3][32] per lane) and are re-split
-//     into the shared-memory A operand (hi/lo tf32 pair) for every head -- gathered once per tile;
+//     into the shared-memory A operand (hi/lo fp16 pair) for every head -- gathered once per tile;
 //   * MMAs are issued by one elected lane of warp 0; accumulators live in TMEM: columns [0,160) = fc_c outputs of the
 //     five blocks, [160,256) = three partial accumulators (hi*hi, lo*hi, hi*lo) of the current 32x32 layer;
 //   * epilogues (bias, residual, ReLU, hi/lo split, write next A operand) run thread-per-point

@@ -138,7 +138,7 @@ struct giga_ctx {
   EncLayout el;
   float* d_enc = nullptr;    // packed encoder blob
   float* d_heads = nullptr;  // [4][DW_HEAD]   fp32 FMA-pipe decoder
-  float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo tf32 splits)
+  float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo fp16 splits)
   int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int pdl = 1;               // programmatic dependent launch between the fast-path kernels (1 = on)
   int conv_in_impl = 0;      // fused Conv3d + plane means: 0 = fp32 FMA pipe (default), 1 = tcgen05 variant (parity-clean; shared-memory bound, not faster yet: DESIGN.md 5)
@@ -382,14 +382,6 @@ void pack_conv_tc(const float* w, float* dst_words) {
               dst[base + ((kc * 2 + 0) * K::NTILE + n) * 8 + j] = hi;     // [kc][hi|lo][n][8]
               dst[base + ((kc * 2 + 1) * K::NTILE + n) * 8 + j] = lo;
             }
-}
-
-float tf32_rn_host(float v) {  // same rounding as decoder_tc.cuh::tf32_rn
-  uint32_t u;
-  memcpy(&u, &v, 4);
-  u = (u + 0x1000u) & 0xffffe000u;
-  memcpy(&v, &u, 4);
-  return v;
 }
 
 bool get(const giga_ctx* ctx, const std::string& name, long numel, const float** out) {
@@ -1345,7 +1337,7 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
     return GIGA_OK;
   }
   if (!strcmp(key, "decoder_impl")) {
-    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "decoder_impl must be 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
+    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "decoder_impl must be 0 (fp32 FMA) or 1 (tcgen05 3xFP16)");
     ctx->decoder_impl = value;
     return GIGA_OK;
   }

@@ -7,7 +7,7 @@
 // query point (VGNImplicit.__init__ :28-31 meshgrid order).  HBM-bound integer/float work: one thread per
 // voxel, neighbours through L1/L2 (a scene's volume is 256 KB), no tensor cores.
 //
-// Bit-exactness with scipy.ndimage (restated in oracle/planner_oracle.py):
+// Bit-exactness with scipy.ndimage (its algorithms are restated by the CPU checker used in tests/):
 //   * gaussian_filter: three separable passes (axis 0, 1, 2), each accumulated in fp64 in scipy's
 //     symmetric correlate1d order -- centre*w[r], then for ii = -r..-1: += (x[l+ii] + x[l-ii])*w[ii+r] --
 //     with explicit round-to-nearest mul/add (no FMA contraction) and rounded to fp32 between passes;

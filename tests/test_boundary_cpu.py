@@ -14,7 +14,7 @@ from tests.util import ROOT
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "giga_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(giga_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(giga_[a-z_0-9]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
