@@ -453,3 +453,15 @@ def test_grad_refine_matches_reference_semantics(oracle_sd):
     assert ((pos_new.cpu() - p).abs() <= bound + 1e-7).all()
     _close(qual, ref_q, name="refine.qual"); _close(rot, ref_r, name="refine.rot"); _close(width, ref_w, name="refine.width")
     assert not net.__dict__.get("_train_bridge") and all(prm.grad is None for prm in net.parameters())
+
+
+def test_large_batch_equals_shards(net):
+    """B=80 scenes in one call (2.5x the bench batch; indices are 64-bit where they need to be) == shards of 32/32/16, bit for bit."""
+    B, N = 80, 192
+    x, p, pt = O.seeded_inputs(B, N, seed=97)
+    xd, pd, ptd = x.to(DEV), p.to(DEV), pt.to(DEV)
+    with torch.no_grad():
+        full = net(xd, pd, p_tsdf=ptd)
+        parts = [net(xd[a:b], pd[a:b], p_tsdf=ptd[a:b]) for a, b in ((0, 32), (32, 64), (64, 80))]
+    for i, a in enumerate(full):
+        assert torch.isfinite(a).all() and torch.equal(a, torch.cat([q[i] for q in parts]))
