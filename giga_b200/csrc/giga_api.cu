@@ -143,6 +143,13 @@ struct giga_ctx {
   int pdl = 1;               // programmatic dependent launch between the fast-path kernels (1 = on)
   int conv_in_impl = 0;      // fused Conv3d + plane means: 0 = fp32 FMA pipe (default), 1 = tcgen05 variant (parity-clean; shared-memory bound, not faster yet: DESIGN.md 5)
   int merge_decode = 1;      // giga_forward: grasp heads + TSDF head in one decoder launch
+  int tile_deps = 1;         // tile-level dependencies between consecutive same-resolution U-Net layers (needs pdl)
+  unsigned long long* d_layer_times = nullptr;   // debug (GIGA_LAYER_TIMES=1): [16][4] u64
+  int layer_slot = 0;
+  int work_slot = 0;
+  int dynamic_items = 0;     // persistent conv layers hand out items from a global counter (needs tile_deps)
+  unsigned* d_flags = nullptr;   // [7 producer layers][flags_stride] LayerDep counters, zeroed every encode
+  long flags_stride = 0;
   int conv_in_split = 1;     // conv_in: output channels split over this many CTAs (1 or 2) at B >= 8 (2 measured 5 % slower)
   int encoder_impl = 1;      // U-Net convs: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
   int last_impl = 0;
@@ -304,6 +311,11 @@ int ensure_workspace(giga_ctx* ctx, int B) {
     CU_TRY(cudaMalloc(&ctx->d_tall[i], bytes));
     CU_TRY(cudaMemset(ctx->d_tall[i], 0, bytes));
   }
+  if (ctx->d_flags) cudaFree(ctx->d_flags);
+  ctx->d_flags = nullptr;
+  ctx->flags_stride = (tall_positions(40, 3 * B) + 127) / 128 + 8;   // >= groups of any layer (the 40^2 ones have the most positions)
+  CU_TRY(cudaMalloc(&ctx->d_flags, sizeof(unsigned) * (9 * ctx->flags_stride + 16)));   // + 16 per-layer work counters
+  CU_TRY(cudaMemset(ctx->d_flags, 0, sizeof(unsigned) * (9 * ctx->flags_stride + 16)));
   ctx->cap_B = B;
   return GIGA_OK;
 }
@@ -325,11 +337,33 @@ void launch_conv(giga_ctx* ctx, const char* name, int n_img, const float* s0, co
 
 struct TallBuf { float* p = nullptr; long ps = 0; };
 
-template <class P>
+// dep_out / dep_in: index of the LayerDep counter array this layer publishes to / waits on (-1: none -> whole-grid wait).
+// PIN = the producer's configuration (its group size and N-tile count define the counters' meaning).
+template <class P, class PIN = P>
 void launch_persist(giga_ctx* ctx, const char* name, int n_img, const TallBuf& s0, const TallBuf& s1, const float* w,
-                    const float* bias, const TallBuf& out, float* fin_out, cudaStream_t st) {
+                    const float* bias, const TallBuf& out, float* fin_out, cudaStream_t st, int dep_out = -1, int dep_in = -1, int reverse = 0) {
   using K = typename P::K;
   const int n_groups = K::num_ctas(n_img), n_items = n_groups * K::NNT;
+  LayerDep dep = {nullptr, nullptr, 1, 0, 0u, 0, 0, 0, nullptr, nullptr};
+  if (ctx->d_layer_times) {   // debug: per-layer CTA start / end envelope (slot = launch order within the encode)
+    dep.dbg = ctx->d_layer_times + 4 * (ctx->layer_slot % 16);
+    ctx->layer_slot++;
+  }
+  dep.early_trigger = n_items >= ctx->num_sms ? 1 : 0;   // one CTA on every SM (each holds all 512 TMEM columns)
+  if (ctx->tile_deps && ctx->pdl) {
+    if (ctx->dynamic_items) dep.work = ctx->d_flags + 9 * ctx->flags_stride + (ctx->work_slot++ % 16);   // zeroed with the flags at the start of the encode
+    if (dep_out >= 0) dep.ready_out = ctx->d_flags + (size_t)dep_out * ctx->flags_stride;
+    if (dep_in >= 0) {
+      using KI = typename PIN::K;
+      dep.ready_in = ctx->d_flags + (size_t)dep_in * ctx->flags_stride;
+      dep.in_mt = KI::MT;
+      dep.in_groups = KI::num_ctas(n_img);
+      dep.in_target = (unsigned)KI::NNT;
+      dep.in_half_res = (KI::MODE == 1 && KI::HW * 2 == K::HW) ? 1 : 0;   // transpose conv one level down -> this concat layer
+      dep.reverse = reverse;   // (kept for experiments; the hardware hands out CTAs in blockIdx order as SMs free up, so the natural
+                               // order already gives the early-freed SMs the CTAs with one item more)
+    }
+  }
   const int grid = n_items < ctx->num_sms ? n_items : ctx->num_sms;
   unsigned long long* tl = nullptr;
   if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, name)) {   // debug: per-CTA stall accounting of one layer
@@ -342,7 +376,7 @@ void launch_persist(giga_ctx* ctx, const char* name, int n_img, const TallBuf& s
   }
   LaunchScope ls(ctx, name, st);
   launch_k(ctx, conv_tall_persistent_kernel<P>, dim3(grid), dim3(P::NTHREADS), P::SMEM_BYTES, st, s0.p, s0.ps, s1.p, s1.ps, w, bias, out.p,
-           out.ps, ctx->d_enc + ctx->el.tc_fin, ctx->d_enc + ctx->el.fin_b, fin_out, n_img, n_groups, tl);
+           out.ps, ctx->d_enc + ctx->el.tc_fin, ctx->d_enc + ctx->el.fin_b, fin_out, n_img, n_groups, dep, tl);
 }
 
 template <class K>
@@ -416,6 +450,12 @@ int giga_ctx_create(giga_ctx** out, int device) {
   ctx->timeline_layer = getenv("GIGA_TIMELINE");
   if (const char* e = getenv("GIGA_PDL")) ctx->pdl = atoi(e) != 0;   // A/B switches (debug)
   if (const char* e = getenv("GIGA_MERGE_DECODE")) ctx->merge_decode = atoi(e) != 0;
+  if (const char* e = getenv("GIGA_TILE_DEPS")) ctx->tile_deps = atoi(e) != 0;
+  if (const char* e = getenv("GIGA_DYNAMIC")) ctx->dynamic_items = atoi(e) != 0;
+  if (getenv("GIGA_LAYER_TIMES")) {
+    cudaMalloc(&ctx->d_layer_times, 16 * 4 * 8);
+    cudaMemset(ctx->d_layer_times, 0, 16 * 4 * 8);
+  }
   if (const char* e = getenv("GIGA_CONV_IN_IMPL")) ctx->conv_in_impl = atoi(e) != 0;
   if (const char* e = getenv("GIGA_CONV_IN_SPLIT")) ctx->conv_in_split = atoi(e) == 2 ? 2 : 1;
   ctx->el = make_enc_layout();
@@ -427,7 +467,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_planes, ctx->d_elem};
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_planes, ctx->d_elem, reinterpret_cast<float*>(ctx->d_flags)};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : ctx->slot) {
@@ -696,6 +736,13 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
   if (int r = ensure_workspace(ctx, B)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_img = 3 * B;
+  if (ctx->d_layer_times) {   // debug: (re)initialise the envelopes: min fields to ~0, max fields to 0
+    static const unsigned long long init[64] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0,
+                                                ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0,
+                                                ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+    cudaMemcpyAsync(ctx->d_layer_times, init, sizeof init, cudaMemcpyHostToDevice, st);
+    ctx->layer_slot = 0;
+  }
   if (ctx->conv_in_impl == 1) {
     {
       LaunchScope ls(ctx, "conv_in:elements", st);
@@ -759,31 +806,34 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
     {
       LaunchScope ls(ctx, "nchw_to_tall:pre", st);
       launch_k(ctx, nchw_to_tall_kernel<40, 4>, dim3(ceil_div(n_img * 4 * G2, 256)), dim3(256), 0, st, (const float*)ctx->d_pre, tb("pre").p,
-               tb("pre").ps, n_img);
+               tb("pre").ps, n_img, ctx->d_flags, (int)(9 * ctx->flags_stride + 16));
+      ctx->work_slot = 0;
     }
     {
-      launch_persist<P_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st);
-      launch_persist<P_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st);
+      // tile-level dependency edges (dep_out -> dep_in): d0c1->d0c2, d1c1->d1c2, d2c1->d2c2->u0up->u0c1->u0c2->u1up->u1c1->u1c2;
+      // the edges through the max-pools are whole-grid waits
+      launch_persist<P_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st, 0, -1);
+      launch_persist<P_c40, P_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st, -1, 0, 0);
       {
         LaunchScope ls(ctx, "maxpool:p0", st);
         launch_k(ctx, pool_tall_kernel<20, 4>, dim3(ceil_div(n_img * 4 * 400, 256)), dim3(256), 0, st, (const float*)tb("d0c2").p, tb("d0c2").ps,
                  tb("p0").p, tb("p0").ps, n_img);
       }
-      launch_persist<P_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st);
-      launch_persist<P_c20>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st);
+      launch_persist<P_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st, 1, -1);
+      launch_persist<P_c20, P_d1c1>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st, -1, 1, 0);
       {
         LaunchScope ls(ctx, "maxpool:p1", st);
         launch_k(ctx, pool_tall_kernel<10, 8>, dim3(ceil_div(n_img * 8 * 100, 256)), dim3(256), 0, st, (const float*)tb("d1c2").p, tb("d1c2").ps,
                  tb("p1").p, tb("p1").ps, n_img);
       }
-      launch_persist<P_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st);
-      launch_persist<P_d2c2>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st);
-      launch_persist<P_u0up>(ctx, "convT:u0", n_img, tb("d2c2"), none, E + L.tc_up[0], E + L.up_b[0], tb("u0"), nullptr, st);
-      launch_persist<P_u0c1>(ctx, "conv3x3:u0c1", n_img, tb("u0"), tb("d1c2"), E + L.tc_conv[6], E + L.bias[6], tb("u0c1"), nullptr, st);
-      launch_persist<P_c20>(ctx, "conv3x3:u0c2", n_img, tb("u0c1"), none, E + L.tc_conv[7], E + L.bias[7], tb("u0c2"), nullptr, st);
-      launch_persist<P_u1up>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st);
-      launch_persist<P_u1c1>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st);
-      launch_persist<P_u1c2>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st);
+      launch_persist<P_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st, 2, -1);
+      launch_persist<P_d2c2, P_d2c1>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st, 3, 2, 0);
+      launch_persist<P_u0up, P_d2c2>(ctx, "convT:u0", n_img, tb("d2c2"), none, E + L.tc_up[0], E + L.up_b[0], tb("u0"), nullptr, st, 7, 3, 0);
+      launch_persist<P_u0c1, P_u0up>(ctx, "conv3x3:u0c1", n_img, tb("u0"), tb("d1c2"), E + L.tc_conv[6], E + L.bias[6], tb("u0c1"), nullptr, st, 4, 7);
+      launch_persist<P_c20, P_u0c1>(ctx, "conv3x3:u0c2", n_img, tb("u0c1"), none, E + L.tc_conv[7], E + L.bias[7], tb("u0c2"), nullptr, st, 5, 4, 0);
+      launch_persist<P_u1up, P_c20>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st, 8, 5, 0);
+      launch_persist<P_u1c1, P_u1up>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st, 6, 8);
+      launch_persist<P_u1c2, P_u1c1>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st, -1, 6, 0);
     }
     ctx->last_B = B;
     ctx->last_impl = ctx->encoder_impl;
@@ -1346,6 +1396,16 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
     ctx->conv_in_impl = value;
     return GIGA_OK;
   }
+  if (!strcmp(key, "dynamic_items")) {
+    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "dynamic_items must be 0 or 1");
+    ctx->dynamic_items = value;
+    return GIGA_OK;
+  }
+  if (!strcmp(key, "tile_deps")) {
+    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "tile_deps must be 0 or 1");
+    ctx->tile_deps = value;
+    return GIGA_OK;
+  }
   if (!strcmp(key, "pdl")) {
     if (value != 0 && value != 1) return fail(GIGA_EINVAL, "pdl must be 0 or 1");
     ctx->pdl = value;
@@ -1399,6 +1459,12 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
   if (int r = set_device(ctx)) return r;
   const float* src = nullptr;
   long numel = 0;
+  if (!strcmp(name, "layer_times")) {
+    if (!ctx->d_layer_times) return fail(GIGA_ESTATE, "giga_debug_copy: set GIGA_LAYER_TIMES=1");
+    if (128 > capacity) return fail(GIGA_EINVAL, "giga_debug_copy: destination too small");
+    CU_TRY(cudaMemcpyAsync(dst, ctx->d_layer_times, 64 * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 128;
+  }
   if (!strcmp(name, "timeline")) {   // u64 stamps reinterpreted as pairs of floats (debug only)
     if (!ctx->d_timeline) return fail(GIGA_ESTATE, "giga_debug_copy: no timeline recorded (set GIGA_TIMELINE=<kernel name>)");
     if (ctx->timeline_n * 2 > capacity) return fail(GIGA_EINVAL, "giga_debug_copy: destination too small");

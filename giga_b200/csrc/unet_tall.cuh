@@ -73,10 +73,12 @@ __device__ __forceinline__ long tall_pos(int hw, int img, int y, int x) { return
 // ---- layout conversion / pooling (thread = one valid pixel x one 8-channel k-chunk) --------------------------
 // grid: ceil(n_img*HW*HW*C8 / 256), block 256
 template <int HW, int C8>   // C8 = channels / 8
-__global__ void __launch_bounds__(256) nchw_to_tall_kernel(const float* __restrict__ src, float* __restrict__ dst, long ps, int n_img) {
+__global__ void __launch_bounds__(256) nchw_to_tall_kernel(const float* __restrict__ src, float* __restrict__ dst, long ps, int n_img,
+                                                           unsigned* __restrict__ flags, int n_flags) {   // flags: LayerDep counters, zeroed here
   pdl_launch();
   pdl_wait();
   const long t = (long)blockIdx.x * 256 + threadIdx.x;
+  if (t < n_flags) flags[t] = 0u;
   const long total = (long)n_img * C8 * HW * HW;
   if (t >= total) return;
   const int pix = (int)(t % (HW * HW));
@@ -225,9 +227,10 @@ struct PersistCfg {
   static constexpr int FIN_BYTES = K::FUSE_FINAL ? 2 * K::FIN_A_BYTES + 4096 : 0;
   static constexpr int OFF_BIAS = OFF_FIN + FIN_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 64 * 4;
-  static constexpr int NBAR = 2 * S + 10;                                        // full[S] empty[S] acc_full[2] acc_empty[2] z_full[2] z_empty[2] wbar fin
-  static constexpr int NTHREADS = 32 * (5 + NMMAW);                              // 4 drain warps + loader warp + MMA-issue warps
-  static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+  static constexpr int NBAR = 2 * S + 19;                                        // full[S] empty[S] acc_full[2] acc_empty[2] z_full[2] z_empty[2] wbar fin pub item[8]
+  static constexpr int NTHREADS = 32 * (6 + NMMAW);                              // 4 drain warps + loader warp + MMA-issue warps + publisher warp
+  static constexpr int PUB_WARP = 5 + NMMAW;
+  static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16 + 32;                // + TMEM slot + item ring
   static constexpr int ACC = K::ACC;
   static constexpr int TMEM_COLS = 512;                                          // X Y | Z1a Z2a | Z1b Z2b | final  (6*ACC + 32 <= 512)
   static_assert(OFF_FINACC + 64 <= 512, "TMEM");   // conv_final: hi*hi columns + scaled-correction columns
@@ -235,6 +238,52 @@ struct PersistCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
   static_assert(!WRES || K::NNT == 1, "resident weights cover one N tile");
 };
+
+// Tile-level dependencies between consecutive persistent layers (same resolution): instead of waiting for the WHOLE
+// previous layer (griddepcontrol.wait), a consumer layer's loader waits until the producer has finished exactly the
+// position groups its operand window covers.  The producer's epilogue publishes a group with
+// __threadfence + barrier + atomicAdd (release); the consumer polls with ld.acquire.gpu and orders its bulk copies
+// (async proxy) behind the acquire with fence.proxy.async.  A consumer CTA can only become resident on an SM whose
+// producer CTA has exited (both hold all 512 TMEM columns), and every producer CTA is resident before the consumer is
+// launched, so producers never wait for consumers: no deadlock.  Consumers walk the item list from the other end
+// (`reverse`), so the SMs that got one item fewer in the producer get one more in the consumer: the per-layer tail
+// (item quantisation over 148 SMs) and the consumer's prologue disappear into the producer's tail.
+// The flags are zeroed once per encode by nchw_to_tall_kernel (which every layer of the step transitively follows).
+struct LayerDep {
+  unsigned* ready_out;        // producer side: [n_groups] counters of this layer's finished (group, N tile) items, or null
+  const unsigned* ready_in;   // consumer side: the previous layer's counters, or null (then: griddepcontrol.wait)
+  int in_mt;                  // producer's positions per group
+  int in_groups;              // producer's number of groups
+  unsigned in_target;         // producer's N tiles per group
+  int in_half_res;            // 1: the producer is the transpose conv one level down (its groups index positions at HW/2)
+  int reverse;                // walk the item list from the last SM
+  int early_trigger;          // grid == #SMs: the successor cannot become resident before one of this grid's CTAs exits
+  unsigned* work;             // dynamic item scheduling: global counter of this layer's next unclaimed item (null: static strided list)
+  unsigned long long* dbg;    // debug (GIGA_LAYER_TIMES): [min CTA start, max CTA start, min CTA end, max CTA end] in ns (globaltimer)
+};
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// bounded poll: a broken dependency must trap, never hang the GPU
+__device__ __forceinline__ void wait_groups(const unsigned* ready, int g_lo, int g_hi, unsigned target) {
+  for (int g = g_lo; g <= g_hi; ++g) {
+    bool ok = false;
+    for (int i = 0; i < (1 << 22) && !ok; ++i) {
+      ok = ld_acquire_gpu(ready + g) >= target;
+      if (!ok) __nanosleep(40);
+    }
+    if (!ok) __trap();
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes acquired above -> visible to the bulk copies below
+}
 
 // A single thread issues a 128xNTILEx8 tcgen05.mma only every ~85 cycles (measured, profiles/r01i: one issuing
 // warp per SM ran at 93 cycles/MMA) while the MMA itself is shared-memory-bound at ~40 cycles, so three
@@ -246,7 +295,8 @@ __global__ void __launch_bounds__(P::NTHREADS, 1)
 conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const float* __restrict__ src1, long ps1,
                             const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out, long pso,
                             const float* __restrict__ fin_w, const float* __restrict__ fin_b, float* __restrict__ fin_out,
-                            int n_img, int n_groups, unsigned long long* __restrict__ tl) {   // tl: optional stall accounting (debug)
+                            int n_img, int n_groups, const LayerDep dep,
+                            unsigned long long* __restrict__ tl) {   // tl: optional stall accounting (debug)
   using K = typename P::K;
   constexpr int HW = K::HW, WP = K::WP, HP1 = K::HP1, NTILE = K::NTILE, NT = K::NT, ACC = K::ACC, S = P::S, NC = K::NC;
   extern __shared__ __align__(128) uint8_t smem_pt[];
@@ -259,14 +309,27 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
   uint64_t* z_empty = z_full + 2;
   uint64_t* wbar = z_empty + 2;
   uint64_t* fin_bar = wbar + 1;
+  uint64_t* pub_bar = fin_bar + 1;   // 128 epilogue arrivals per item -> publisher warp (LayerDep)
+  uint64_t* item_bar = pub_bar + 1;  // [8] the loader has published item j (ring slot j & 7)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::OFF_BAR + P::NBAR * 8);
+  // Items (M-tile group x N tile) are handed out by the loader warp: from a global counter when dep.work is set (the CTAs that
+  // become resident first simply take more items -- no per-layer tail from the static 148-way split), else the strided list.
+  // The other roles learn the item (or -1 = no more) from an 8-slot ring; the loader is never more than 5 items ahead.
+  volatile int* ring = reinterpret_cast<volatile int*>(smem + P::OFF_BAR + P::NBAR * 8 + 16);
   float* sbias = reinterpret_cast<float*>(smem + P::OFF_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int total_rows = tall_rows(HW, n_img);
   const int n_items = n_groups * K::NNT;
-  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x + j*gridDim.x
+  const int bid = dep.reverse ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
 
-  pdl_launch();   // the next layer may start its prologue (barriers, TMEM, weights) as soon as SM resources free up
+  // A layer that waits for its whole predecessor releases its own successor only after that wait (below): the successor
+  // may then rely on everything older being complete.  A tile-dependent consumer releases its successor at once.
+  if (dep.ready_in || dep.early_trigger) pdl_launch();
+  if (dep.dbg && tid == 0) {
+    const unsigned long long t = globaltimer_ns();
+    atomicMin(dep.dbg + 0, t);
+    atomicMax(dep.dbg + 1, t);
+  }
   if (warp == 4) tc::tmem_alloc(tmem_slot, P::TMEM_COLS);
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], P::NMMAW); }   // every MMA warp releases a stage
@@ -274,7 +337,8 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
     tc::mbar_init(&acc_empty[0], 128); tc::mbar_init(&acc_empty[1], 128);
     tc::mbar_init(&z_full[0], P::NMMAW - 1); tc::mbar_init(&z_full[1], P::NMMAW - 1);
     tc::mbar_init(&z_empty[0], 128); tc::mbar_init(&z_empty[1], 128);
-    tc::mbar_init(wbar, 1); tc::mbar_init(fin_bar, 1);
+    tc::mbar_init(wbar, 1); tc::mbar_init(fin_bar, 1); tc::mbar_init(pub_bar, 128);
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&item_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (K::FUSE_FINAL && tid < 128) {   // conv_final weights: staged once per CTA
@@ -287,7 +351,22 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const int total_chunks = my_items * NC;
+  if (warp == 4 && P::WRES) {   // the layer's weights, resident for the whole kernel (single N tile): constants,
+    if (tc::elect_one()) {                       // so their copy overlaps the wait for the previous layer
+      tc::mbar_arrive_expect_tx(wbar, (uint32_t)P::W_BYTES);
+      for (int c = 0; c < NC; ++c)
+        tc::bulk_g2s(smem + c * K::B_BYTES, wt + (size_t)c * (K::B_BYTES / 4), K::B_BYTES, wbar);
+    }
+    __syncwarp();
+  }
+  if (!dep.ready_in) {
+    pdl_wait();     // activations of the previous layer(s) are complete and visible (weights / biases are constants)
+    if (!dep.early_trigger) pdl_launch();   // small grids: release the successor only now (it may land on an SM without a CTA of ours)
+  }
+  auto next_item = [&](int j) -> int {   // every role but the loader: wait for the loader's verdict on item j
+    tc::mbar_wait(&item_bar[j & 7], (uint32_t)((j >> 3) & 1));
+    return ring[j & 7];
+  };
   // debug stall accounting: cycles spent in each kind of wait, per role (slots: 32 u64 per CTA)
   unsigned long long* tlc = tl ? tl + (size_t)blockIdx.x * 32 : nullptr;
   long long w_a = 0, w_b = 0, w_c = 0;
@@ -300,20 +379,44 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
 
   if (warp == 4) {
     // ============================ loader warp: bulk copies only ============================
-    if (P::WRES && my_items > 0) {   // the layer's weights, resident for the whole kernel (single N tile)
-      if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(wbar, (uint32_t)P::W_BYTES);
-        for (int c = 0; c < NC; ++c)
-          tc::bulk_g2s(smem + c * K::B_BYTES, wt + (size_t)c * (K::B_BYTES / 4), K::B_BYTES, wbar);
-      }
-      __syncwarp();
-    }
-    pdl_wait();   // activations of the previous layer(s) are complete and visible; weights / biases above are constants
 #pragma unroll 1
-    for (int i = 0; i < total_chunks; ++i) {   // i = flat chunk index of this CTA
-      const int s = i % S, j = i / NC, c = i - j * NC;
-      const int item = (int)blockIdx.x + j * (int)gridDim.x;
+    for (int j = 0;; ++j) {
+      int item = -1;
+      if ((tid & 31) == 0) {
+        item = dep.work ? (int)atomicAdd(dep.work, 1u) : bid + j * (int)gridDim.x;
+        if (item >= n_items) item = -1;
+        ring[j & 7] = item;
+        tc::mbar_arrive(&item_bar[j & 7]);   // release: the ring entry is visible to whoever sees the phase complete
+      }
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item < 0) break;
       const int grp = item / K::NNT, nt = item - grp * K::NNT;
+      if (dep.ready_in) {   // the producer groups this item's operand window [f0 - HALO, f0 + MT + HALO) covers
+        long lo = (long)grp * K::MT - K::HALO, hi = (long)grp * K::MT + K::MT + K::HALO - 1;
+        if (lo < 0) lo = 0;
+        if (dep.in_half_res) {   // position at HW -> the HW/2 position whose transpose-conv outputs land there (monotone, clamped into the images)
+          auto down = [&](long f) -> long {
+            long r = f / WP - 1;
+            if (r < 0) r = 0;
+            long img = r / HP1;
+            if (img > n_img - 1) img = n_img - 1;
+            long y = r - img * HP1, x = f % WP - 1;
+            y = y < 0 ? 0 : (y > HW - 1 ? HW - 1 : y);
+            x = x < 0 ? 0 : (x > HW - 1 ? HW - 1 : x);
+            return (1 + img * (HW / 2 + 1) + y / 2) * (HW / 2 + 2) + x / 2 + 1;
+          };
+          lo = down(lo);
+          hi = down(hi);
+        }
+        const int g_lo = (int)(lo / dep.in_mt);
+        int g_hi = (int)(hi / dep.in_mt);
+        if (g_hi > dep.in_groups - 1) g_hi = dep.in_groups - 1;
+        if (tc::elect_one()) wait_groups(dep.ready_in, g_lo, g_hi, dep.in_target);
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int c = 0; c < NC; ++c) {   // i = flat chunk index of this CTA
+      const int i = j * NC + c, s = i % S;
       if (i >= S) twait(&empty[s], (uint32_t)(((i / S) - 1) & 1), w_a);   // all three MMA warps are done with the stage
       uint8_t* stA = smem + P::OFF_STAGES + s * P::STAGE_BYTES;
       const int ch0 = c * 16;
@@ -331,18 +434,39 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
         if (!P::WRES) tc::bulk_g2s(stA + K::A_BYTES, wt + ((size_t)nt * NC + c) * (K::B_BYTES / 4), K::B_BYTES, &full[s]);
       }
       __syncwarp();
+      }
     }
     if (tlc && (tid & 31) == 0) { tlc[0] = (unsigned long long)w_a; tlc[1] = (unsigned long long)(clock64() - t_begin); }
+  } else if (warp == P::PUB_WARP) {
+    // ============================ publisher warp (tile-level dependencies) ============================
+    // The device-wide release fence costs ~1 us; done here it delays nobody in this CTA (done by an epilogue thread it
+    // stalled the drain warps' chunk barriers and made the layer 2.5 us slower: profiles/r01w_layer_times.txt).
+    if (dep.ready_out) {
+#pragma unroll 1
+      for (int j = 0;; ++j) {
+        const int item = next_item(j);
+        if (item < 0) break;
+        tc::mbar_wait(pub_bar, (uint32_t)(j & 1));   // all 128 epilogue threads have stored the item (arrive = release, wait = acquire)
+        if (tc::elect_one()) {
+          __threadfence();                           // cumulative: their stores are ordered before the counter device-wide
+          atomicAdd(dep.ready_out + item / K::NNT, 1u);
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp >= 5) {
     // ============================ MMA-issue warps ============================
     // 3-product form: 5 = hi*hi, 6 = lo*hi, 7 = hi*lo.   N-concat form: 5 = Ahi.[Bhi;Blo]^T, 6 = Alo.Bhi^T.
     const int kind = warp - 5;
     constexpr int NMMA = (P::NCONCAT ? 2 : 1) * NTILE;             // N of warp 5's MMAs
     const uint32_t idesc = (P::NCONCAT && kind == 0) ? tc::make_idesc_f16(128, NMMA) : tc::make_idesc_f16(128, NTILE);
-    if (P::WRES && my_items > 0) tc::mbar_wait(wbar, 0u);
+    if (P::WRES) tc::mbar_wait(wbar, 0u);
 #pragma unroll 1
-    for (int i = 0; i < total_chunks; ++i) {
-      const int s = i % S, j = i / NC, c = i - j * NC, set = i & 1, zp = j & 1;
+    for (int j = 0;; ++j) {
+      if (next_item(j) < 0) break;
+#pragma unroll 1
+      for (int c = 0; c < NC; ++c) {
+      const int i = j * NC + c, s = i % S, set = i & 1, zp = j & 1;
       twait(&full[s], (uint32_t)((i / S) & 1), w_a);
       if (kind == 0) {
         if (i >= 2) twait(&acc_empty[set], (uint32_t)(((i - 2) >> 1) & 1), w_b);
@@ -375,6 +499,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
       }
       __syncwarp();
       w_c += clock64() - t_issue;
+      }
     }
     if (tlc && (tid & 31) == 0) {
       tlc[4 + 4 * kind] = (unsigned long long)w_a; tlc[5 + 4 * kind] = (unsigned long long)w_b;
@@ -384,9 +509,12 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
     // ============================ drain + epilogue warps ============================
     const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t fin_use = 0;
+    int n_done = 0;
 #pragma unroll 1
-    for (int j = 0; j < my_items; ++j) {
-      const int item = (int)blockIdx.x + j * (int)gridDim.x;
+    for (int j = 0;; ++j) {
+      const int item = next_item(j);
+      if (item < 0) break;
+      ++n_done;
       const int grp = item / K::NNT, nt_idx = item - grp * K::NNT;
       const int f0 = grp * K::MT, zp = j & 1;
       if (tid < NTILE) sbias[tid] = __ldg(bias + (K::MODE == 0 ? nt_idx * NTILE : 0) + tid);
@@ -535,17 +663,23 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           tc::named_bar_sync(1, 128);   // scratch / final accumulator free for the next M tile
         }
       }
+      if (dep.ready_out) tc::mbar_arrive(pub_bar);   // this thread's stores of the item are done -> publisher warp
       tc::named_bar_sync(1, 128);   // everyone is done with sbias before the next item overwrites it
       w_c += clock64() - t_e;
     }
     if (tlc && tid == 0) {
       tlc[16] = (unsigned long long)w_a; tlc[17] = (unsigned long long)w_b; tlc[18] = (unsigned long long)w_c;
-      tlc[19] = (unsigned long long)(clock64() - t_begin); tlc[20] = (unsigned long long)my_items;
+      tlc[19] = (unsigned long long)(clock64() - t_begin); tlc[20] = (unsigned long long)n_done;
     }
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 4) tc::tmem_dealloc(tmem, P::TMEM_COLS);
+  if (dep.dbg && tid == 0) {
+    const unsigned long long t = globaltimer_ns();
+    atomicMin(dep.dbg + 2, t);
+    atomicMax(dep.dbg + 3, t);
+  }
 }
 
 }  // namespace giga

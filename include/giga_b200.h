@@ -178,6 +178,8 @@ long giga_ctx_launch_count(const giga_ctx *ctx);
  *                   shared-memory-bandwidth bound, currently not faster)
  *   "graph":        1 = giga_detect_host replays a captured CUDA graph of the whole call from its third invocation of a
  *                   configuration on (default), 0 = always enqueue kernel by kernel
+ *   "tile_deps":    1 = consecutive same-resolution U-Net layers synchronise per position group instead of per grid
+ *                   (default; needs "pdl"), 0 = every layer waits for its whole predecessor
  *   "pdl":          1 = programmatic dependent launch between the fast-path kernels (default), 0 = plain stream order */
 int giga_ctx_set_option(giga_ctx *ctx, const char *key, int value);
 /* per-kernel device timing for the roofline report: when enabled every kernel launch is bracketed

@@ -465,3 +465,24 @@ def test_large_batch_equals_shards(net):
         parts = [net(xd[a:b], pd[a:b], p_tsdf=ptd[a:b]) for a, b in ((0, 32), (32, 64), (64, 80))]
     for i, a in enumerate(full):
         assert torch.isfinite(a).all() and torch.equal(a, torch.cat([q[i] for q in parts]))
+
+
+def test_tile_dependencies_do_not_change_results(oracle_sd):
+    """tile_deps=1 (consumer layers start on position groups as soon as the producer layer has published them, walking the
+    items in the opposite direction) must give the bits of the whole-grid-wait schedule, for small and bench-sized batches,
+    repeatedly (a missed dependency would show up as run-to-run differences)."""
+    net = make_net("giga", oracle_sd)
+    eng = net._engine()
+    for B in (1, 5, 32):
+        x, p, pt = O.seeded_inputs(B, 96, seed=99 + B)
+        xd, pd, ptd = x.to(DEV), p.to(DEV), pt.to(DEV)
+        with torch.no_grad():
+            eng.set_option("tile_deps", 0)
+            ref = net(xd, pd, p_tsdf=ptd)
+            ref_planes = net.encode_inputs(xd).packed.clone()
+            eng.set_option("tile_deps", 1)
+            for _ in range(6):
+                out = net(xd, pd, p_tsdf=ptd)
+                for a, b in zip(out, ref):
+                    assert torch.equal(a, b)
+                assert torch.equal(net.encode_inputs(xd).packed, ref_planes)
