@@ -119,10 +119,11 @@ __device__ __forceinline__ void store_a_row(uint8_t* a_hi, uint8_t* a_lo, int ro
   }
 }
 
-// grid (ceil(N/128) + ceil(N2/128), B), block 128, dynamic smem TD_SMEM_BYTES, 2 CTAs/SM (2 x 256 TMEM columns).
-// Two jobs can share one launch (forward(): the grasp heads at p and the TSDF head at p_tsdf): tiles [0, tiles1) evaluate
-// `heads` at pts, the rest `heads2` at pts2 -- the long (3-head) tiles are scheduled first and the short ones fill the tail
-// instead of paying a second launch and a second partial wave.
+// grid ((ceil(N/128) + ceil(N2/128)) * B), block 128, dynamic smem TD_SMEM_BYTES, 2 CTAs/SM (2 x 256 TMEM columns).
+// Two jobs can share one launch (forward(): the grasp heads at p and the TSDF head at p_tsdf).  The grid is ONE-dimensional
+// and ordered by cost: CTAs [0, tiles1*B) evaluate `heads` at pts for all scenes, the rest `heads2` at pts2 -- CTAs are
+// dispatched in blockIdx order, so every long (3-head) tile starts before any short one and the kernel's tail consists of
+// short tiles (with a (tile, scene) grid the last scenes' long tiles ran alone at the end: 158 -> 12x us).
 __global__ void __launch_bounds__(TD_PTS, 2)
 decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
                         const float* __restrict__ pts,     // [B][N][3]
@@ -145,15 +146,21 @@ decode_points_tc_kernel(const float* __restrict__ planes,  // [3][B][40][40][32]
   uint64_t* bar3 = bar + 4;                                             // 32x32 layer: three issuing warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TD_OFF_BAR + 40);
 
-  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int tile = blockIdx.x;
-  if (tile >= tiles1) { tile -= tiles1; pts = pts2; N = N2; heads = heads2; }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int tile = blockIdx.x, b;
+  if (tile < tiles1 * B) { b = tile / tiles1; tile -= b * tiles1; }
+  else {
+    const int tiles2 = (N2 + TD_PTS - 1) / TD_PTS;
+    tile -= tiles1 * B;
+    b = tile / tiles2; tile -= b * tiles2;
+    pts = pts2; N = N2; heads = heads2;
+  }
   const int n0 = tile * TD_PTS;
   const int n = n0 + tid;
   const bool valid = n < N;
   const int nc = valid ? n : N - 1;
 
-  unsigned long long* tlc = tl ? tl + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+  unsigned long long* tlc = tl ? tl + (size_t)blockIdx.x * 32 : nullptr;
   int tslot = 0;
   auto stamp = [&]() {
     if (tlc && tid == 0 && tslot < 31) {

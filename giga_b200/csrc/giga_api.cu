@@ -884,7 +884,7 @@ int launch_decode(giga_ctx* ctx, const float* planes, int B, const float* points
       ctx->timeline_n = (long)n;
       tl = ctx->d_timeline;
     }
-    launch_k(ctx, decode_points_tc_kernel, dim3(tiles1 + tiles2, B), dim3(TD_PTS), TD_SMEM_BYTES, st, planes, points,
+    launch_k(ctx, decode_points_tc_kernel, dim3((tiles1 + tiles2) * B), dim3(TD_PTS), TD_SMEM_BYTES, st, planes, points,
              (const float*)ctx->d_heads_tc, B, N, heads, qual, rot, width, occ, points2, two ? N2 : 0, heads2, tiles1, tl);
   } else {
     decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N, heads, qual, rot,
