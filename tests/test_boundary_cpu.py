@@ -73,3 +73,35 @@ def test_product_never_imports_the_oracle():
         p = os.path.join(ROOT, f)
         if os.path.exists(p):
             assert "/root/reference" not in open(p).read(), f"{f} must not read /root/reference at run time"
+
+
+def test_planner_host_mirror_surface():
+    """The planner mirror has the reference's constructor / call surface (detection_implicit.py:17-33) and the parameter struct
+    carries the reference's defaults (process/bound/select); no GPU needed for any of this."""
+    import inspect
+
+    import giga_b200
+    from giga_b200._lib import SelectParams, lib
+    from giga_b200.detection_implicit import LOW_TH, VGNImplicit, lattice, select_params
+
+    sig = inspect.signature(VGNImplicit.__init__)
+    assert list(sig.parameters)[:9] == ["self", "model_path", "model_type", "best", "force_detection", "qual_th", "out_th", "visualize", "resolution"]
+    assert (sig.parameters["qual_th"].default, sig.parameters["out_th"].default, sig.parameters["resolution"].default) == (0.9, 0.5, 40)
+    assert list(inspect.signature(VGNImplicit.__call__).parameters) == ["self", "state", "scene_mesh", "aff_kwargs"]
+    p = SelectParams()
+    lib.giga_select_params_default(C.byref(p))
+    q = select_params()
+    for f, _ in SelectParams._fields_:
+        assert getattr(p, f) == getattr(q, f), f
+    assert (p.lim_x, p.lim_y, p.lim_z, p.max_filter_size, p.force_detection) == (2, 2, 7, 4, 0) and LOW_TH == 0.5
+    pos = lattice()
+    assert pos.shape == (1, 64000, 3) and pos.dtype == torch.float32
+    lin = torch.linspace(start=-0.5, end=0.5 - 1.0 / 40, steps=40)
+    assert torch.equal(pos[0, :40, 2], lin) and torch.equal(pos[0, ::1600, 0], lin)     # meshgrid 'ij': z fastest, x slowest
+    if not torch.cuda.is_available():
+        with pytest.raises(giga_b200.GigaError):
+            VGNImplicit(None, "giga")
+        # compute entry points refuse to run without a device (no context can exist)
+        assert lib.giga_select_grasps(None, None, None, None, None, 1, C.byref(p), 8, None, None, None, None, None, None, None) == -1
+        assert lib.giga_detect_host(None, None, None, 1, C.byref(p), 8, None, None, None, None, None, None) == -1
+        assert lib.giga_forward(None, None, 1, None, 0, None, 0, None, None, None, None, None, None, None, None) == -1
