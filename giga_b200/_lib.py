@@ -22,6 +22,8 @@ SYMBOLS = {
     "giga_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "giga_ctx_destroy": (None, [C.c_void_p]),
     "giga_ctx_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long, C.c_int]),
+    "giga_ctx_set_params_flat": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_long), C.POINTER(C.c_long),
+                                          C.c_void_p, C.c_long, C.c_int]),
     "giga_ctx_commit_params": (C.c_int, [C.c_void_p]),
     "giga_ctx_heads": (C.c_uint, [C.c_void_p]),
     "giga_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

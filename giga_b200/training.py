@@ -47,8 +47,19 @@ def _unet(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
     return F.conv2d(x, g("conv_final.weight"), g("conv_final.bias"))
 
 
+def _conv_in(x, w, b):
+    """Conv3d(1, 32, 3, padding=1) as 27 shifted views x one matmul.  Same arithmetic as F.conv3d; cuDNN's weight-gradient kernel for a
+    single input channel (wgrad2d_grouped_direct) took 37 ms per step at batch 64 -- 58 % of the whole training step -- while this
+    form differentiates into a [32 x 27] <- [32 x B*64000] x [B*64000 x 27] matmul."""
+    B = x.shape[0]
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    cols = torch.stack([xp[:, dx:dx + 40, dy:dy + 40, dz:dz + 40] for dx in range(3) for dy in range(3) for dz in range(3)], 1)   # [B,27,40,40,40]
+    f = torch.matmul(w.reshape(32, 27), cols.reshape(B, 27, -1)) + b.view(1, 32, 1)
+    return f.view(B, 32, 40, 40, 40)
+
+
 def _encode(sd, x):
-    f = F.relu(F.conv3d(x.unsqueeze(1), sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1))  # [b,c,ix,iy,iz]
+    f = F.relu(_conv_in(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"]))  # [b,c,ix,iy,iz]
     # 40^3 voxels onto 40^2 cells: the scatter_mean is the mean along the perpendicular axis (SURVEY.md 8a-a4)
     pre = {"xz": f.mean(3).transpose(2, 3), "xy": f.mean(4).transpose(2, 3), "yz": f.mean(2).transpose(2, 3)}
     return {k: _unet(sd, v) for k, v in pre.items()}
@@ -109,14 +120,9 @@ class _Bridge(torch.autograd.Function):
         x, p, pt, *params = ctx.saved_tensors
         leaves = [t.detach().requires_grad_(True) for t in params]
         sd = dict(zip(ctx.names, leaves))
-        # fp32 library kernels for the recompute (cuDNN/cuBLAS default to TF32, which costs ~1e-2 relative on gradients)
-        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-        torch.backends.cudnn.allow_tf32 = False
-        torch.backends.cuda.matmul.allow_tf32 = False
-        try:
-            return _Bridge._backward_impl(ctx, leaves, sd, x, p, pt, grads)
-        finally:
-            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        # the recompute runs under the caller's torch.backends flags, exactly like the reference's own training step would
+        # (PyTorch's default lets cuDNN use TF32 for convolutions; set torch.backends.cudnn.allow_tf32 = False for fp32 gradients)
+        return _Bridge._backward_impl(ctx, leaves, sd, x, p, pt, grads)
 
     @staticmethod
     def _backward_impl(ctx, leaves, sd, x, p, pt, grads):

@@ -69,6 +69,10 @@ void giga_ctx_destroy(giga_ctx *ctx);
  * `data` is a device pointer.  giga_ctx_commit_params() re-packs everything into the
  * kernel layouts (synchronous) and must be called after any parameter change. */
 int giga_ctx_set_param(giga_ctx *ctx, const char *name, const float *data, long numel, int on_device);
+/* all parameters in one call: `flat` holds the n tensors back to back (offsets[i], numels[i] in elements), on the device
+ * or the host; one copy instead of n (a training loop re-uploads every step: optimizer.step() changes every tensor). */
+int giga_ctx_set_params_flat(giga_ctx *ctx, int n, const char *const *names, const long *offsets, const long *numels,
+                             const float *flat, long total, int on_device);
 int giga_ctx_commit_params(giga_ctx *ctx);
 /* bit mask of GIGA_HEAD_* whose parameters are committed (giga_aff lacks TSDF; giga_geo has only TSDF) */
 unsigned giga_ctx_heads(const giga_ctx *ctx);
