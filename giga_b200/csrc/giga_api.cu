@@ -518,6 +518,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   for (auto& g : ctx->det_graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (ctx->st_graph) cudaStreamDestroy(ctx->st_graph);
+  if (ctx->d_layer_times) cudaFree(ctx->d_layer_times);
   if (ctx->h_det_in) cudaFreeHost(ctx->h_det_in);
   if (ctx->h_det_out) cudaFreeHost(ctx->h_det_out);
   void* pl[] = {ctx->d_pl_a, ctx->d_pl_b, ctx->d_pl_qlow, ctx->d_pl_cval, ctx->d_pl_cidx, ctx->d_pl_flag, ctx->d_lattice, ctx->d_det_pts,
