@@ -488,3 +488,31 @@ def test_tile_dependencies_do_not_change_results(oracle_sd):
                 for a, b in zip(out, ref):
                     assert torch.equal(a, b)
                 assert torch.equal(net.encode_inputs(xd).packed, ref_planes)
+
+
+def test_default_initialised_and_rescaled_networks():
+    """Parameter scales other than the seeded N(0, 0.1^2): the network exactly as get_network() initialises it (xavier convs,
+    zero conv biases, fc_1 = 0: activations <= 0.7, the regime where fp16 lo halves would underflow without the 2^11 / 2^s
+    scaling) and a copy with the encoder weights scaled by 2.5 (activations up to ~400, planes ~1000, head outputs ~200 --
+    inside fp16's documented +-65504 range).  Relative accuracy must stay fp32-class at both ends."""
+    import giga_b200
+    torch.manual_seed(123)
+    base = giga_b200.get_network("giga")
+    sd0 = {k: v.detach().clone() for k, v in base.state_dict().items()}
+    x, p, pt = O.seeded_inputs(2, 200, seed=77)
+    for name, scale in (("default-init", 1.0), ("encoder x2.5", 2.5)):
+        sd = {k: (v * scale if k.endswith("weight") and k.startswith("encoder") else v.clone()) for k, v in sd0.items()}
+        net = make_net("giga", sd)
+        with torch.no_grad():
+            ref_planes = O.encode_inputs(sd, x)
+            c = net.encode_inputs(x.to(DEV))
+            for k in O.PLANES:
+                r = ref_planes[k]
+                err = (c[k].cpu() - r).abs().max().item()
+                assert err <= 4e-6 * max(r.abs().max().item(), 1e-3), (name, k, err, r.abs().max().item())
+            ref = O.forward(sd, x, p, pt)
+            out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+        for nme, a, b in zip(("qual", "rot", "width", "occ"), out, ref):
+            err = (a.cpu() - b).abs().max().item()
+            assert torch.isfinite(a).all() and err <= 1e-5 * max(b.abs().max().item(), 1.0), (name, nme, err)
+        assert torch.equal(out[0].argmax(1).cpu(), ref[0].argmax(1))
