@@ -48,6 +48,7 @@ SYMBOLS = {
     "giga_detect_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_ctx_launch_count": (C.c_long, [C.c_void_p]),
+    "giga_ctx_overflow_count": (C.c_long, [C.c_void_p, C.c_int]),
     "giga_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "giga_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "giga_ctx_timing_report": (C.c_long, [C.c_void_p, C.c_char_p, C.c_long]),

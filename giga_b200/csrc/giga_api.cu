@@ -17,7 +17,7 @@
 #include "conv_in.cuh"
 #include "conv_in_tc.cuh"
 #include "decoder.cuh"
-#include "decoder_tc.cuh"
+#include "decoder_ws.cuh"
 #include "planner.cuh"
 #include "unet.cuh"
 #include "unet_tall.cuh"
@@ -138,8 +138,10 @@ struct giga_ctx {
   EncLayout el;
   float* d_enc = nullptr;    // packed encoder blob
   float* d_heads = nullptr;  // [4][DW_HEAD]   fp32 FMA-pipe decoder
-  float* d_heads_tc = nullptr;  // [4][TW_HEAD] tensor-core decoder (operand-layout hi/lo fp16 splits)
-  int decoder_impl = 1;      // 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA pipe
+  float* d_hc = nullptr;        // [4][HC_SIZE] head constants of the warp-specialised decoder (decoder_ws.cuh)
+  uint8_t* d_wblob[5] = {};     // streamed weight blobs per job type (0: the three grasp heads, 1 + h: head h alone)
+  unsigned* d_sched = nullptr;  // [0] next item, [1] CTAs done, [2] overflow count (self-resetting work counter)
+  int decoder_impl = 1;      // 1 = warp-specialised tcgen05 3xFP16, A operand in TMEM (default), 0 = fp32 FMA pipe
   int pdl = 1;               // programmatic dependent launch between the fast-path kernels (1 = on)
   int conv_in_impl = 0;      // fused Conv3d + plane means: 0 = fp32 FMA pipe (default), 1 = tcgen05 variant (parity-clean; shared-memory bound, not faster yet: DESIGN.md 5)
   int merge_decode = 1;      // giga_forward: grasp heads + TSDF head in one decoder launch
@@ -198,6 +200,13 @@ struct giga_ctx {
   cudaStream_t st_graph = nullptr;
   long launches = 0;
   bool attrs_set = false;
+  // cross-stream ordering of the shared workspaces: every public entry point that enqueues work records ev_order on its
+  // stream when it returns; an entry point called on a DIFFERENT stream first makes that stream wait for the event.
+  cudaEvent_t ev_order = nullptr;
+  cudaStream_t order_stream = nullptr;
+  bool order_valid = false, capturing = false;
+  int order_depth = 0;
+  size_t det_out_words = 0;
   // optional per-kernel CUDA-event timing (bench.py roofline): events recorded on the launch stream
   bool timing = false;
   struct Timed { const char* name; cudaEvent_t a, b; };
@@ -236,6 +245,23 @@ struct LaunchScope {
   }
 };
 
+// One giga_ctx owns ONE set of workspaces (activations, tile-dependency flags, planner volumes): calls are serialised in
+// submission order even when the caller alternates between streams (include/giga_b200.h, "Streams").  Nested entry points
+// (giga_forward -> giga_encode ...) only act at the outermost level; inside a stream capture the guard is off (the capture
+// stream is private to the ctx and the replay is guarded by the enclosing call).
+struct OrderScope {
+  giga_ctx* ctx; cudaStream_t st;
+  OrderScope(giga_ctx* c, cudaStream_t s) : ctx(c), st(s) {
+    if (ctx->order_depth++ == 0 && !ctx->capturing && ctx->order_valid && ctx->order_stream != st) cudaStreamWaitEvent(st, ctx->ev_order, 0);
+  }
+  ~OrderScope() {
+    if (--ctx->order_depth == 0 && !ctx->capturing) {
+      if (!ctx->ev_order) cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming);
+      if (ctx->ev_order && cudaEventRecord(ctx->ev_order, st) == cudaSuccess) { ctx->order_stream = st; ctx->order_valid = true; }
+    }
+  }
+};
+
 // Launch on the fast path: with ctx->pdl the kernel carries the programmatic-stream-serialization attribute, i.e. it may
 // start (up to its griddepcontrol.wait) while the previous kernel in the stream is still running (common.cuh).
 template <typename... KArgs, typename... Args>
@@ -264,7 +290,7 @@ int ensure_attrs(giga_ctx* ctx) {
     if (getenv("GIGA_VERBOSE")) fprintf(stderr, "[giga] conv_in_tc occupancy: %d CTAs/SM\n", nb);
   }
   CU_TRY(cudaFuncSetAttribute(decode_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
-  CU_TRY(cudaFuncSetAttribute(decode_points_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(decode_points_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(sample_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
 #define SET_CONV(K) CU_TRY(cudaFuncSetAttribute(conv3x3_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES))
   SET_CONV(K_d0c1); SET_CONV(K_d0c2); SET_CONV(K_d1c1); SET_CONV(K_d1c2); SET_CONV(K_d2c1);
@@ -500,7 +526,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_heads_tc, ctx->d_pre, ctx->d_xzpart, ctx->d_planes, ctx->d_elem, reinterpret_cast<float*>(ctx->d_flags)};
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_pre, ctx->d_xzpart, ctx->d_planes, ctx->d_elem, reinterpret_cast<float*>(ctx->d_flags)};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : ctx->slot) {
@@ -515,6 +541,11 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (ctx->st_compute) cudaStreamDestroy(ctx->st_compute);
   if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
   if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+  if (ctx->d_hc) cudaFree(ctx->d_hc);
+  if (ctx->d_sched) cudaFree(ctx->d_sched);
+  if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
+  for (auto& b : ctx->d_wblob)
+    if (b) cudaFree(b);
   for (auto& g : ctx->det_graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (ctx->st_graph) cudaStreamDestroy(ctx->st_graph);
@@ -540,6 +571,7 @@ int giga_ctx_set_param(giga_ctx* ctx, const char* name, const float* data, long 
   std::vector<float>& v = ctx->raw[name];
   v.resize(numel);
   if (on_device) {
+    CU_TRY(cudaDeviceSynchronize());   // the producer of `data` may run on a non-blocking stream the legacy-stream copy does not wait for
     CU_TRY(cudaMemcpy(v.data(), data, sizeof(float) * numel, cudaMemcpyDeviceToHost));
   } else {
     memcpy(v.data(), data, sizeof(float) * numel);
@@ -556,6 +588,7 @@ int giga_ctx_set_params_flat(giga_ctx* ctx, int n, const char* const* names, con
   const float* src = flat;
   if (on_device) {
     host.resize(total);
+    CU_TRY(cudaDeviceSynchronize());   // see giga_ctx_set_param
     CU_TRY(cudaMemcpy(host.data(), flat, sizeof(float) * total, cudaMemcpyDeviceToHost));
     src = host.data();
   }
@@ -572,6 +605,9 @@ int giga_ctx_set_params_flat(giga_ctx* ctx, int n, const char* const* names, con
 int giga_ctx_commit_params(giga_ctx* ctx) {
   if (!ctx) return fail(GIGA_EINVAL, "giga_ctx_commit_params: ctx is null");
   if (int r = set_device(ctx)) return r;
+  // the packed blobs below are overwritten with synchronous copies on the legacy stream, which does not order against the non-blocking
+  // streams kernels of this ctx may still be running on (torch side streams, the pipelined host path): drain the device first
+  CU_TRY(cudaDeviceSynchronize());
   const float* w;
   const float* b;
   // ---- encoder ----
@@ -672,8 +708,8 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
   }
   // ---- decoder heads ----
   std::vector<float> hb((size_t)4 * DW_HEAD, 0.f);
-  std::vector<float> tb((size_t)4 * TW_HEAD, 0.f);
   unsigned heads = 0;
+  int head_sexp[4] = {0, 0, 0, 0};
   for (int h = 0; h < 4; ++h) {
     const std::string pre = std::string("decoder_") + kHeadName[h] + ".";
     if (!ctx->raw.count(pre + "fc_p.weight")) continue;
@@ -711,9 +747,8 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       for (int k = 0; k < 32; ++k) H[DW_OUT + k * 4 + m] = w[m * 32 + k];
       H[DW_OUT + 128 + m] = b[m];
     }
-    // tensor-core blob: the same parameters, pre-scaled by 2^s and split into fp16 hi/lo pairs in UMMA operand layout
-    float* T = tb.data() + (size_t)h * TW_HEAD;
-    memcpy(T + TW_FCP, H + DW_FCP, sizeof(float) * 128);
+    // per-head power-of-two weight pre-scale of the tensor-core decoder: max |w| * 2^s in [512, 1024), so that the hi/lo fp16 halves of
+    // every non-negligible weight are normal fp16 numbers
     float wmax = 0.f;
     for (int i = 0; i < 5; ++i) {
       const std::string si = std::to_string(i);
@@ -724,7 +759,7 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
         for (int e = 0; e < 32 * 32; ++e) wmax = fmaxf(wmax, fabsf(w[e]));
       }
     }
-    int sexp = 0;   // max |w| * 2^s in [512, 1024): hi/lo halves of every non-negligible weight are normal fp16 numbers
+    int sexp = 0;
     if (wmax > 0.f && std::isfinite(wmax)) {
       int e;
       frexpf(wmax, &e);           // wmax = m * 2^e, m in [0.5, 1)
@@ -732,51 +767,77 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       if (sexp < -14) sexp = -14;
       if (sexp > 24) sexp = 24;
     }
-    const float wscale = ldexpf(1.f, sexp);
-    T[TW_INV] = ldexpf(1.f, -sexp);
-    uint16_t* T16 = reinterpret_cast<uint16_t*>(T);
-    for (int i = 0; i < 5; ++i) {
-      const std::string si = std::to_string(i);
-      need("fc_c." + si + ".weight", 32 * 96, &w);
-      need("fc_c." + si + ".bias", 32, &b);
-      for (int j = 0; j < 32; ++j) {
-        for (int k96 = 0; k96 < 96; ++k96) {
-          const int pl = k96 / 32, k = k96 % 32, n = i * 32 + j;
-          uint16_t hi, lo;
-          split_half_host(w[j * 96 + k96] * wscale, hi, lo, 1.f);
-          uint16_t* S = T16 + 2 * (TW_FCC + pl * 2 * TW_FCC_SLICE);      // halfs: [k/8][n 160][8]
-          S[(k / 8) * 1280 + n * 8 + (k % 8)] = hi;
-          S[2 * TW_FCC_SLICE + (k / 8) * 1280 + n * 8 + (k % 8)] = lo;
-        }
-        T[TW_BC + i * 32 + j] = b[j];
-      }
-      float* Bk = T + TW_BLK + i * TW_BLK_SIZE;
-      uint16_t* Bk16 = reinterpret_cast<uint16_t*>(Bk);                  // W0hi W0lo W1hi W1lo, 1024 halfs each: [k/8][n 32][8]
-      for (int f = 0; f < 2; ++f) {
-        const std::string fn = "blocks." + si + ".fc_" + std::to_string(f);
-        need(fn + ".weight", 32 * 32, &w);
-        need(fn + ".bias", 32, &b);
-        for (int j = 0; j < 32; ++j) {
-          for (int k = 0; k < 32; ++k) {
-            uint16_t hi, lo;
-            split_half_host(w[j * 32 + k] * wscale, hi, lo, 1.f);
-            Bk16[f * 2048 + (k / 8) * 256 + j * 8 + (k % 8)] = hi;
-            Bk16[f * 2048 + 1024 + (k / 8) * 256 + j * 8 + (k % 8)] = lo;
-          }
-          Bk[2048 + f * 32 + j] = b[j];
-        }
-      }
-    }
-    memcpy(T + TW_OUT, H + DW_OUT, sizeof(float) * 132);
+    head_sexp[h] = sexp;
     heads |= 1u << h;
   }
-  if (!ctx->d_heads_tc) CU_TRY(cudaMalloc(&ctx->d_heads_tc, sizeof(float) * 4 * TW_HEAD));
-  CU_TRY(cudaMemcpy(ctx->d_heads_tc, tb.data(), sizeof(float) * 4 * TW_HEAD, cudaMemcpyHostToDevice));
+  {
+    // ---- warp-specialised decoder (decoder_ws.cuh): head constants + one streamed weight blob per job type ----
+    std::vector<float> hc((size_t)4 * HC_SIZE, 0.f);
+    for (int h = 0; h < 4; ++h) {
+      if (!(heads & (1u << h))) continue;
+      const float* H = hb.data() + (size_t)h * DW_HEAD;
+      float* D = hc.data() + (size_t)h * HC_SIZE;
+      memcpy(D + HC_FCP, H + DW_FCP, sizeof(float) * 128);
+      memcpy(D + HC_OUT, H + DW_OUT, sizeof(float) * 132);
+      memcpy(D + HC_B1, H + DW_BLOCK0 + 4 * DW_BLK + DW_BLK_B1, sizeof(float) * 32);
+      D[HC_INV] = ldexpf(1.f, -head_sexp[h]);
+    }
+    if (!ctx->d_hc) CU_TRY(cudaMalloc(&ctx->d_hc, sizeof(float) * 4 * HC_SIZE));
+    CU_TRY(cudaMemcpy(ctx->d_hc, hc.data(), sizeof(float) * 4 * HC_SIZE, cudaMemcpyHostToDevice));
+    if (!ctx->d_sched) {
+      CU_TRY(cudaMalloc(&ctx->d_sched, sizeof(unsigned) * 4));
+      CU_TRY(cudaMemset(ctx->d_sched, 0, sizeof(unsigned) * 4));
+    }
+    for (int type = 0; type < 5; ++type) {
+      const int nh = type == 0 ? 3 : 1, head0 = type == 0 ? 0 : type - 1;
+      const unsigned need = type == 0 ? 7u : (1u << head0);
+      if ((heads & need) != need) {
+        if (ctx->d_wblob[type]) { cudaFree(ctx->d_wblob[type]); ctx->d_wblob[type] = nullptr; }
+        continue;
+      }
+      std::vector<uint8_t> blob((size_t)5 * wd_block_bytes(nh), 0);
+      for (int blk = 0; blk < 5; ++blk) {
+        uint8_t* base = blob.data() + (size_t)blk * wd_block_bytes(nh);
+        uint16_t* fcc = reinterpret_cast<uint16_t*>(base);                         // [hi|lo][kc 12][n nh*32][8]
+        uint16_t* ch = reinterpret_cast<uint16_t*>(base + wd_fcc_bytes(nh));       // W0 [head][hi|lo][kc 4][n 32][8], W1 same
+        float* bias = reinterpret_cast<float*>(base + wd_fcc_bytes(nh) + nh * 8192);   // b0 [nh][32], bin [nh][32]
+        for (int c = 0; c < nh; ++c) {
+          const float* Hb = hb.data() + (size_t)(head0 + c) * DW_HEAD + DW_BLOCK0 + blk * DW_BLK;   // input-major fp32 copies: Wt[k][j]
+          const float wscale = ldexpf(1.f, head_sexp[head0 + c]);
+          for (int k = 0; k < 96; ++k)
+            for (int j = 0; j < 32; ++j) {
+              uint16_t hi, lo;
+              split_half_host(Hb[DW_BLK_FCC + k * 32 + j] * wscale, hi, lo, 1.f);
+              const size_t e = ((size_t)(k / 8) * (nh * 32) + c * 32 + j) * 8 + (k % 8);
+              fcc[e] = hi;
+              fcc[(size_t)12 * nh * 32 * 8 + e] = lo;
+            }
+          const int woff[2] = {DW_BLK_W0, DW_BLK_W1};
+          for (int f = 0; f < 2; ++f)
+            for (int k = 0; k < 32; ++k)
+              for (int j = 0; j < 32; ++j) {
+                uint16_t hi, lo;
+                split_half_host(Hb[woff[f] + k * 32 + j] * wscale, hi, lo, 1.f);
+                const size_t e = (size_t)f * nh * 2048 + (size_t)c * 2048 + (k / 8) * 256 + j * 8 + (k % 8);
+                ch[e] = hi;
+                ch[e + 1024] = lo;
+              }
+          for (int j = 0; j < 32; ++j) {
+            bias[c * 32 + j] = Hb[DW_BLK_B0 + j];
+            bias[nh * 32 + c * 32 + j] = Hb[DW_BLK_BC + j] + (blk > 0 ? Hb[DW_BLK_B1 + j - DW_BLK] : 0.f);   // bc_b + b1_{b-1}
+          }
+        }
+      }
+      if (!ctx->d_wblob[type]) CU_TRY(cudaMalloc(&ctx->d_wblob[type], blob.size()));
+      CU_TRY(cudaMemcpy(ctx->d_wblob[type], blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    }
+  }
   if (!ctx->d_heads) CU_TRY(cudaMalloc(&ctx->d_heads, sizeof(float) * 4 * DW_HEAD));
   CU_TRY(cudaMemcpy(ctx->d_heads, hb.data(), sizeof(float) * 4 * DW_HEAD, cudaMemcpyHostToDevice));
   ctx->heads = heads;
   if (!ctx->has_encoder && !heads) return fail(GIGA_ESTATE, "giga_ctx_commit_params: no parameters were set");
   if (int r = ensure_attrs(ctx)) return r;
+  CU_TRY(cudaDeviceSynchronize());   // pageable-source copies may still be in flight when cudaMemcpy returns
   ctx->committed = true;
   ctx->graph_epoch++;   // conv_in's weights are kernel parameters (baked into captured graphs)
   return GIGA_OK;
@@ -790,6 +851,7 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
   if (int r = set_device(ctx)) return r;
   if (int r = ensure_workspace(ctx, B)) return r;
   cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);
   const int n_img = 3 * B;
   if (ctx->d_layer_times) {   // debug: (re)initialise the envelopes: min fields to ~0, max fields to 0
     static const unsigned long long init[64] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0,
@@ -921,27 +983,69 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
 
 namespace {
 
+// warp-specialised decoder (decoder_ws.cuh): one persistent launch for up to WD_MAX_JOBS jobs
+int launch_decode_ws(giga_ctx* ctx, const float* planes, int B, const float* const* pts, const int* Ns, const unsigned* masks, int nsets, bool raw,
+                     float* qual, float* rot, float* width, float* occ, cudaStream_t st, const char* name) {
+  DecArgs a = {};
+  int nj = 0, items = 0;
+  auto add = [&](const float* p, int N, int type) {
+    DecJob& j = a.job[nj++];
+    j.pts = p; j.N = N; j.type = type; j.tiles = ceil_div(N, WD_PTS); j.item0 = items;
+    items += B * j.tiles;
+  };
+  // heavy (3-head) jobs first: items are handed out in index order, so the tail of the launch consists of short items
+  for (int s = 0; s < nsets; ++s)
+    if ((masks[s] & 7u) == 7u && ctx->d_wblob[0]) add(pts[s], Ns[s], 0);
+  for (int s = 0; s < nsets; ++s) {
+    const unsigned single = ((masks[s] & 7u) == 7u && ctx->d_wblob[0]) ? (masks[s] & 8u) : (masks[s] & 15u);
+    for (int h = 0; h < 4; ++h)
+      if (single & (1u << h)) {
+        if (nj >= WD_MAX_JOBS) return fail(GIGA_EINVAL, "launch_decode_ws: too many jobs for one launch");
+        add(pts[s], Ns[s], 1 + h);
+      }
+  }
+  a.njobs = nj; a.n_items = items; a.B = B; a.raw = raw ? 1u : 0u;
+  a.planes = planes; a.hc = ctx->d_hc;
+  for (int t = 0; t < 5; ++t) a.wblob[t] = ctx->d_wblob[t];
+  a.qual = qual; a.rot = rot; a.width = width; a.occ = occ;
+  a.sched = ctx->d_sched;
+  const int grid = items < ctx->num_sms ? items : ctx->num_sms;
+  a.tl = nullptr;
+  a.debug = getenv("GIGA_DEC_DEBUG") ? (unsigned)atoi(getenv("GIGA_DEC_DEBUG")) : 0u;
+  if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, "decode")) {
+    const size_t n = (size_t)grid * 32;
+    if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+    cudaMalloc(&ctx->d_timeline, n * 8);
+    cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
+    ctx->timeline_n = (long)n;
+    a.tl = ctx->d_timeline;
+  }
+  LaunchScope ls(ctx, name, st);
+  launch_k(ctx, decode_points_ws_kernel, dim3(grid), dim3(WD_THREADS), WD_SMEM_BYTES, st, a);
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
 // one decoder launch for up to two jobs (heads at points / heads2 at points2); validation is the callers' job
 int launch_decode(giga_ctx* ctx, const float* planes, int B, const float* points, int N, unsigned heads, const float* points2, int N2,
                   unsigned heads2, float* qual, float* rot, float* width, float* occ, cudaStream_t st) {
   const bool two = points2 && N2 > 0;
-  if (two && ctx->decoder_impl != 1) return fail(GIGA_EINVAL, "launch_decode: merged jobs need the tensor-core decoder");
+  if (two && ctx->decoder_impl == 0) return fail(GIGA_EINVAL, "launch_decode: merged jobs need a tensor-core decoder");
   const char* name = two ? "decode_points:grasp+tsdf" : ((heads & 15u) == GIGA_HEAD_TSDF ? "decode_points:tsdf" : "decode_points:grasp");
-  LaunchScope ls(ctx, name, st);
   if (ctx->decoder_impl == 1) {
-    const int tiles1 = ceil_div(N, TD_PTS), tiles2 = two ? ceil_div(N2, TD_PTS) : 0;
-    unsigned long long* tl = nullptr;
-    if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, "decode")) {
-      const size_t n = (size_t)(tiles1 + tiles2) * B * 32;
-      if (ctx->d_timeline) cudaFree(ctx->d_timeline);
-      cudaMalloc(&ctx->d_timeline, n * 8);
-      cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
-      ctx->timeline_n = (long)n;
-      tl = ctx->d_timeline;
+    const float* pts[2] = {points, points2};
+    const int Ns[2] = {N, N2};
+    const unsigned masks[2] = {heads & 15u, heads2 & 15u};
+    const bool raw = (heads & 16u) != 0;
+    auto njobs = [&](unsigned m) { return ((m & 7u) == 7u && ctx->d_wblob[0]) ? 1 + ((m >> 3) & 1) : __builtin_popcount(m); };
+    if (two && njobs(masks[0]) + njobs(masks[1]) > WD_MAX_JOBS) {   // rare head combinations: one launch per point set
+      if (int r = launch_decode_ws(ctx, planes, B, pts, Ns, masks, 1, raw, qual, rot, width, occ, st, name)) return r;
+      return launch_decode_ws(ctx, planes, B, pts + 1, Ns + 1, masks + 1, 1, raw, qual, rot, width, occ, st, name);
     }
-    launch_k(ctx, decode_points_tc_kernel, dim3((tiles1 + tiles2) * B), dim3(TD_PTS), TD_SMEM_BYTES, st, planes, points,
-             (const float*)ctx->d_heads_tc, B, N, heads, qual, rot, width, occ, points2, two ? N2 : 0, heads2, tiles1, tl);
-  } else {
+    return launch_decode_ws(ctx, planes, B, pts, Ns, masks, two ? 2 : 1, raw, qual, rot, width, occ, st, name);
+  }
+  LaunchScope ls(ctx, name, st);
+  {
     decode_points_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(planes, points, ctx->d_heads, B, N, heads, qual, rot,
                                                                                          width, occ);
   }
@@ -963,6 +1067,7 @@ int giga_decode(giga_ctx* ctx, const float* planes, int B, const float* points, 
       ((heads & GIGA_HEAD_TSDF) && !occ))
     return fail(GIGA_EINVAL, "giga_decode: output pointer of a requested head is null");
   if (int r = set_device(ctx)) return r;
+  OrderScope order(ctx, (cudaStream_t)stream);
   return launch_decode(ctx, planes, B, points, N, heads, nullptr, 0, 0u, qual, rot, width, occ, (cudaStream_t)stream);
 }
 
@@ -972,6 +1077,7 @@ int giga_sample_feature(giga_ctx* ctx, const float* planes, int B, const float* 
     return fail(GIGA_EINVAL, "giga_sample_feature: bad argument");
   if (int r = set_device(ctx)) return r;
   if (int r = ensure_attrs(ctx)) return r;
+  OrderScope order(ctx, (cudaStream_t)stream);
   {
     LaunchScope ls(ctx, "sample_feature", (cudaStream_t)stream);
     sample_feature_kernel<<<dim3(ceil_div(N, DEC_PTS), B), DEC_PTS, SF_SMEM_BYTES, (cudaStream_t)stream>>>(planes, points, B, N, mode, out);
@@ -983,6 +1089,7 @@ int giga_sample_feature(giga_ctx* ctx, const float* planes, int B, const float* 
 int giga_scene_argmax(giga_ctx* ctx, const float* qual, int B, int N, float* best_val, int* best_idx, void* stream) {
   if (!ctx || !qual || !best_val || !best_idx || B <= 0 || N <= 0) return fail(GIGA_EINVAL, "giga_scene_argmax: bad argument");
   if (int r = set_device(ctx)) return r;
+  OrderScope order(ctx, (cudaStream_t)stream);
   {
     LaunchScope ls(ctx, "scene_argmax", (cudaStream_t)stream);
     launch_k(ctx, scene_argmax_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, qual, N, best_val, best_idx);
@@ -998,8 +1105,9 @@ int giga_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, int Ng
   if (!grasp && !geo) return fail(GIGA_EINVAL, "giga_forward: no query points");
   if ((best_val || best_idx) && !(grasp && best_val && best_idx && qual))
     return fail(GIGA_EINVAL, "giga_forward: the arg-max needs the grasp heads and both best_val and best_idx");
+  if (int r = set_device(ctx)) return r;
+  OrderScope order(ctx, (cudaStream_t)stream);
   if (!planes) {
-    if (int r = set_device(ctx)) return r;
     if (B > ctx->planes_cap) {
       ctx->graph_epoch++;
       CU_TRY(cudaDeviceSynchronize());
@@ -1014,7 +1122,7 @@ int giga_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, int Ng
   if (int r = giga_encode(ctx, tsdf, B, planes, stream)) return r;
   const unsigned hm = ctx->heads & (GIGA_HEAD_QUAL | GIGA_HEAD_ROT | GIGA_HEAD_WIDTH);
   if (grasp && !hm) return fail(GIGA_ESTATE, "giga_forward: no grasp head committed (pass p = NULL for giga_geo)");
-  if (grasp && geo && ctx->decoder_impl == 1 && ctx->merge_decode) {   // both point sets in ONE launch (long 3-head tiles first, TSDF tiles fill the tail)
+  if (grasp && geo && ctx->decoder_impl >= 1 && ctx->merge_decode) {   // both point sets in ONE launch (long 3-head tiles first, TSDF tiles fill the tail)
     if (!(ctx->heads & GIGA_HEAD_TSDF)) return fail(GIGA_ESTATE, "giga_forward: no TSDF head committed");
     if (!occ || ((hm & GIGA_HEAD_QUAL) && !qual) || ((hm & GIGA_HEAD_ROT) && !rot) || ((hm & GIGA_HEAD_WIDTH) && !width))
       return fail(GIGA_EINVAL, "giga_forward: output pointer of a requested head is null");
@@ -1226,7 +1334,8 @@ int ensure_planner_ws(giga_ctx* ctx, int B) {
 }
 
 int ensure_detect_ws(giga_ctx* ctx, int B, int K) {
-  if (B > ctx->det_cap_B || (long)B * K > (long)ctx->det_cap_K) ctx->graph_epoch++;
+  const size_t out_words_needed = (size_t)B + 7 * (size_t)B * K;
+  if (B > ctx->det_cap_B || out_words_needed > ctx->det_out_words) ctx->graph_epoch++;
   if (B > ctx->det_cap_B) {
     CU_TRY(cudaDeviceSynchronize());
     void** ptrs[] = {(void**)&ctx->d_det_pts, (void**)&ctx->d_det_qual, (void**)&ctx->d_det_rot, (void**)&ctx->d_det_width,
@@ -1242,12 +1351,13 @@ int ensure_detect_ws(giga_ctx* ctx, int B, int K) {
     CU_TRY(cudaMalloc(&ctx->d_det_tsdfp, vol));
     ctx->det_cap_B = B;
   }
-  if ((long)B * K > (long)ctx->det_cap_K) {
+  if (out_words_needed > ctx->det_out_words) {   // B + 7*B*K words: compare the word count itself ((B, K) pairs with equal B*K differ in B)
     CU_TRY(cudaDeviceSynchronize());
     if (ctx->d_det_out) cudaFree(ctx->d_det_out);
     ctx->d_det_out = nullptr;
-    ctx->det_cap_K = 0;
-    CU_TRY(cudaMalloc(&ctx->d_det_out, sizeof(int) * ((size_t)B + 7 * (size_t)B * K)));
+    ctx->det_out_words = 0;
+    CU_TRY(cudaMalloc(&ctx->d_det_out, sizeof(int) * out_words_needed));
+    ctx->det_out_words = out_words_needed;
     ctx->det_cap_K = B * K;
   }
   return GIGA_OK;
@@ -1269,6 +1379,7 @@ int giga_select_grasps(giga_ctx* ctx, const float* tsdf, const float* qual, cons
   if (int r = set_device(ctx)) return r;
   if (int r = ensure_planner_ws(ctx, B)) return r;
   cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);
   const int blocks = ceil_div(B * G3, 256);
   int *flag = ctx->d_pl_flag, *cnt = ctx->d_pl_flag + B;
   CU_TRY(cudaMemsetAsync(flag, 0, sizeof(int) * 2 * B, st));
@@ -1303,6 +1414,7 @@ int giga_detect(giga_ctx* ctx, const float* tsdf, const float* tsdf_process, int
   if (int r = set_device(ctx)) return r;
   if (int r = ensure_detect_ws(ctx, B, K)) return r;
   cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);
   if (ctx->det_lat_B < B) {
     LaunchScope ls(ctx, "planner:broadcast_lattice", st);
     broadcast_points_kernel<<<ceil_div(3 * G3, 256), 256, 0, st>>>(ctx->d_lattice, ctx->d_det_pts, 3 * G3, ctx->det_cap_B);
@@ -1322,6 +1434,7 @@ int giga_detect_host(giga_ctx* ctx, const float* tsdf, const float* tsdf_process
   if (int r = set_device(ctx)) return r;
   if (int r = ensure_detect_ws(ctx, B, K)) return r;
   cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);   // covers the graph replay on `st`; the capture itself runs with the guard off
   const size_t vol = sizeof(float) * (size_t)B * G3, bk = (size_t)B * K, out_words = 7 * bk + B;
   // pinned staging: the call is ONE H2D (+1 with a separate tsdf_process), the kernels, ONE D2H of B*(1+7K) words
   if (B <= 4 && 2 * vol > ctx->h_det_in_cap) {
@@ -1396,7 +1509,9 @@ int giga_detect_host(giga_ctx* ctx, const float* tsdf, const float* tsdf_process
       if (!ctx->st_graph) CU_TRY(cudaStreamCreateWithFlags(&ctx->st_graph, cudaStreamNonBlocking));
       const long l0 = ctx->launches;
       CU_TRY(cudaStreamBeginCapture(ctx->st_graph, cudaStreamCaptureModeThreadLocal));
+      ctx->capturing = true;
       const int r = enqueue(ctx->st_graph);
+      ctx->capturing = false;
       cudaGraph_t graph = nullptr;
       const cudaError_t ce = cudaStreamEndCapture(ctx->st_graph, &graph);
       if (r) { if (graph) cudaGraphDestroy(graph); return r; }
@@ -1433,6 +1548,19 @@ int giga_detect_host(giga_ctx* ctx, const float* tsdf, const float* tsdf_process
 
 long giga_ctx_launch_count(const giga_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+long giga_ctx_overflow_count(giga_ctx* ctx, int reset) {
+  if (!ctx) return fail(GIGA_EINVAL, "giga_ctx_overflow_count: ctx is null");
+  if (!ctx->d_sched) return 0;
+  if (int r = set_device(ctx)) return r;
+  CU_TRY(cudaDeviceSynchronize());
+  unsigned n = 0;
+  CU_TRY(cudaMemcpy(&n, ctx->d_sched + 2, sizeof n, cudaMemcpyDeviceToHost));
+  if (reset && n) CU_TRY(cudaMemset(ctx->d_sched + 2, 0, sizeof n));
+  if (n) g_err = "giga: " + std::to_string(n) + " decoder outputs were not finite: an activation or plane feature left fp16's +-65504 operand range "
+                 "(or an input was not finite); use decoder_impl 0 (fp32 FMA pipe) for such weights";
+  return (long)n;
+}
+
 int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
   if (!ctx || !key) return fail(GIGA_EINVAL, "giga_ctx_set_option: bad argument");
   ctx->graph_epoch++;
@@ -1442,7 +1570,7 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
     return GIGA_OK;
   }
   if (!strcmp(key, "decoder_impl")) {
-    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "decoder_impl must be 0 (fp32 FMA) or 1 (tcgen05 3xFP16)");
+    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "decoder_impl must be 0 (fp32 FMA pipe) or 1 (warp-specialised tcgen05 3xFP16)");
     ctx->decoder_impl = value;
     return GIGA_OK;
   }
@@ -1512,6 +1640,7 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
   if (!ctx || !name || !dst) return fail(GIGA_EINVAL, "giga_debug_copy: bad argument");
   if (ctx->last_B <= 0 && strcmp(name, "timeline")) return fail(GIGA_ESTATE, "giga_debug_copy: no giga_encode call yet");
   if (int r = set_device(ctx)) return r;
+  OrderScope order(ctx, (cudaStream_t)stream);
   const float* src = nullptr;
   long numel = 0;
   if (!strcmp(name, "layer_times")) {

@@ -64,7 +64,8 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-// Bounded wait: a wrong descriptor must trap, never hang the GPU.
+// Bounded wait: a wrong descriptor must trap, never hang the GPU.  Plain try_wait (hardware-default suspend window): an explicit
+// suspend-time hint was measured 2x slower per hand-off (tools/tc_hop_probe.cu: 1679 vs 933 cycles per layer round trip).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
   for (int i = 0; i < (1 << 24) && !ok; ++i) {
@@ -72,6 +73,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(ok)
                  : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");
+  }
+  if (!ok) __trap();
+}
+// Same, for roles that wait LONG and off the critical path (producers waiting for a free buffer): back off between polls so the
+// spinning warp does not take issue slots / mbarrier-unit bandwidth from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned sleep_ns = 256) {
+  uint32_t ok = 0;
+  for (int i = 0; i < (1 << 22) && !ok; ++i) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    if (!ok) __nanosleep(sleep_ns);
   }
   if (!ok) __trap();
 }

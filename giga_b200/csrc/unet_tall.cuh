@@ -156,6 +156,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// One arrival per WARP (the barrier's count is in warps): 32 per-thread arrivals are 32 serialised shared-memory atomics on one word;
+// tools/tc_hop_probe.cu measured ~300 cycles per hand-off for 256 arriving threads.  Each lane orders its own prior accesses with its
+// fence, the warp barrier orders the lanes before the elected lane's release.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 }  // namespace tc
 
 // MODE 0: 3x3 conv + bias + ReLU, same resolution (unet.py conv3x3 + F.relu)
@@ -309,7 +316,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
   uint64_t* z_empty = z_full + 2;
   uint64_t* wbar = z_empty + 2;
   uint64_t* fin_bar = wbar + 1;
-  uint64_t* pub_bar = fin_bar + 1;   // 128 epilogue arrivals per item -> publisher warp (LayerDep)
+  uint64_t* pub_bar = fin_bar + 1;   // 4 epilogue-warp arrivals per item -> publisher warp (LayerDep)
   uint64_t* item_bar = pub_bar + 1;  // [8] the loader has published item j (ring slot j & 7)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::OFF_BAR + P::NBAR * 8);
   // Items (M-tile group x N tile) are handed out by the loader warp: from a global counter when dep.work is set (the CTAs that
@@ -334,10 +341,10 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], P::NMMAW); }   // every MMA warp releases a stage
     tc::mbar_init(&acc_full[0], 1); tc::mbar_init(&acc_full[1], 1);
-    tc::mbar_init(&acc_empty[0], 128); tc::mbar_init(&acc_empty[1], 128);
+    tc::mbar_init(&acc_empty[0], 4); tc::mbar_init(&acc_empty[1], 4);   // drain side: one arrival per warp
     tc::mbar_init(&z_full[0], P::NMMAW - 1); tc::mbar_init(&z_full[1], P::NMMAW - 1);
-    tc::mbar_init(&z_empty[0], 128); tc::mbar_init(&z_empty[1], 128);
-    tc::mbar_init(wbar, 1); tc::mbar_init(fin_bar, 1); tc::mbar_init(pub_bar, 128);
+    tc::mbar_init(&z_empty[0], 4); tc::mbar_init(&z_empty[1], 4);
+    tc::mbar_init(wbar, 1); tc::mbar_init(fin_bar, 1); tc::mbar_init(pub_bar, 4);
     for (int i = 0; i < 8; ++i) tc::mbar_init(&item_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -547,7 +554,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
             }
           }
         tc::fence_before_sync();
-        tc::mbar_arrive(&acc_empty[set]);
+        tc::warp_arrive(&acc_empty[set]);
         w_b += clock64() - t_d;
       }
       const long long t_e = clock64();
@@ -569,7 +576,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           }
         }
       tc::fence_before_sync();
-      tc::mbar_arrive(&z_empty[zp]);
+      tc::warp_arrive(&z_empty[zp]);
       tc::named_bar_sync(1, 128);   // sbias visible to all epilogue threads (and previous tile's readers are done)
 
 #pragma unroll
@@ -663,7 +670,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           tc::named_bar_sync(1, 128);   // scratch / final accumulator free for the next M tile
         }
       }
-      if (dep.ready_out) tc::mbar_arrive(pub_bar);   // this thread's stores of the item are done -> publisher warp
+      if (dep.ready_out) tc::warp_arrive(pub_bar);   // this warp's stores of the item are done -> publisher warp
       tc::named_bar_sync(1, 128);   // everyone is done with sbias before the next item overwrites it
       w_c += clock64() - t_e;
     }

@@ -121,6 +121,11 @@ class LocalDecoder(nn.Module):  # conv_onet/models/decoder.py:61-206 (concat_fea
         self.__dict__["_owner"] = None   # weakref to the model whose engine evaluates this head
         self.__dict__["_head_bit"] = 0
 
+    def __getstate__(self):   # the owner back-reference is rebound by the owning model (copy.deepcopy / pickle)
+        d = self.__dict__.copy()
+        d["_owner"] = None
+        return d
+
     def forward(self, p, c_plane, **kwargs):
         """decoder.py:133-176 -- the bare head output (no sigmoid / normalise): (B,N) or (B,N,4)."""
         owner = self._owner() if self._owner is not None else None
@@ -162,8 +167,15 @@ class _Engine:
         except Exception:
             pass
 
+    def invalidate(self):
+        """Forget the committed parameters: the next call re-packs and re-uploads all of them."""
+        self.param_key = None
+        self.struct_version = -1
+
     def sync_params(self, module: nn.Module):
-        # fast path (every call): the cached tensor objects still hold the committed storage and version
+        # fast path (every call): the cached tensor objects still hold the committed storage and version.
+        # NOTE: change detection is (storage pointer, tensor._version); in-place writes through `.data` / `.detach()` views
+        # made BEFORE the write do not bump the version counter -- call net.invalidate_params() after such writes.
         if self.struct_version == _STRUCT_VERSION[0] and self.param_key == tuple((v.data_ptr(), v._version) for v in self.tensors):
             return
         params = list(module.state_dict(keep_vars=True).items())
@@ -242,6 +254,34 @@ class _GigaBase(nn.Module):
         model = super().to(device)
         model._device = device
         return model
+
+    def invalidate_params(self):
+        """Force a re-commit of all parameters on the next call.  Parameter changes are detected through
+        (storage pointer, tensor._version): `optimizer.step()`, `load_state_dict`, `p.add_()`, `p.copy_()` are all seen.
+        Writes that bypass the version counter -- `p.data.copy_(ema)`, `p.data.clamp_()`, writes through a view taken with
+        `.detach()` -- are NOT; call this method after them (or the engine keeps evaluating the previously committed weights)."""
+        eng = self.__dict__.get("_eng")
+        if eng is not None:
+            eng.invalidate()
+        return self
+
+    def overflow_count(self, reset: bool = True) -> int:
+        """Number of non-finite head outputs the tensor-core decoder has produced since the last reset (an activation or plane
+        feature beyond fp16's +-65504 operand range turns the affected outputs into NaN; giga_ctx_overflow_count).  Synchronises."""
+        eng = self.__dict__.get("_eng")
+        return int(check(int(lib.giga_ctx_overflow_count(eng.h, int(reset))), "giga_ctx_overflow_count")) if eng else 0
+
+    # copy.deepcopy / pickle / torch.save(net): the ctypes engine is per-object device state, never copied; the copy builds its
+    # own on first use and its heads are re-bound to it (a copied head must not keep evaluating the original model's weights)
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        for k in ("_eng", "_inflight"):
+            d.pop(k, None)
+        return d
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._bind_heads()
 
     # -- training bridge (opt-in; see giga_b200/training.py) --------------------------------
     def enable_training_bridge(self, enabled: bool = True):

@@ -14,6 +14,13 @@
  *     leaves a message retrievable with giga_last_error() (thread local);
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all
  *     device work of a call is enqueued on it, nothing synchronises unless stated;
+ *   - Streams: a giga_ctx owns ONE set of device workspaces (activations, tile-dependency
+ *     counters, planner volumes), so its calls execute in SUBMISSION order: an entry point
+ *     called on a different stream than the previous one (including the internal streams of
+ *     giga_forward_host_submit) first makes its stream wait for the previous call's work
+ *     (event).  Calls from several host threads into one ctx must be serialised by the
+ *     caller; use one ctx per thread for concurrency.  giga_ctx_set_param*() and
+ *     giga_ctx_commit_params() drain the whole device before touching the parameters;
  *   - device tensors are dense fp32, layouts stated per argument.  There is NO CPU
  *     fallback: without a CUDA device every compute entry point fails with GIGA_ENODEV.
  *
@@ -175,8 +182,15 @@ int giga_detect_host(giga_ctx *ctx, const float *tsdf, const float *tsdf_process
 /* introspection ------------------------------------------------------------------- */
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 long giga_ctx_launch_count(const giga_ctx *ctx);
+/* Range guard of the tensor-core decoder.  Its operands are fp16 (hi, lo) pairs: a plane feature or hidden activation beyond
+ * +-65504 cannot be represented.  Such a value is never clamped silently: it becomes NaN, propagates to the head outputs of that
+ * query point (qual/rot/width/occ read NaN) and is counted on the device.  Returns the number of non-finite head outputs produced
+ * since the last reset (synchronises the device; giga_last_error() then holds a description), or a negative error.  The
+ * reference's fp32 path has no such limit (decoder.py:165-174); GIGA's activations are O(10). */
+long giga_ctx_overflow_count(giga_ctx *ctx, int reset);
 /* implementation switches (A/B testing; defaults are the fastest parity-clean variants):
- *   "decoder_impl": 1 = tcgen05 tensor cores with 3xFP16 operand splitting (default), 0 = fp32 FMA pipe
+ *   "decoder_impl": 1 = warp-specialised tcgen05 decoder, 3xFP16 operand splitting, A operand in tensor memory (default),
+ *                   0 = fp32 FMA pipe (no fp16 operand range limit: the fallback for giga_ctx_overflow_count() != 0)
  *   "encoder_impl": U-Net convolutions: 1 = tcgen05 3xFP16 with persistent CTAs (default), 0 = fp32 FMA pipe
  *   "conv_in_impl": fused Conv3d + plane means: 0 = fp32 FMA pipe (default), 1 = tcgen05 3xFP16 variant (same parity bar;
  *                   shared-memory-bandwidth bound, currently not faster)

@@ -180,3 +180,21 @@ def test_detect_graph_replay_equals_eager(net):
     assert not all(np.array_equal(a, b) for a, b in zip(eager2, eager[0]))
     with torch.no_grad():
         net.encoder.conv_in.bias.sub_(0.05)
+
+
+def test_detect_workspace_grows_with_batch_at_equal_bk(net):
+    """the grasp output buffer holds B + 7*B*K words; a later call with the same B*K but a larger B needs more
+    (here (1, 4K) -> (4, K): three more count words) and must re-allocate instead of writing past the end."""
+    from giga_b200.detection_implicit import detect_host, select_params
+    tsdfs = np.stack([P.seeded_volumes(200 + i)[0] for i in range(4)])
+    prm = select_params()
+    K = 512
+    a = detect_host(net, tsdfs[:1], None, prm, K=4 * K)
+    b = detect_host(net, tsdfs, None, prm, K=K)
+    for i in range(4):
+        c = detect_host(net, tsdfs[i:i + 1], None, prm, K=K)
+        n = int(c[0][0])
+        assert int(b[0][i]) == n and n <= K
+        for u, v in zip(b[1:], c[1:]):
+            assert np.array_equal(u[i][:n], v[0][:n])
+    assert int(a[0][0]) == int(b[0][0])

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Debug: in-kernel phase timeline of the tensor-core decoder.  GIGA_TIMELINE=decode python tools/decode_timeline.py"""
+"""Debug: in-kernel item timeline of the warp-specialised decoder (decoder_ws.cuh).
+GIGA_TIMELINE=decode python tools/decode_timeline.py   -> per CTA: stamps of the compute warpgroup (item start, 5 blocks, item end) for its first 4 items"""
 import ctypes as C
 import os
 import sys
@@ -19,9 +20,9 @@ net.load_state_dict(O.seeded_state_dict(seed=1))
 net = net.to("cuda:0")
 x = torch.rand(B, 40, 40, 40, device="cuda:0")
 p = torch.rand(B, N, 3, device="cuda:0") - 0.5
-c = net.encode_inputs(x)
+pt = torch.rand(B, N, 3, device="cuda:0") - 0.5
 for _ in range(3):
-    out = net.decode(p, c)       # 3 grasp heads
+    out = net(x, p, p_tsdf=pt)       # merged launch: 3 grasp heads + tsdf head
 torch.cuda.synchronize()
 eng = net._engine()
 buf = torch.zeros(8 << 20, dtype=torch.float32, device="cuda:0")
@@ -29,18 +30,19 @@ n = lib.giga_debug_copy(eng.h, b"timeline", C.c_void_p(buf.data_ptr()), buf.nume
 assert n > 0, lib.giga_last_error()
 torch.cuda.synchronize()
 t = buf[:n].cpu().numpy().view(np.uint64).reshape(-1, 32).astype(np.int64)
-t0 = t[:, 0].min()
-rel = (t - t0) / 1000.0
-order = np.argsort(t[:, 0])
-print("decode (3 heads) CTAs", len(t), "span us", rel[:, :26].max())
-for label, idx in (("first", order[0]), ("median", order[len(order) // 2]), ("last", order[-1])):
-    r = rel[idx] - rel[idx, 0]
-    k = [i for i in range(26) if t[idx, i] > 0]
-    print(f"-- {label} CTA {idx}: " + " ".join(f"{r[i]:.2f}" for i in k))
-d = rel[:, 1:26] - rel[:, 0:25]
-lab = ["gather"] + sum([[f"h{h}.pl{p}" for p in range(3)] + [f"h{h}.blk{b}" for b in range(5)] for h in range(3)], [])
-print("median phase durations us:")
-for i, l in enumerate(lab):
-    print(f"  {l:>8}: {np.median(d[:, i]):.2f}", end="" if (i + 1) % 4 else "\n")
-print()
-print("CTA start times (every 64th):", np.round(np.sort(rel[:, 0])[::64], 1))
+t0 = t[t > 0].min()
+rel = np.where(t > 0, (t - t0) / 1000.0, np.nan)
+print("decode_points_ws CTAs", len(t), "kernel span us %.2f" % np.nanmax(rel))
+ends = np.nanmax(rel, axis=1)
+print("CTA end times us: min %.1f median %.1f max %.1f" % (ends.min(), np.median(ends), ends.max()))
+lab = ["fc_p+blk0", "blk1", "blk2", "blk3", "blk4", "final"]
+for k in range(4):
+    seg = rel[:, 7 * k:7 * k + 7]
+    ok = ~np.isnan(seg).any(axis=1)
+    if not ok.any():
+        continue
+    d = np.diff(seg[ok], axis=1)
+    gap = seg[ok, 0] - rel[ok, 7 * k - 1] if k > 0 else seg[ok, 0]
+    print(f"item ordinal {k}: {ok.sum()} CTAs, start median {np.median(seg[ok, 0]):.1f} us (gap after previous item {np.median(gap):.2f}), "
+          f"duration median {np.median(seg[ok, 6] - seg[ok, 0]):.2f} (min {np.min(seg[ok, 6] - seg[ok, 0]):.2f}, max {np.max(seg[ok, 6] - seg[ok, 0]):.2f})")
+    print("   phases: " + "  ".join(f"{l} {np.median(d[:, i]):.2f}" for i, l in enumerate(lab)))
