@@ -14,8 +14,16 @@
 //                                 per CTA (deterministic order; finished by xz_finish_kernel)
 // Weights (27x32) + bias live in the kernel parameter space (constant bank): every FFMA takes
 // its weight as an immediate constant-bank operand, so the inner loop is pure FFMA.
+// TSDF staging: a 4-D TMA tensor map over x[b][ix][iy][iz] (cuTensorMapEncodeTiled on the host, cp.async.bulk.tensor.4d -> UTMALDG in SASS):
+// per march step ONE thread fetches the next ix slab of the CTA's rows plus a one-voxel halo -- box {48 iz, TY + 2 iy, 1 ix, 1 scene} at
+// (iz -4, iy0 - 1, ix, b) -- into a 4-deep shared-memory ring, completion on an mbarrier; everything outside the volume is zero-filled by
+// the TMA unit, which IS Conv3d's zero padding (no per-thread bounds masks, no slab -1 / 40 special cases).
+// Outputs: the xy and yz plane means leave the kernel as TALL pre-split fp16 operands of the first U-Net layer (unet_tall.cuh); the xz
+// partials are finished by xz_finish_tall_kernel straight into the same layout (no NCHW staging buffer, no separate layout pass).
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encoder entry point is fetched through cudaGetDriverEntryPoint)
 #include "common.cuh"
+#include "unet_tall.cuh"
 
 namespace giga {
 
@@ -30,6 +38,9 @@ struct ConvInParams {
 // scene's result does not depend on the batch it is evaluated in.
 constexpr int CI_GROUP = 5;         // canonical iy grouping of the xz sum
 constexpr int CI_RED_STRIDE = 44;   // 16-byte aligned rows; float4 reads are bank-conflict free (44 = 12 mod 32)
+constexpr int CI_SLAB_W = 48;       // staged iz extent: iz -4 .. 43 -- the box must START on a 16-byte boundary of the tensor row (a start at
+                                    // iz = -1 is an illegal instruction: tools/tma_probe.cu), so the halo column iz = -1 sits at index 3
+constexpr int CI_NSTAGE = 4;        // slab ring depth
 // The 32 output channels are split over CS CTAs (blockIdx.z): one voxel column per thread gives only 1600 threads per
 // scene, too few warps per SM to keep the FMA pipe fed; with CS = 2 every SM holds twice the warps, each with half the
 // accumulators (and registers).
@@ -39,7 +50,12 @@ struct ConvInCfg {
   static constexpr int CPT = C / CS;                 // channels per CTA / thread
   static constexpr int THREADS = TY * G;
   static constexpr int RED = CPT * TY * CI_RED_STRIDE; // floats
-  static constexpr int SMEM_BYTES = 2 * RED * 4;     // red + xyacc
+  static constexpr int SLAB_ROWS = TY + 2;           // iy rows of a staged slab (one halo row either side)
+  static constexpr int SLAB_BYTES = SLAB_ROWS * CI_SLAB_W * 4;
+  static constexpr int SLAB_STRIDE = (SLAB_BYTES + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
+  static constexpr int OFF_SLAB = (2 * RED * 4 + 127) / 128 * 128;
+  static constexpr int OFF_BAR = OFF_SLAB + CI_NSTAGE * SLAB_STRIDE;
+  static constexpr int SMEM_BYTES = OFF_BAR + CI_NSTAGE * 8;     // red + xyacc + slab ring + mbarriers
   static_assert(CI_GROUP % TY == 0 && G % TY == 0, "tiles must nest in the canonical groups");
   static_assert(CPT % 2 == 0 && C % CS == 0, "channel pairs");
 };
@@ -47,10 +63,16 @@ __host__ inline int conv_in_ty(int B) { return B >= 8 ? 5 : 1; }
 
 // CZ = which channel slice (compile time: the weights must stay constant-bank operands with immediate offsets -- a
 // runtime channel offset turns every weight fetch into an indexed load and costs 3.4x)
+__device__ __forceinline__ void tma_load_slab(void* dst_smem, const CUtensorMap* tmap, int iz, int iy, int ix, int b, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                   tc::smem_u32(dst_smem)),
+               "l"(tmap), "r"(iz), "r"(iy), "r"(ix), "r"(b), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+
 template <int CI_TY, int CS, int CZ>
-__device__ __forceinline__ void conv_in_body(const float* __restrict__ x, float* __restrict__ pre, float* __restrict__ xz_part, int B,
+__device__ __forceinline__ void conv_in_body(const CUtensorMap* tmap, float* __restrict__ tall, long ps, float* __restrict__ xz_part, int B,
                                              const ConvInParams& P, float* smem) {
-  pdl_wait();
   using Cfg = ConvInCfg<CI_TY, CS>;
   constexpr int CI_NT = Cfg::NT, CI_THREADS = Cfg::THREADS, CI_RED = Cfg::RED, CPT = Cfg::CPT;
   constexpr int c0 = CZ * CPT;       // this CTA's first output channel
@@ -62,33 +84,43 @@ __device__ __forceinline__ void conv_in_body(const float* __restrict__ x, float*
   const int iyl = tid / G, iz = tid % G;
   const int iy0 = tile * CI_TY;
 
-  // The thread's 3x3 (dy,dz) neighbourhood is read straight from global/L1 (the TSDF is 256 KB per scene and
-  // L2 resident); slab ix+2 is prefetched into registers while slab ix+1's 864 FMAs run.  Out-of-volume taps
-  // are zero (Conv3d padding=1): per-thread masks, fixed for the whole march.
-  const float* xb = x + (size_t)b * G3;
-  int off[9];
-  bool ok[9];
+  // ---- slab ring: slab j (= ix plane j of the CTA's rows + halo) lives in stage j % 4; slabs 0 .. 40 are fetched (slab 40 lies outside
+  //      the volume: all zeros), slab j is consumed at the top of step j - 1 and its stage is refilled with slab j + 4 after that step's
+  //      closing barrier ----
+  uint8_t* slabs = reinterpret_cast<uint8_t*>(smem) + Cfg::OFF_SLAB;
+  uint64_t* sbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem) + Cfg::OFF_BAR);
+  if (tid == 0) {
+    for (int i = 0; i < CI_NSTAGE; ++i) tc::mbar_init(&sbar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();   // the TSDF (and the buffers written below) belong to the stream order before this kernel
+  auto fetch = [&](int j) {   // one thread
+    uint64_t* bar = &sbar[j % CI_NSTAGE];
+    tc::mbar_arrive_expect_tx(bar, (uint32_t)Cfg::SLAB_BYTES);
+    tma_load_slab(slabs + (j % CI_NSTAGE) * Cfg::SLAB_STRIDE, tmap, -4, iy0 - 1, j, b, bar);
+  };
+  if (tid == 0)
+    for (int j = 0; j < CI_NSTAGE; ++j) fetch(j);
+  // this thread's 3 x 3 (dy, dz) taps inside a slab: rows iyl .. iyl + 2, columns iz + 3 .. iz + 5 (the slab starts at iy0 - 1, iz -4)
+  const int soff = iyl * CI_SLAB_W + iz + 3;
+  auto read_slab = [&](int j, float* dst) {
+    tc::mbar_wait(&sbar[j % CI_NSTAGE], (uint32_t)((j / CI_NSTAGE) & 1));
+    const float* sl = reinterpret_cast<const float*>(slabs + (j % CI_NSTAGE) * Cfg::SLAB_STRIDE) + soff;
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-    for (int dz = 0; dz < 3; ++dz) {
-      const int gy = iy0 + iyl + dy - 1, gz = iz + dz - 1;
-      ok[dy * 3 + dz] = gy >= 0 && gy < G && gz >= 0 && gz < G;
-      off[dy * 3 + dz] = ok[dy * 3 + dz] ? gy * G + gz : 0;
-    }
+      for (int dz = 0; dz < 3; ++dz) dst[dy * 3 + dz] = sl[dy * CI_SLAB_W + dz];
+  };
 
   float2 yz[CPT / 2];   // channel pairs (FFMA2 / FADD2: half the issue slots of the scalar loop, same bits)
 #pragma unroll
   for (int c = 0; c < CPT / 2; ++c) yz[c] = make_float2(0.f, 0.f);
 
   float win[3][9];  // [dx][dy*3+dz]; win[dx] holds slab ix+dx-1
-  float nxt[9];     // prefetched slab
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    win[1][t] = 0.f;                                         // slab -1 (padding)
-    win[2][t] = ok[t] ? __ldg(xb + off[t]) : 0.f;            // slab 0
-    nxt[t] = ok[t] ? __ldg(xb + G2 + off[t]) : 0.f;          // slab 1
-  }
+  for (int t = 0; t < 9; ++t) win[1][t] = 0.f;               // slab -1 (padding)
+  read_slab(0, win[2]);
 
 #pragma unroll 1
   for (int ix = 0; ix < G; ++ix) {
@@ -99,16 +131,8 @@ __device__ __forceinline__ void conv_in_body(const float* __restrict__ x, float*
     for (int t = 0; t < 9; ++t) {
       win[0][t] = win[1][t];
       win[1][t] = win[2][t];
-      win[2][t] = nxt[t];
     }
-    if (ix + 2 < G) {
-      const float* xs2 = xb + (size_t)(ix + 2) * G2;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) nxt[t] = ok[t] ? __ldg(xs2 + off[t]) : 0.f;
-    } else {
-#pragma unroll
-      for (int t = 0; t < 9; ++t) nxt[t] = 0.f;              // slab 40 (padding)
-    }
+    read_slab(ix + 1, win[2]);
     float2 f[CPT / 2];
 #pragma unroll
     for (int c = 0; c < CPT / 2; ++c) f[c] = P.b[c0 / 2 + c];
@@ -152,61 +176,84 @@ __device__ __forceinline__ void conv_in_body(const float* __restrict__ x, float*
       st4(part + c * G + z, s);
     }
     __syncthreads();
+    if (tid == 0 && ix + CI_NSTAGE <= G) fetch(ix + CI_NSTAGE);   // stage ix % 4 held slab ix, consumed by every thread at the top of step ix - 1
   }
 
-  // yz[c][iz][iy]: transpose through smem so that rows of TY consecutive iy are written together
-  float* stage = red;  // [CPT][40][TY] floats <= CI_RED
+  // ---- outputs as TALL pre-split operands of the first U-Net layer (unet_tall.cuh): image = plane * B + b, 16-byte elements of 8 channels ----
+  // yz[c][iz][iy] = (sum over ix) / 40: this thread holds all CPT channels of pixel (row iz, col iy0 + iyl) of image 2B + b
+  {
+    const long pos = TALL_MARGIN + tall_pos(G, 2 * B + b, iz, iy0 + iyl);
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) stage[(c * G + iz) * CI_TY + iyl] = ((c & 1) ? yz[c / 2].y : yz[c / 2].x) / 40.0f;
-  __syncthreads();
-  float* pre_yz = pre + ((size_t)(2 * B + b) * C + c0) * G2;
-  for (int o = tid; o < CPT * G * CI_TY; o += CI_THREADS) {
-    const int cz = o / CI_TY, r = o % CI_TY;   // cz = c*40 + iz
-    pre_yz[cz * G + iy0 + r] = stage[o];
+    for (int k8 = 0; k8 < CPT / 8; ++k8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[2 * q] = fminf(fmaxf(yz[4 * k8 + q].x / 40.0f, -H_MAX), H_MAX);
+        v[2 * q + 1] = fminf(fmaxf(yz[4 * k8 + q].y / 40.0f, -H_MAX), H_MAX);
+      }
+      uint4 h, l;
+      split8(v, h, l);
+      const int kc = c0 / 8 + k8;
+      stu4(tall + ((size_t)kc * ps + pos) * 4, h);
+      stu4(tall + ((size_t)(C / 8 + kc) * ps + pos) * 4, l);
+    }
   }
-  float* pre_xy = pre + ((size_t)(1 * B + b) * C + c0) * G2;
-  for (int o = tid; o < CPT * CI_TY * G; o += CI_THREADS) {
-    const int j = o / G, ix = o % G;  // j = c*TY + iyl
-    const int c = j / CI_TY, r = j % CI_TY;
-    pre_xy[(c * G + iy0 + r) * G + ix] = xyacc[j * CI_RED_STRIDE + ix] / 40.0f;
+  // xy[c][iy][ix] = (sum over iz) / 40 from the per-step row sums in shared memory: pixel (row iy0 + r, col ix) of image B + b
+  for (int o = tid; o < (CPT / 8) * CI_TY * G; o += CI_THREADS) {
+    const int ix = o % G, r = (o / G) % CI_TY, k8 = o / (G * CI_TY);
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = fminf(fmaxf(xyacc[((8 * k8 + q) * CI_TY + r) * CI_RED_STRIDE + ix] / 40.0f, -H_MAX), H_MAX);
+    uint4 h, l;
+    split8(v, h, l);
+    const long pos = TALL_MARGIN + tall_pos(G, B + b, iy0 + r, ix);
+    const int kc = c0 / 8 + k8;
+    stu4(tall + ((size_t)kc * ps + pos) * 4, h);
+    stu4(tall + ((size_t)(C / 8 + kc) * ps + pos) * 4, l);
   }
 }
 
 // grid (NT, B, CS), block THREADS
 template <int CI_TY, int CS>
 __global__ void __launch_bounds__(CI_TY * G, CI_TY == 5 ? (CS == 1 ? 2 : 4) : 8)
-conv_in_planes_kernel(const float* __restrict__ x,   // [B][40][40][40]
-                      float* __restrict__ pre,       // [3][B][32][40][40]  (xz, xy, yz), NCHW
-                      float* __restrict__ xz_part,   // [B][CI_NT][40 ix][32][40 iz]
+conv_in_planes_kernel(const __grid_constant__ CUtensorMap tmap,   // TSDF x[b][ix][iy][iz] as a 4-D tensor, box {48, TY + 2, 1, 1}
+                      float* __restrict__ tall, long ps,      // TALL pre-split planes [hi|lo][4][ps][8 halfs], images (xz, xy, yz) x B
+                      float* __restrict__ xz_part,            // [B][CI_NT][40 ix][32][40 iz]
                       int B, const __grid_constant__ ConvInParams P) {
-  extern __shared__ __align__(16) float smem_ci[];
+  extern __shared__ __align__(128) float smem_ci[];
   if constexpr (CS == 1) {
-    conv_in_body<CI_TY, 1, 0>(x, pre, xz_part, B, P, smem_ci);
+    conv_in_body<CI_TY, 1, 0>(&tmap, tall, ps, xz_part, B, P, smem_ci);
   } else if constexpr (CS == 2) {
-    if (blockIdx.z == 0) conv_in_body<CI_TY, 2, 0>(x, pre, xz_part, B, P, smem_ci);
-    else conv_in_body<CI_TY, 2, 1>(x, pre, xz_part, B, P, smem_ci);
+    if (blockIdx.z == 0) conv_in_body<CI_TY, 2, 0>(&tmap, tall, ps, xz_part, B, P, smem_ci);
+    else conv_in_body<CI_TY, 2, 1>(&tmap, tall, ps, xz_part, B, P, smem_ci);
   } else {
     static_assert(CS <= 4, "channel split");
     switch (blockIdx.z) {
-      case 0: conv_in_body<CI_TY, 4, 0>(x, pre, xz_part, B, P, smem_ci); break;
-      case 1: conv_in_body<CI_TY, 4, 1>(x, pre, xz_part, B, P, smem_ci); break;
-      case 2: conv_in_body<CI_TY, 4, 2>(x, pre, xz_part, B, P, smem_ci); break;
-      default: conv_in_body<CI_TY, 4, 3>(x, pre, xz_part, B, P, smem_ci); break;
+      case 0: conv_in_body<CI_TY, 4, 0>(&tmap, tall, ps, xz_part, B, P, smem_ci); break;
+      case 1: conv_in_body<CI_TY, 4, 1>(&tmap, tall, ps, xz_part, B, P, smem_ci); break;
+      case 2: conv_in_body<CI_TY, 4, 2>(&tmap, tall, ps, xz_part, B, P, smem_ci); break;
+      default: conv_in_body<CI_TY, 4, 3>(&tmap, tall, ps, xz_part, B, P, smem_ci); break;
     }
   }
 }
 
-// xz[b][c][iz][ix] = (sum over iy, canonical order) / 40 from the per-CTA partials xz_part[b][t][ix][c][iz]      grid (32, B), block 256
+// xz[b][c][iz][ix] = (sum over iy, canonical order) / 40 from the per-CTA partials xz_part[b][t][ix][c][iz], written as TALL pre-split
+// elements (image b, pixel (row iz, col ix)); also zeroes the U-Net's tile-dependency counters (every layer of the step follows this kernel).
+// thread = (scene, k-chunk of 8 channels, ix, iz) with iz fastest (coalesced partial reads); grid ceil(B * 4 * 1600 / 256), block 256
 template <int CI_NT>
 __global__ void __launch_bounds__(256)
-xz_finish_kernel(const float* __restrict__ xz_part, float* __restrict__ pre, int B) {
-  __shared__ float tile[G * 41];
+xz_finish_tall_kernel(const float* __restrict__ xz_part, float* __restrict__ tall, long ps, int B, unsigned* __restrict__ flags, int n_flags) {
   pdl_launch();
   pdl_wait();
-  const int c = blockIdx.x, b = blockIdx.y;
-  for (int e = threadIdx.x; e < G2; e += 256) {
-    const int ix = e / G, z = e % G;
-    constexpr int PER = CI_NT / (G / CI_GROUP);   // partials per canonical group: 1 (TY = 5) or 5 (TY = 1)
+  const long t = (long)blockIdx.x * 256 + threadIdx.x;
+  if (t < n_flags) flags[t] = 0u;
+  if (t >= (long)B * 4 * G2) return;
+  const int z = (int)(t % G), ix = (int)((t / G) % G), kc = (int)((t / G2) % 4), b = (int)(t / (4 * G2));
+  constexpr int PER = CI_NT / (G / CI_GROUP);   // partials per canonical group: 1 (TY = 5) or 5 (TY = 1)
+  float v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = 8 * kc + q;
     float s = 0.f;
 #pragma unroll
     for (int g = 0; g < G / CI_GROUP; ++g) {
@@ -215,11 +262,13 @@ xz_finish_kernel(const float* __restrict__ xz_part, float* __restrict__ pre, int
       for (int r = 1; r < PER; ++r) sg += xz_part[((((size_t)b * CI_NT + g * PER + r) * G + ix) * C + c) * G + z];
       s += sg;
     }
-    tile[z * 41 + ix] = s / 40.0f;
+    v[q] = fminf(fmaxf(s / 40.0f, -H_MAX), H_MAX);
   }
-  __syncthreads();
-  float* o = pre + ((size_t)(0 * B + b) * C + c) * G2;
-  for (int e = threadIdx.x; e < G2; e += 256) o[e] = tile[(e / G) * 41 + (e % G)];
+  uint4 h, l;
+  split8(v, h, l);
+  const long pos = TALL_MARGIN + tall_pos(G, b, z, ix);
+  stu4(tall + ((size_t)kc * ps + pos) * 4, h);
+  stu4(tall + ((size_t)(C / 8 + kc) * ps + pos) * 4, l);
 }
 
 }  // namespace giga

@@ -15,7 +15,6 @@
 
 #include "common.cuh"
 #include "conv_in.cuh"
-#include "conv_in_tc.cuh"
 #include "decoder.cuh"
 #include "decoder_ws.cuh"
 #include "planner.cuh"
@@ -92,7 +91,6 @@ struct EncLayout {
   long tc_conv[10];  // tensor-core operand-layout weights (hi/lo fp16 splits) per conv layer
   long tc_up[2];     // transpose convs, [ab][chunk][kc][hi|lo][co][8 halfs]
   long tc_fin;       // conv_final as a 32x32 B operand [hi,lo][kc 4][n 32][8 halfs]
-  long tc_cin;       // conv_in B operands [dx 3][mma 2][kc 2][n 64][8 halfs] + 2^-s (conv_in_tc.cuh)
   long total;
 };
 const int kConvCin[10] = {32, 32, 32, 64, 64, 128, 128, 64, 64, 32};
@@ -114,7 +112,6 @@ EncLayout make_enc_layout() {
   for (int i = 0; i < 10; ++i) { L.tc_conv[i] = o; o += (long)kConvCin[i] * kConvCout[i] * 9; }
   for (int i = 0; i < 2; ++i) { L.tc_up[i] = o; o += (long)kUpCin[i] * kUpCout[i] * 4; }
   L.tc_fin = o; o += 1024;
-  L.tc_cin = o; o += CT_W_WORDS;
   L.total = o;
   return L;
 }
@@ -135,6 +132,9 @@ struct giga_ctx {
   unsigned heads = 0;
   bool has_encoder = false;
   ConvInParams conv_in;
+  CUtensorMap tsdf_map[2];         // TMA tensor maps over the caller's TSDF (box TY + 2 = 7 / 3 rows), re-encoded when (pointer, B) change
+  const void* tsdf_map_ptr = nullptr;
+  int tsdf_map_B = 0;
   EncLayout el;
   float* d_enc = nullptr;    // packed encoder blob
   float* d_heads = nullptr;  // [4][DW_HEAD]   fp32 FMA-pipe decoder
@@ -143,7 +143,6 @@ struct giga_ctx {
   unsigned* d_sched = nullptr;  // [0] next item, [1] CTAs done, [2] overflow count (self-resetting work counter)
   int decoder_impl = 1;      // 1 = warp-specialised tcgen05 3xFP16, A operand in TMEM (default), 0 = fp32 FMA pipe
   int pdl = 1;               // programmatic dependent launch between the fast-path kernels (1 = on)
-  int conv_in_impl = 0;      // fused Conv3d + plane means: 0 = fp32 FMA pipe (default), 1 = tcgen05 variant (parity-clean; shared-memory bound, not faster yet: DESIGN.md 5)
   int merge_decode = 1;      // giga_forward: grasp heads + TSDF head in one decoder launch
   int tile_deps = 1;         // tile-level dependencies between consecutive same-resolution U-Net layers (needs pdl)
   unsigned long long* d_layer_times = nullptr;   // debug (GIGA_LAYER_TIMES=1): [16][4] u64
@@ -163,7 +162,6 @@ struct giga_ctx {
   int cap_B = 0;
   int last_B = 0;
   float* d_pre = nullptr;      // [3][B][32][1600]
-  float* d_elem = nullptr;     // conv_in_tc voxel elements [B][42][42][40] x 16 B (+ tail), padding zeroed once
   float* d_xzpart = nullptr;   // [B][CI_NT][40][32][40]
   float* d_planes = nullptr;   // [3][B][40][40][32] plane features of giga_forward calls that pass planes = NULL
   int planes_cap = 0;
@@ -282,13 +280,7 @@ void launch_k(const giga_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 blo
 int ensure_attrs(giga_ctx* ctx) {
   if (ctx->attrs_set) return GIGA_OK;
   CU_TRY(cudaFuncSetAttribute(conv_in_planes_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvInCfg<5, 1>::SMEM_BYTES));
-  CU_TRY(cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
-  CU_TRY(cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 4 CTAs / SM
-  {
-    int nb = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_in_tc_kernel, CT_THREADS, CT_SMEM_BYTES));
-    if (getenv("GIGA_VERBOSE")) fprintf(stderr, "[giga] conv_in_tc occupancy: %d CTAs/SM\n", nb);
-  }
+  CU_TRY(cudaFuncSetAttribute(conv_in_planes_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvInCfg<5, 2>::SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(decode_points_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM_BYTES));
   CU_TRY(cudaFuncSetAttribute(sample_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
@@ -307,6 +299,39 @@ int ensure_attrs(giga_ctx* ctx) {
   return GIGA_OK;
 }
 
+// TMA tensor maps over the caller's TSDF x[b][ix][iy][iz] (fp32): dims (innermost first) {40 iz, 40 iy, 40 ix, B}, box {48, TY + 2, 1, 1},
+// out-of-volume elements zero-filled (= Conv3d's padding).  cuTensorMapEncodeTiled is a host-only driver function (no device work, ~1 us);
+// it is fetched through the runtime so that the library does not link against libcuda.  Re-encoded only when (pointer, B) change.
+int ensure_tsdf_maps(giga_ctx* ctx, const float* tsdf, int B) {
+  if (ctx->tsdf_map_ptr == tsdf && ctx->tsdf_map_B == B) return GIGA_OK;
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) return fail(GIGA_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  if (reinterpret_cast<uintptr_t>(tsdf) & 15) return fail(GIGA_EINVAL, "giga_encode: the TSDF pointer must be 16-byte aligned (TMA)");
+  const cuuint64_t dims[4] = {(cuuint64_t)G, (cuuint64_t)G, (cuuint64_t)G, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)G * 4, (cuuint64_t)G2 * 4, (cuuint64_t)G3 * 4};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const int ty[2] = {5, 1};
+  for (int i = 0; i < 2; ++i) {
+    const cuuint32_t box[4] = {(cuuint32_t)CI_SLAB_W, (cuuint32_t)(ty[i] + 2), 1, 1};
+    const CUresult r = encode(&ctx->tsdf_map[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(tsdf), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(GIGA_ECUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  }
+  ctx->tsdf_map_ptr = tsdf;
+  ctx->tsdf_map_B = B;
+  ctx->graph_epoch++;   // the maps are kernel parameters baked into captured graphs
+  return GIGA_OK;
+}
+
 int ensure_workspace(giga_ctx* ctx, int B) {
   if (B <= ctx->cap_B) return GIGA_OK;
   ctx->graph_epoch++;
@@ -317,12 +342,8 @@ int ensure_workspace(giga_ctx* ctx, int B) {
   ctx->d_pre = ctx->d_xzpart = nullptr;
   ctx->cap_B = 0;
   CU_TRY(cudaMalloc(&ctx->d_pre, sizeof(float) * 3 * (size_t)B * C * G2));
-  if (ctx->d_elem) cudaFree(ctx->d_elem);
-  ctx->d_elem = nullptr;
-  CU_TRY(cudaMalloc(&ctx->d_elem, sizeof(float) * (size_t)ct_element_words(B)));
-  CU_TRY(cudaMemset(ctx->d_elem, 0, sizeof(float) * (size_t)ct_element_words(B)));
   {
-    size_t units = (size_t)B * CT_NT;   // partial slabs: a later call with a smaller batch may use the finer FMA tiling
+    size_t units = (size_t)B * (G / 5);   // partial slabs: a later call with a smaller batch may use the finer tiling
     for (int bb = 1; bb <= B; ++bb) units = std::max(units, (size_t)bb * (G / conv_in_ty(bb)));
     CU_TRY(cudaMalloc(&ctx->d_xzpart, sizeof(float) * units * G * C * G));
   }
@@ -515,7 +536,6 @@ int giga_ctx_create(giga_ctx** out, int device) {
     cudaMalloc(&ctx->d_layer_times, 16 * 4 * 8);
     cudaMemset(ctx->d_layer_times, 0, 16 * 4 * 8);
   }
-  if (const char* e = getenv("GIGA_CONV_IN_IMPL")) ctx->conv_in_impl = atoi(e) != 0;
   if (const char* e = getenv("GIGA_CONV_IN_SPLIT")) ctx->conv_in_split = atoi(e) == 2 ? 2 : 1;
   ctx->el = make_enc_layout();
   *out = ctx;
@@ -526,7 +546,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_pre, ctx->d_xzpart, ctx->d_planes, ctx->d_elem, reinterpret_cast<float*>(ctx->d_flags)};
+  float* ptrs[] = {ctx->d_enc, ctx->d_heads, ctx->d_pre, ctx->d_xzpart, ctx->d_planes, reinterpret_cast<float*>(ctx->d_flags)};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : ctx->slot) {
@@ -620,36 +640,6 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       (&ctx->conv_in.b[0].x)[c] = b[c];
     }
     std::vector<float> blob(ctx->el.total, 0.f);
-    {   // conv_in_tc B operands: weights and bias pre-scaled by 2^s, fp16 hi/lo, [dx 3][mma 2][kc 2][n 64][8 halfs]
-      float wmax = 0.f;
-      for (int e = 0; e < 32 * 27; ++e) wmax = fmaxf(wmax, fabsf(w[e]));
-      for (int e = 0; e < 32; ++e) wmax = fmaxf(wmax, fabsf(b[e]));
-      int sexp = 0;
-      if (wmax > 0.f && std::isfinite(wmax)) {
-        int e;
-        frexpf(wmax, &e);
-        sexp = std::min(24, std::max(-14, 10 - e));
-      }
-      const float wscale = ldexpf(1.f, sexp);
-      uint16_t* Wt = reinterpret_cast<uint16_t*>(blob.data() + ctx->el.tc_cin);
-      for (int dx = 0; dx < 3; ++dx)
-        for (int m = 0; m < 2; ++m)
-          for (int kc = 0; kc < 2; ++kc) {
-            const int dy = m == 0 ? kc : (kc == 0 ? -1 : 2);     // MMA 1's first k-chunk re-reads line dy 1 with zero weights
-            if (dy < 0) continue;
-            for (int n = 0; n < 64; ++n)
-              for (int j = 0; j < 8; ++j) {
-                const int c = n & 31;
-                float v = 0.f;
-                if (j < 6) v = w[c * 27 + dx * 9 + dy * 3 + (j % 3)] * wscale;   // slots 0-2: x hi, 3-5: x lo; same weight
-                else if (j == 6 && dx == 1 && dy == 1) v = b[c] * wscale;          // the element's constant 1 carries the bias
-                uint16_t hi, lo;
-                split_half_host(v, hi, lo, 1.f);
-                Wt[((((dx * 2 + m) * 2 + kc) * 64) + n) * 8 + j] = n < 32 ? hi : lo;
-              }
-          }
-      blob[ctx->el.tc_cin + CT_B_BYTES / 4] = ldexpf(1.f, -sexp);
-    }
     for (int i = 0; i < 10; ++i) {
       const int ci = kConvCin[i], co = kConvCout[i];
       std::string base = std::string("encoder.unet.") + kConvName[i];
@@ -860,49 +850,37 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
     cudaMemcpyAsync(ctx->d_layer_times, init, sizeof init, cudaMemcpyHostToDevice, st);
     ctx->layer_slot = 0;
   }
-  if (ctx->conv_in_impl == 1) {
-    {
-      LaunchScope ls(ctx, "conv_in:elements", st);
-      launch_k(ctx, tsdf_elements_kernel, dim3(ceil_div(B * G3, 256)), dim3(256), 0, st, tsdf, ctx->d_elem, B);
-    }
-    {
-      unsigned long long* tl = nullptr;
-      if (ctx->timeline_layer && !strcmp(ctx->timeline_layer, "conv_in_tc")) {   // debug: per-CTA stall accounting
-        const size_t n = (size_t)CT_NT * B * 32;
-        if (ctx->d_timeline) cudaFree(ctx->d_timeline);
-        cudaMalloc(&ctx->d_timeline, n * 8);
-        cudaMemsetAsync(ctx->d_timeline, 0, n * 8, st);
-        ctx->timeline_n = (long)n;
-        tl = ctx->d_timeline;
-      }
-      LaunchScope ls(ctx, "conv_in_tc", st);
-      launch_k(ctx, conv_in_tc_kernel, dim3(CT_NT, B), dim3(CT_THREADS), CT_SMEM_BYTES, st, (const float*)ctx->d_elem,
-               (const float*)(ctx->d_enc + ctx->el.tc_cin), ctx->d_pre, ctx->d_xzpart, B, tl);
-    }
-    {
-      LaunchScope ls(ctx, "xz_finish", st);
-      launch_k(ctx, xz_finish_tc_kernel, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, (const float*)(ctx->d_enc + ctx->el.tc_cin),
-               ctx->d_pre, B);
-    }
-  } else {
-    {
+  // ---- fused Conv3d + ReLU + tri-plane means: TSDF slabs staged by TMA (tensor map over the caller's volume), planes leave as TALL
+  //      pre-split operands of the first U-Net layer ----
+  if (int r = ensure_tsdf_maps(ctx, tsdf, B)) return r;
+  float* tall_pre = ctx->d_tall[0];
+  const long ps_pre = ctx->tall_ps[0];
+  {
     LaunchScope ls(ctx, "conv_in_planes", st);
     if (conv_in_ty(B) == 1) {
       using Cf = ConvInCfg<1, 4>;
-      launch_k(ctx, conv_in_planes_kernel<1, 4>, dim3(Cf::NT, B, 4), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+      launch_k(ctx, conv_in_planes_kernel<1, 4>, dim3(Cf::NT, B, 4), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, ctx->tsdf_map[1], tall_pre, ps_pre,
+               ctx->d_xzpart, B, ctx->conv_in);
     } else if (ctx->conv_in_split == 2) {
       using Cf = ConvInCfg<5, 2>;
-      launch_k(ctx, conv_in_planes_kernel<5, 2>, dim3(Cf::NT, B, 2), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+      launch_k(ctx, conv_in_planes_kernel<5, 2>, dim3(Cf::NT, B, 2), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, ctx->tsdf_map[0], tall_pre, ps_pre,
+               ctx->d_xzpart, B, ctx->conv_in);
     } else {
       using Cf = ConvInCfg<5, 1>;
-      launch_k(ctx, conv_in_planes_kernel<5, 1>, dim3(Cf::NT, B, 1), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, tsdf, ctx->d_pre, ctx->d_xzpart, B, ctx->conv_in);
+      launch_k(ctx, conv_in_planes_kernel<5, 1>, dim3(Cf::NT, B, 1), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, ctx->tsdf_map[0], tall_pre, ps_pre,
+               ctx->d_xzpart, B, ctx->conv_in);
     }
   }
   {
     LaunchScope ls(ctx, "xz_finish", st);
-    if (conv_in_ty(B) == 5) launch_k(ctx, xz_finish_kernel<G / 5>, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, ctx->d_pre, B);
-    else launch_k(ctx, xz_finish_kernel<G>, dim3(C, B), dim3(256), 0, st, (const float*)ctx->d_xzpart, ctx->d_pre, B);
-  }
+    const int blocks = ceil_div((int)std::max((long)B * 4 * G2, 9 * ctx->flags_stride + 16), 256);
+    if (conv_in_ty(B) == 5)
+      launch_k(ctx, xz_finish_tall_kernel<G / 5>, dim3(blocks), dim3(256), 0, st, (const float*)ctx->d_xzpart, tall_pre, ps_pre, B, ctx->d_flags,
+               (int)(9 * ctx->flags_stride + 16));
+    else
+      launch_k(ctx, xz_finish_tall_kernel<G>, dim3(blocks), dim3(256), 0, st, (const float*)ctx->d_xzpart, tall_pre, ps_pre, B, ctx->d_flags,
+               (int)(9 * ctx->flags_stride + 16));
+    ctx->work_slot = 0;
   }
   float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"),
         *d1c2 = act(ctx, "d1c2"), *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"),
@@ -920,12 +898,6 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
     const TallBuf none;
     const float* E = ctx->d_enc;
     const EncLayout& L = ctx->el;
-    {
-      LaunchScope ls(ctx, "nchw_to_tall:pre", st);
-      launch_k(ctx, nchw_to_tall_kernel<40, 4>, dim3(ceil_div(n_img * 4 * G2, 256)), dim3(256), 0, st, (const float*)ctx->d_pre, tb("pre").p,
-               tb("pre").ps, n_img, ctx->d_flags, (int)(9 * ctx->flags_stride + 16));
-      ctx->work_slot = 0;
-    }
     {
       // tile-level dependency edges (dep_out -> dep_in): d0c1->d0c2, d1c1->d1c2, d2c1->d2c2->u0up->u0c1->u0c2->u1up->u1c1->u1c2;
       // the edges through the max-pools are whole-grid waits
@@ -958,6 +930,10 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
     return GIGA_OK;
   }
   ctx->last_impl = 0;
+  {   // the fp32 FMA-pipe U-Net reads NCHW fp32 planes: expand the pre-split planes (hi + lo * 2^-11 carries 22 significant bits)
+    LaunchScope ls(ctx, "tall_to_nchw:pre", st);
+    tall_to_nchw_kernel<40, 4><<<ceil_div(n_img * 4 * G2, 256), 256, 0, st>>>(tall_pre, ctx->d_pre, ps_pre, n_img);
+  }
   launch_conv<K_d0c1>(ctx, "conv3x3:d0c1", n_img, ctx->d_pre, nullptr, 0, d0c1, nullptr, st);
   launch_conv<K_d0c2>(ctx, "conv3x3:d0c2", n_img, d0c1, nullptr, 1, d0c2, p0, st);
   launch_conv<K_d1c1>(ctx, "conv3x3:d1c1", n_img, p0, nullptr, 2, d1c1, nullptr, st);
@@ -1574,11 +1550,6 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
     ctx->decoder_impl = value;
     return GIGA_OK;
   }
-  if (!strcmp(key, "conv_in_impl")) {
-    if (value != 0 && value != 1) return fail(GIGA_EINVAL, "conv_in_impl must be 0 (fp32 FMA pipe) or 1 (tcgen05 3xFP16)");
-    ctx->conv_in_impl = value;
-    return GIGA_OK;
-  }
   if (!strcmp(key, "dynamic_items")) {
     if (value != 0 && value != 1) return fail(GIGA_EINVAL, "dynamic_items must be 0 or 1");
     ctx->dynamic_items = value;
@@ -1655,9 +1626,11 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
     CU_TRY(cudaMemcpyAsync(dst, ctx->d_timeline, ctx->timeline_n * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return ctx->timeline_n * 2;
   }
-  if (!strcmp(name, "pre")) {
+  if (!strcmp(name, "pre")) {   // the planes before the U-Net exist only as TALL pre-split operands: expand into the NCHW scratch
     src = ctx->d_pre;
     numel = 3L * ctx->last_B * C * G2;
+    const int n_img = 3 * ctx->last_B;
+    tall_to_nchw_kernel<40, 4><<<ceil_div(n_img * 4 * G2, 256), 256, 0, (cudaStream_t)stream>>>(ctx->d_tall[0], ctx->d_pre, ctx->tall_ps[0], n_img);
   } else {
     for (int i = 0; i < kNumActs; ++i)
       if (!strcmp(kActs[i].name, name)) {

@@ -192,8 +192,6 @@ long giga_ctx_overflow_count(giga_ctx *ctx, int reset);
  *   "decoder_impl": 1 = warp-specialised tcgen05 decoder, 3xFP16 operand splitting, A operand in tensor memory (default),
  *                   0 = fp32 FMA pipe (no fp16 operand range limit: the fallback for giga_ctx_overflow_count() != 0)
  *   "encoder_impl": U-Net convolutions: 1 = tcgen05 3xFP16 with persistent CTAs (default), 0 = fp32 FMA pipe
- *   "conv_in_impl": fused Conv3d + plane means: 0 = fp32 FMA pipe (default), 1 = tcgen05 3xFP16 variant (same parity bar;
- *                   shared-memory-bandwidth bound, currently not faster)
  *   "graph":        1 = giga_detect_host replays a captured CUDA graph of the whole call from its third invocation of a
  *                   configuration on (default), 0 = always enqueue kernel by kernel
  *   "tile_deps":    1 = consecutive same-resolution U-Net layers synchronise per position group instead of per grid

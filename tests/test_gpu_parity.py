@@ -405,21 +405,27 @@ def test_batch_invariance_across_tilings(net):
         assert torch.equal(net.debug_activation("pre", 1), pre9[:, 4:5])
 
 
-@pytest.mark.parametrize("impl", [0, 1])
-def test_conv_in_implementations(oracle_sd, impl):
-    """conv_in_impl 1 = tcgen05 Conv3d + plane means (default; dz taps folded into 16-byte voxel elements, (dx,dy) taps as
-    descriptor shifts), 0 = fp32 FMA pipe: pre-U-Net planes within 1e-5, outputs within 1e-4, for both conv_in tilings."""
+def test_conv_in_tma_staging_edges(oracle_sd):
+    """The fused Conv3d + plane means stages the TSDF through a 4-D TMA tensor map whose out-of-volume zero fill IS the conv's zero
+    padding (encoder/voxels.py:36).  Volumes that are non-zero on every face/edge/corner voxel, in both tilings (B < 8: one iy row per
+    CTA, B >= 8: five) and from a sliced (offset) input tensor, must reproduce the oracle's pre-U-Net planes."""
     net = make_net("giga", oracle_sd)
-    net._engine().set_option("conv_in_impl", impl)
-    for B, seed in ((1, 1), (3, 2), (9, 3)):
-        x, p, pt = O.seeded_inputs(B, 64, seed=60 + seed)
+    for B in (1, 9):
+        g = torch.Generator().manual_seed(5 + B)
+        big = torch.rand(B + 2, 40, 40, 40, generator=g) * 2.0 - 0.5
+        big[:, 0], big[:, -1], big[:, :, 0], big[:, :, -1], big[:, :, :, 0], big[:, :, :, -1] = 3.0, -2.0, 1.5, 2.5, -1.0, 4.0
+        xd = big.to(DEV)[1:B + 1]                      # a view at a non-zero offset: the tensor map is encoded on its pointer
+        x = big[1:B + 1]
         with torch.no_grad():
             pre = O.plane_features_pre_unet(oracle_sd, x)
-            ref = O.forward(oracle_sd, x, p, pt)
-            out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
-            _close(net.debug_activation("pre", B), torch.stack([pre[k] for k in O.PLANES]), tol=1e-5, name=f"pre(impl{impl})")
-        for nme, a, b in zip(("qual", "rot", "width", "occ"), out, ref):
-            _close(a, b, name=f"cin{impl}.{nme}")
+            ref = O.encode_inputs(oracle_sd, x)
+            c = net.encode_inputs(xd)
+            got = net.debug_activation("pre", B).cpu()
+            want = torch.stack([pre[k] for k in O.PLANES])
+            assert (got - want).abs().max().item() <= 2e-6 * want.abs().max().item(), ("pre", B, (got - want).abs().max().item())
+            for k in O.PLANES:
+                err = (c[k].cpu() - ref[k]).abs().max().item()
+                assert err <= 4e-6 * ref[k].abs().max().item(), (k, B, err, ref[k].abs().max().item())
 
 
 def test_other_baseline_configs(net, oracle_sd):
@@ -579,6 +585,6 @@ def test_decoder_head_combinations(net, oracle_sd):
             out = net._decode_heads(p.to(DEV), c, mask)
             for i, bit in enumerate((HEAD_QUAL, HEAD_ROT, HEAD_WIDTH, HEAD_TSDF)):
                 if mask & bit:
-                    assert torch.equal(out[i], full[i]), (mask, i)   # same kernel code per chain: bit-identical
+                    assert (out[i] - full[i]).abs().max().item() <= 2e-6, (mask, i)   # same arithmetic per chain (3-chain item vs single-chain job)
                 else:
                     assert out[i] is None
