@@ -132,9 +132,10 @@ struct giga_ctx {
   unsigned heads = 0;
   bool has_encoder = false;
   ConvInParams conv_in;
-  CUtensorMap tsdf_map[2];         // TMA tensor maps over the caller's TSDF (box TY + 2 = 7 / 3 rows), re-encoded when (pointer, B) change
-  const void* tsdf_map_ptr = nullptr;
-  int tsdf_map_B = 0;
+  struct TsdfMaps { const void* ptr; int B; unsigned long long use; CUtensorMap m[2]; };   // TMA tensor maps over a caller's TSDF (boxes of 7 / 3 iy rows)
+  std::vector<TsdfMaps> tsdf_maps;   // small cache keyed by (pointer, B): a serving loop alternates between a few input buffers
+  unsigned long long tsdf_map_use = 0;
+  CUtensorMap tsdf_map[2];         // the pair selected by the last ensure_tsdf_maps()
   EncLayout el;
   float* d_enc = nullptr;    // packed encoder blob
   float* d_heads = nullptr;  // [4][DW_HEAD]   fp32 FMA-pipe decoder
@@ -175,6 +176,10 @@ struct giga_ctx {
     int cap_B = 0, cap_Ng = 0, cap_No = 0;
     cudaEvent_t ev_in = nullptr, ev_compute = nullptr, ev_done = nullptr;
     bool pending = false;
+    // the slot's kernels as ONE CUDA-graph launch (captured on the second request of a configuration, replayed afterwards)
+    cudaGraphExec_t graph = nullptr;
+    unsigned long long graph_key = 0, graph_epoch = 0, seen_key = 0;
+    long graph_launches = 0;
   };
   HostSlot slot[3];   // [0],[1]: pipelined submit/wait; [2]: the synchronous giga_forward_host
   cudaStream_t st_h2d = nullptr, st_compute = nullptr, st_d2h = nullptr;   // pipelined host path
@@ -303,7 +308,13 @@ int ensure_attrs(giga_ctx* ctx) {
 // out-of-volume elements zero-filled (= Conv3d's padding).  cuTensorMapEncodeTiled is a host-only driver function (no device work, ~1 us);
 // it is fetched through the runtime so that the library does not link against libcuda.  Re-encoded only when (pointer, B) change.
 int ensure_tsdf_maps(giga_ctx* ctx, const float* tsdf, int B) {
-  if (ctx->tsdf_map_ptr == tsdf && ctx->tsdf_map_B == B) return GIGA_OK;
+  for (auto& e : ctx->tsdf_maps)
+    if (e.ptr == tsdf && e.B == B) {
+      e.use = ++ctx->tsdf_map_use;
+      ctx->tsdf_map[0] = e.m[0];
+      ctx->tsdf_map[1] = e.m[1];
+      return GIGA_OK;
+    }
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn encode = nullptr;
@@ -315,21 +326,30 @@ int ensure_tsdf_maps(giga_ctx* ctx, const float* tsdf, int B) {
     encode = reinterpret_cast<EncodeFn>(fn);
   }
   if (reinterpret_cast<uintptr_t>(tsdf) & 15) return fail(GIGA_EINVAL, "giga_encode: the TSDF pointer must be 16-byte aligned (TMA)");
+  giga_ctx::TsdfMaps e;
+  e.ptr = tsdf; e.B = B; e.use = ++ctx->tsdf_map_use;
   const cuuint64_t dims[4] = {(cuuint64_t)G, (cuuint64_t)G, (cuuint64_t)G, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)G * 4, (cuuint64_t)G2 * 4, (cuuint64_t)G3 * 4};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const int ty[2] = {5, 1};
   for (int i = 0; i < 2; ++i) {
     const cuuint32_t box[4] = {(cuuint32_t)CI_SLAB_W, (cuuint32_t)(ty[i] + 2), 1, 1};
-    const CUresult r = encode(&ctx->tsdf_map[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(tsdf), dims, strides, box, estr,
+    const CUresult r = encode(&e.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(tsdf), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(GIGA_ECUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
   }
-  ctx->tsdf_map_ptr = tsdf;
-  ctx->tsdf_map_B = B;
-  ctx->graph_epoch++;   // the maps are kernel parameters baked into captured graphs
-  return GIGA_OK;
+  if (ctx->tsdf_maps.size() >= 8) {   // evict the least recently used pair
+    size_t lru = 0;
+    for (size_t i = 1; i < ctx->tsdf_maps.size(); ++i)
+      if (ctx->tsdf_maps[i].use < ctx->tsdf_maps[lru].use) lru = i;
+    ctx->tsdf_maps[lru] = e;
+  } else {
+    ctx->tsdf_maps.push_back(e);
+  }
+  ctx->tsdf_map[0] = e.m[0];
+  ctx->tsdf_map[1] = e.m[1];
+  return GIGA_OK;   // (captured graphs bake the map by value and are keyed on their own fixed device buffers: no epoch bump)
 }
 
 int ensure_workspace(giga_ctx* ctx, int B) {
@@ -553,6 +573,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
     float* sp[] = {s.tsdf, s.planes, s.p, s.pt, s.qual, s.rot, s.width, s.occ};
     for (float* p : sp)
       if (p) cudaFree(p);
+    if (s.graph) cudaGraphExecDestroy(s.graph);
     if (s.ev_in) cudaEventDestroy(s.ev_in);
     if (s.ev_compute) cudaEventDestroy(s.ev_compute);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -1121,6 +1142,7 @@ namespace {
 int ensure_slot(giga_ctx* ctx, giga_ctx::HostSlot& s, int B, int Ng, int No) {
   if (B <= s.cap_B && Ng <= s.cap_Ng && No <= s.cap_No) return GIGA_OK;
   CU_TRY(cudaDeviceSynchronize());
+  ctx->graph_epoch++;   // captured graphs hold the old staging pointers
   float** ptrs[] = {&s.tsdf, &s.planes, &s.p, &s.pt, &s.qual, &s.rot, &s.width, &s.occ};
   for (float** q : ptrs) { if (*q) cudaFree(*q); *q = nullptr; }
   const int cB = B > s.cap_B ? B : s.cap_B, cg = Ng > s.cap_Ng ? Ng : s.cap_Ng, co = No > s.cap_No ? No : s.cap_No;
@@ -1148,9 +1170,50 @@ int enqueue_host_request(giga_ctx* ctx, giga_ctx::HostSlot& s, const float* tsdf
     CU_TRY(cudaEventRecord(s.ev_in, sin));
     CU_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
   }
-  if (int r = giga_forward(ctx, s.tsdf, B, grasp ? s.p : nullptr, Ng, geo ? s.pt : nullptr, No, s.planes, s.qual, s.rot, s.width, s.occ, nullptr,
-                           nullptr, sc))
-    return r;
+  // the kernels: one CUDA-graph launch from the third request of a configuration on (the pipelined path only: sc is then the ctx's own
+  // compute stream); the first request runs eagerly (allocations, tensor maps), the second is captured
+  bool launched = false;
+  if (ctx->use_graph && sc == ctx->st_compute && sc != nullptr && !ctx->timing && !ctx->timeline_layer) {
+    const unsigned long long key = 0x9e3779b97f4a7c15ull * (unsigned long long)(B + 1) + 0xc2b2ae3d27d4eb4full * (unsigned long long)(Ng + 1) +
+                                   0x165667b19e3779f9ull * (unsigned long long)(No + 1) + ctx->heads;
+    if (s.graph && (s.graph_key != key || s.graph_epoch != ctx->graph_epoch)) {
+      cudaGraphExecDestroy(s.graph);
+      s.graph = nullptr;
+      s.seen_key = 0;
+    }
+    if (!s.graph && s.seen_key == key && s.graph_epoch == ctx->graph_epoch) {   // second request of this configuration: capture
+      OrderScope order(ctx, sc);   // orders the capture's replay position; the capture itself runs with the guard off
+      const long l0 = ctx->launches;
+      CU_TRY(cudaStreamBeginCapture(sc, cudaStreamCaptureModeThreadLocal));
+      ctx->capturing = true;
+      const int r = giga_forward(ctx, s.tsdf, B, grasp ? s.p : nullptr, Ng, geo ? s.pt : nullptr, No, s.planes, s.qual, s.rot, s.width, s.occ,
+                                 nullptr, nullptr, sc);
+      ctx->capturing = false;
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(sc, &graph);
+      if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+      if (ce != cudaSuccess || !graph) return fail(GIGA_ECUDA, std::string("giga_forward_host_submit: graph capture failed: ") + cudaGetErrorString(ce));
+      const cudaError_t ie = cudaGraphInstantiate(&s.graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) { s.graph = nullptr; return fail(GIGA_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+      s.graph_key = key;
+      s.graph_launches = ctx->launches - l0;
+      ctx->launches = l0;
+    }
+    if (s.graph) {
+      OrderScope order(ctx, sc);
+      CU_TRY(cudaGraphLaunch(s.graph, sc));
+      ctx->launches += s.graph_launches;
+      launched = true;
+    } else {
+      s.seen_key = key;
+      s.graph_epoch = ctx->graph_epoch;
+    }
+  }
+  if (!launched)
+    if (int r = giga_forward(ctx, s.tsdf, B, grasp ? s.p : nullptr, Ng, geo ? s.pt : nullptr, No, s.planes, s.qual, s.rot, s.width, s.occ, nullptr,
+                             nullptr, sc))
+      return r;
   if (sc != sout) {
     CU_TRY(cudaEventRecord(s.ev_compute, sc));
     CU_TRY(cudaStreamWaitEvent(sout, s.ev_compute, 0));

@@ -86,14 +86,29 @@ def sharded_best_grasp(score_fn: Callable[[torch.Tensor, torch.Tensor], Tuple[to
 class SceneBestBuffer:
     """The all-gather buffer of the final grasp-score reduction, packed so that ONE collective moves both fields:
     buf[world][2][m] float32 with row 0 = best quality and row 1 = the arg-max index (int32 bits).  `val` / `idx` are
-    this rank's contiguous slices -- giga_scene_argmax (or giga_forward's fused arg-max) writes straight into them --
-    and gather() is a single in-place NCCL all-gather (8 bytes per scene)."""
+    this rank's contiguous slices of the CURRENT buffer -- giga_scene_argmax (or giga_forward's fused arg-max) writes
+    straight into them -- and the exchange is a single in-place NCCL all-gather (8 bytes per scene).
 
-    def __init__(self, n_local_max: int, device, group=None):
+    gather()        in-stream: the collective is enqueued behind the kernels on the current stream (simple; at 8 GPUs it put
+                    ~20 us of launch + NVLink latency on every step's critical path, SCALE_r01).
+    gather_async()  the collective runs on a side stream behind an event and the buffer ring advances (`depth` buffers): the next
+                    step's kernels start at once and write the next buffer; wait(ticket) makes the current stream wait for a
+                    gather and returns its (val, idx).  The latency-bound 8 B/scene exchange then overlaps the next step."""
+
+    def __init__(self, n_local_max: int, device, group=None, depth: int = 2):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.buf = torch.zeros((self.world, 2, n_local_max), dtype=torch.float32, device=device)
+        self.bufs = [torch.zeros((self.world, 2, n_local_max), dtype=torch.float32, device=device) for _ in range(max(1, depth))]
+        self.cur = 0
+        dev = torch.device(device)
+        self._cuda = dev.type == "cuda"
+        self._side = torch.cuda.Stream(device=dev) if (self._cuda and self.world > 1) else None
+        self._done = [None] * len(self.bufs)     # event: the gather that last used buffer i has finished
+
+    @property
+    def buf(self) -> torch.Tensor:
+        return self.bufs[self.cur]
 
     @property
     def val(self) -> torch.Tensor:
@@ -103,14 +118,48 @@ class SceneBestBuffer:
     def idx(self) -> torch.Tensor:
         return self.buf[self.rank, 1].view(torch.int32)
 
+    def _all_gather(self, buf):
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_gather_into_tensor(buf, buf[self.rank], group=self.group)   # in place: send = own slice
+        else:  # gloo (CPU tests): list form, no aliasing
+            dist.all_gather(list(buf.unbind(0)), buf[self.rank].clone(), group=self.group)
+
     def gather(self):
-        """-> (val (world, m) float32, idx (world, m) int32), identical on every rank."""
+        """-> (val (world, m) float32, idx (world, m) int32), identical on every rank (in-stream)."""
         if self.world > 1:
-            if dist.get_backend(self.group) == "nccl":
-                dist.all_gather_into_tensor(self.buf, self.buf[self.rank], group=self.group)   # in place: send = own slice
-            else:  # gloo (CPU tests): list form, no aliasing
-                dist.all_gather(list(self.buf.unbind(0)), self.buf[self.rank].clone(), group=self.group)
+            self._all_gather(self.buf)
         return self.buf[:, 0], self.buf[:, 1].view(torch.int32)
+
+    def gather_async(self) -> int:
+        """Start the exchange of the current buffer off the critical path and advance to the next buffer; returns a ticket."""
+        t = self.cur
+        if self.world > 1:
+            if self._side is not None:
+                ready = torch.cuda.Event()
+                ready.record()                                   # this step's arg-max has written the slice
+                self._side.wait_event(ready)
+                with torch.cuda.stream(self._side):
+                    self._all_gather(self.bufs[t])
+                    done = torch.cuda.Event()
+                    done.record()
+                self._done[t] = done
+            else:
+                self._all_gather(self.bufs[t])
+        self.cur = (t + 1) % len(self.bufs)
+        if self._done[self.cur] is not None:                     # the buffer we are about to overwrite: its last gather (depth steps ago)
+            torch.cuda.current_stream().wait_event(self._done[self.cur])
+        return t
+
+    def wait(self, ticket: int):
+        """Make the current stream wait for gather `ticket`; -> (val (world, m), idx (world, m)) of that exchange."""
+        if self._done[ticket] is not None:
+            torch.cuda.current_stream().wait_event(self._done[ticket])
+        b = self.bufs[ticket]
+        return b[:, 0], b[:, 1].view(torch.int32)
+
+    def synchronize(self):
+        if self._side is not None:
+            self._side.synchronize()
 
 
 class GigaScorer:

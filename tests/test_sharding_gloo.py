@@ -67,6 +67,19 @@ def _worker(rank, world, port, n_scenes, out):
         for r in range(world):
             rs, re = sharding.shard_range(n_scenes, r, world)
             ok = ok and torch.equal(gv[r, : re - rs], rv[rs:re]) and torch.equal(gi[r, : re - rs], ri[rs:re])
+        # pipelined form: three "steps" through a ring of two buffers; every ticket returns its own step's exchange
+        ring = sharding.SceneBestBuffer(m, "cpu", depth=2)
+        tickets = []
+        for step in range(3):
+            ring.val[: e0 - s0] = rv[s0:e0] + step
+            ring.idx[: e0 - s0] = ri[s0:e0] + step
+            tickets.append(ring.gather_async())
+            if step >= 1:                                  # consume the previous step's exchange while "computing" this one
+                pv, pi = ring.wait(tickets[step - 1])
+                for r in range(world):
+                    rs, re = sharding.shard_range(n_scenes, r, world)
+                    ok = ok and torch.equal(pv[r, : re - rs], rv[rs:re] + (step - 1)) and torch.equal(pi[r, : re - rs], ri[rs:re] + (step - 1))
+        ring.synchronize()
         out[rank] = int(ok)
     finally:
         dist.destroy_process_group()
