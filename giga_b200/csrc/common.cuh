@@ -40,4 +40,13 @@ __device__ __forceinline__ void add2(float2& d, const float2 a) {               
   d = *reinterpret_cast<float2*>(&dd);
 }
 
+// ReLU / max that PROPAGATE NaN (fmaxf returns the non-NaN operand and would swallow an fp16-range overflow: a value beyond 65504 becomes the
+// operand pair (inf, -inf), the next contraction turns it into NaN, and that NaN must reach the outputs -- giga_ctx_overflow_count)
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float relu_nan(float x) { return max_nan(x, 0.f); }
+
 }  // namespace giga

@@ -188,8 +188,8 @@ __device__ __forceinline__ void conv_in_body(const CUtensorMap* tmap, float* __r
       float v[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        v[2 * q] = fminf(fmaxf(yz[4 * k8 + q].x / 40.0f, -H_MAX), H_MAX);
-        v[2 * q + 1] = fminf(fmaxf(yz[4 * k8 + q].y / 40.0f, -H_MAX), H_MAX);
+        v[2 * q] = yz[4 * k8 + q].x / 40.0f;
+        v[2 * q + 1] = yz[4 * k8 + q].y / 40.0f;
       }
       uint4 h, l;
       split8(v, h, l);
@@ -203,7 +203,7 @@ __device__ __forceinline__ void conv_in_body(const CUtensorMap* tmap, float* __r
     const int ix = o % G, r = (o / G) % CI_TY, k8 = o / (G * CI_TY);
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = fminf(fmaxf(xyacc[((8 * k8 + q) * CI_TY + r) * CI_RED_STRIDE + ix] / 40.0f, -H_MAX), H_MAX);
+    for (int q = 0; q < 8; ++q) v[q] = xyacc[((8 * k8 + q) * CI_TY + r) * CI_RED_STRIDE + ix] / 40.0f;
     uint4 h, l;
     split8(v, h, l);
     const long pos = TALL_MARGIN + tall_pos(G, B + b, iy0 + r, ix);
@@ -262,7 +262,7 @@ xz_finish_tall_kernel(const float* __restrict__ xz_part, float* __restrict__ tal
       for (int r = 1; r < PER; ++r) sg += xz_part[((((size_t)b * CI_NT + g * PER + r) * G + ix) * C + c) * G + z];
       s += sg;
     }
-    v[q] = fminf(fmaxf(s / 40.0f, -H_MAX), H_MAX);
+    v[q] = s / 40.0f;
   }
   uint4 h, l;
   split8(v, h, l);

@@ -102,11 +102,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float relu_nan(float x) {   // max that PROPAGATES NaN (fmaxf would swallow an overflow)
-  float r;
-  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
-  return r;
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -354,10 +349,10 @@ __device__ __forceinline__ void wd_compute_item(const DecArgs& args, const DecJo
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4) {
       const float4 b1 = ld4(W + HC_B1 + col0 + 4 * k4);
-      v[4 * k4 + 0] = wd::relu_nan(fmaf(__uint_as_float(va[4 * k4 + 0]), winv[c], h[c][4 * k4 + 0] + b1.x));
-      v[4 * k4 + 1] = wd::relu_nan(fmaf(__uint_as_float(va[4 * k4 + 1]), winv[c], h[c][4 * k4 + 1] + b1.y));
-      v[4 * k4 + 2] = wd::relu_nan(fmaf(__uint_as_float(va[4 * k4 + 2]), winv[c], h[c][4 * k4 + 2] + b1.z));
-      v[4 * k4 + 3] = wd::relu_nan(fmaf(__uint_as_float(va[4 * k4 + 3]), winv[c], h[c][4 * k4 + 3] + b1.w));
+      v[4 * k4 + 0] = relu_nan(fmaf(__uint_as_float(va[4 * k4 + 0]), winv[c], h[c][4 * k4 + 0] + b1.x));
+      v[4 * k4 + 1] = relu_nan(fmaf(__uint_as_float(va[4 * k4 + 1]), winv[c], h[c][4 * k4 + 1] + b1.y));
+      v[4 * k4 + 2] = relu_nan(fmaf(__uint_as_float(va[4 * k4 + 2]), winv[c], h[c][4 * k4 + 2] + b1.z));
+      v[4 * k4 + 3] = relu_nan(fmaf(__uint_as_float(va[4 * k4 + 3]), winv[c], h[c][4 * k4 + 3] + b1.w));
     }
     o[c] = half == 0 ? ld4(W + HC_OUT + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (head == 1) {   // rot: 4 outputs

@@ -21,7 +21,9 @@
 // hi*hi products therefore go to one of two alternating TMEM accumulator sets that are drained into fp32 REGISTERS after
 // every 16-channel chunk (<= 9 MMAs per chain, round-to-nearest adds on the CUDA cores), while the 2^11-scaled
 // correction products accumulate in separate sets and are folded in with one FMA (x 2^-11) at the end of the tile.
-// Range: activations and weights must stay inside fp16's +-65504 (conv outputs are clamped there; GIGA's are O(10)).
+// Range: activations and weights must stay inside fp16's +-65504 (GIGA's are O(10)).  Nothing is clamped: a larger value becomes the pair
+// (inf, -inf), the next contraction makes it NaN, ReLU / max-pool propagate NaN (max.NaN), so the plane features and every head output
+// computed from them read NaN -- counted by giga_ctx_overflow_count().
 #pragma once
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -72,29 +74,6 @@ __device__ __forceinline__ long tall_pos(int hw, int img, int y, int x) { return
 
 // ---- layout conversion / pooling (thread = one valid pixel x one 8-channel k-chunk) --------------------------
 // grid: ceil(n_img*HW*HW*C8 / 256), block 256
-template <int HW, int C8>   // C8 = channels / 8
-__global__ void __launch_bounds__(256) nchw_to_tall_kernel(const float* __restrict__ src, float* __restrict__ dst, long ps, int n_img,
-                                                           unsigned* __restrict__ flags, int n_flags) {   // flags: LayerDep counters, zeroed here
-  pdl_launch();
-  pdl_wait();
-  const long t = (long)blockIdx.x * 256 + threadIdx.x;
-  if (t < n_flags) flags[t] = 0u;
-  const long total = (long)n_img * C8 * HW * HW;
-  if (t >= total) return;
-  const int pix = (int)(t % (HW * HW));
-  const int kc = (int)((t / (HW * HW)) % C8);
-  const int img = (int)(t / ((long)HW * HW * C8));
-  const float* p = src + ((size_t)img * (8 * C8) + 8 * kc) * (HW * HW) + pix;
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = fminf(fmaxf(__ldg(p + j * HW * HW), -H_MAX), H_MAX);
-  uint4 h, l;
-  split8(v, h, l);
-  const long pos = TALL_MARGIN + tall_pos(HW, img, pix / HW, pix % HW);
-  stu4(dst + ((size_t)kc * ps + pos) * 4, h);
-  stu4(dst + ((size_t)(C8 + kc) * ps + pos) * 4, l);
-}
-
 template <int HW, int C8>
 __global__ void __launch_bounds__(256) tall_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, long ps, int n_img) {
   pdl_launch();
@@ -132,7 +111,7 @@ __global__ void __launch_bounds__(256) pool_tall_kernel(const float* __restrict_
     float v[8];
     join8(ldu4(src + ((size_t)kc * ps_in + pos) * 4), ldu4(src + ((size_t)(C8 + kc) * ps_in + pos) * 4), v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = q == 0 ? v[j] : fmaxf(m[j], v[j]);
+    for (int j = 0; j < 8; ++j) m[j] = q == 0 ? v[j] : max_nan(m[j], v[j]);
   }
   uint4 h, l;
   split8(m, h, l);
@@ -593,7 +572,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
               const int co = nt_idx * NTILE + 8 * kc;
               float v[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = fminf(fmaxf(acc[mt][8 * kc + q] + sbias[8 * kc + q], 0.f), H_MAX);
+              for (int q = 0; q < 8; ++q) v[q] = relu_nan(acc[mt][8 * kc + q] + sbias[8 * kc + q]);
               uint4 h, l;
               split8(v, h, l);
               stu4(out + ((size_t)(co / 8) * pso + pos) * 4, h);
@@ -608,7 +587,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
             for (int kc = 0; kc < NTILE / 8; ++kc) {
               float v[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = fminf(fmaxf(acc[mt][8 * kc + q] + sbias[8 * kc + q], -H_MAX), H_MAX);
+              for (int q = 0; q < 8; ++q) v[q] = acc[mt][8 * kc + q] + sbias[8 * kc + q];
               uint4 h, l;
               split8(v, h, l);
               stu4(out + ((size_t)kc * pso + pos) * 4, h);
@@ -623,7 +602,7 @@ conv_tall_persistent_kernel(const float* __restrict__ src0, long ps0, const floa
           for (int kc = 0; kc < 4; ++kc) {
             float v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fminf(fmaxf(acc[mt][8 * kc + q] + sbias[8 * kc + q], 0.f), H_MAX);
+            for (int q = 0; q < 8; ++q) v[q] = relu_nan(acc[mt][8 * kc + q] + sbias[8 * kc + q]);
             uint4 h, l;
             split8(v, h, l);
             *reinterpret_cast<uint4*>(fa_hi + kc * K::FIN_KS + tid * 16) = h;

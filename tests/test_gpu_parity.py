@@ -568,6 +568,15 @@ def test_fp16_range_overflow_is_loud(oracle_sd):
         assert torch.isfinite(q0).all() and net.overflow_count() == 0
         for a, b in zip((r0, w0, o0, r, w, o), (ref[1], ref[2], ref[3]) * 2):
             assert (a.cpu() - b).abs().max().item() <= 1e-4
+    # the same inside the encoder: first U-Net layer scaled so that its activations leave fp16's range -> NaN planes, NaN outputs, counted
+    sd2 = {k: v.clone() for k, v in oracle_sd.items()}
+    sd2["encoder.unet.down_convs.0.conv1.weight"] = sd2["encoder.unet.down_convs.0.conv1.weight"] * 3.0e4
+    net2 = make_net("giga", sd2)
+    with torch.no_grad():
+        c = net2.encode_inputs(x.to(DEV))
+        assert not torch.isfinite(c["xz"]).all()
+        q2 = net2(x.to(DEV), p.to(DEV))[0]
+        assert torch.isnan(q2).any() and net2.overflow_count() > 0
 
 
 def test_decoder_head_combinations(net, oracle_sd):
