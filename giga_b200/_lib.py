@@ -47,6 +47,7 @@ SYMBOLS = {
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_detect_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_mise_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "giga_ctx_launch_count": (C.c_long, [C.c_void_p]),
     "giga_ctx_overflow_count": (C.c_long, [C.c_void_p, C.c_int]),
     "giga_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

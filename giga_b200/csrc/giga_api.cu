@@ -17,6 +17,7 @@
 #include "conv_in.cuh"
 #include "decoder.cuh"
 #include "decoder_ws.cuh"
+#include "mise.cuh"
 #include "planner.cuh"
 #include "unet.cuh"
 #include "unet_tall.cuh"
@@ -201,6 +202,11 @@ struct giga_ctx {
   struct DetGraph { unsigned long long key, epoch; cudaGraphExec_t exec; long launches; };
   std::vector<DetGraph> det_graphs;
   cudaStream_t st_graph = nullptr;
+  // Generator3D occupancy sweep (mise.cuh): dense MISE state for one scene
+  int mise_R = 0;
+  unsigned char *d_mise_pstate = nullptr, *d_mise_level = nullptr, *d_mise_active = nullptr;
+  float *d_mise_val = nullptr, *d_mise_qpts = nullptr, *d_mise_occ = nullptr;
+  int *d_mise_qidx = nullptr, *d_mise_count = nullptr;
   long launches = 0;
   bool attrs_set = false;
   // cross-stream ordering of the shared workspaces: every public entry point that enqueues work records ev_order on its
@@ -582,6 +588,12 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   if (ctx->st_compute) cudaStreamDestroy(ctx->st_compute);
   if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
   if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+  {
+    void* mp[] = {ctx->d_mise_pstate, ctx->d_mise_level, ctx->d_mise_active, ctx->d_mise_val, ctx->d_mise_qpts, ctx->d_mise_occ, ctx->d_mise_qidx,
+                  ctx->d_mise_count};
+    for (void* q : mp)
+      if (q) cudaFree(q);
+  }
   if (ctx->d_hc) cudaFree(ctx->d_hc);
   if (ctx->d_sched) cudaFree(ctx->d_sched);
   if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
@@ -1582,6 +1594,67 @@ int giga_detect_host(giga_ctx* ctx, const float* tsdf, const float* tsdf_process
   memcpy(out_width, ho + 5 * bk, sizeof(float) * bk);
   memcpy(index, ho + 6 * bk, sizeof(int) * bk);
   memcpy(count, ho + 7 * bk, sizeof(int) * B);
+  return GIGA_OK;
+}
+
+int giga_mise_sweep(giga_ctx* ctx, const float* planes, int resolution0, int upsampling_steps, double threshold, double box_size, float* value_grid,
+                    int* stats, void* stream) {
+  if (!ctx || !planes || !value_grid || resolution0 < 1 || upsampling_steps < 1 || upsampling_steps > 6)
+    return fail(GIGA_EINVAL, "giga_mise_sweep: bad argument (upsampling_steps 1..6; use giga_decode on a regular grid for 0)");
+  const long R = (long)resolution0 << upsampling_steps;
+  if (R > 512) return fail(GIGA_EINVAL, "giga_mise_sweep: resolution0 * 2^upsampling_steps must be <= 512");
+  if (!ctx->committed || !(ctx->heads & GIGA_HEAD_TSDF)) return fail(GIGA_ESTATE, "giga_mise_sweep: no committed TSDF head (decoder_tsdf)");
+  if (int r = set_device(ctx)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);
+  const long L = R + 1, np = L * L * L, nc = R * R * R;
+  if (ctx->mise_R != (int)R) {
+    CU_TRY(cudaDeviceSynchronize());
+    void** mp[] = {(void**)&ctx->d_mise_pstate, (void**)&ctx->d_mise_level, (void**)&ctx->d_mise_active, (void**)&ctx->d_mise_val, (void**)&ctx->d_mise_qpts,
+                   (void**)&ctx->d_mise_occ, (void**)&ctx->d_mise_qidx, (void**)&ctx->d_mise_count};
+    for (void** q : mp) { if (*q) cudaFree(*q); *q = nullptr; }
+    ctx->mise_R = 0;
+    CU_TRY(cudaMalloc(&ctx->d_mise_pstate, np));
+    CU_TRY(cudaMalloc(&ctx->d_mise_level, nc));
+    CU_TRY(cudaMalloc(&ctx->d_mise_active, nc));
+    CU_TRY(cudaMalloc(&ctx->d_mise_val, sizeof(float) * np));
+    CU_TRY(cudaMalloc(&ctx->d_mise_qpts, sizeof(float) * 3 * np));
+    CU_TRY(cudaMalloc(&ctx->d_mise_occ, sizeof(float) * np));
+    CU_TRY(cudaMalloc(&ctx->d_mise_qidx, sizeof(int) * np));
+    CU_TRY(cudaMalloc(&ctx->d_mise_count, sizeof(int)));
+    ctx->mise_R = (int)R;
+  }
+  const MiseDims d = {(int)R, (int)L, upsampling_steps};
+  const int gp = (int)((np + 255) / 256), gc = (int)((nc + 255) / 256);
+  { LaunchScope ls(ctx, "mise:init", st);
+    mise_init_kernel<<<gp, 256, 0, st>>>(d, ctx->d_mise_pstate, ctx->d_mise_val, ctx->d_mise_level, ctx->d_mise_active, ctx->d_mise_count); }
+  int iters = 0;
+  long total = 0;
+  for (;; ++iters) {
+    if (iters > 64) return fail(GIGA_ESTATE, "giga_mise_sweep: no convergence after 64 iterations");
+    { LaunchScope ls(ctx, "mise:collect", st);
+      mise_collect_kernel<<<gp, 256, 0, st>>>(d, ctx->d_mise_pstate, box_size, ctx->d_mise_count, ctx->d_mise_qidx, ctx->d_mise_qpts, (int)np); }
+    int n = 0;   // the one host round trip per level: the size of the next decoder launch (the reference moves every value through the host)
+    CU_TRY(cudaMemcpyAsync(&n, ctx->d_mise_count, sizeof n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (n == 0) break;
+    total += n;
+    if (int r = launch_decode(ctx, planes, 1, ctx->d_mise_qpts, n, GIGA_HEAD_TSDF, nullptr, 0, 0u, nullptr, nullptr, nullptr, ctx->d_mise_occ, st)) return r;
+    { LaunchScope ls(ctx, "mise:scatter", st);
+      mise_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_mise_qidx, ctx->d_mise_occ, n, ctx->d_mise_pstate, ctx->d_mise_val, ctx->d_mise_count); }
+    { LaunchScope ls(ctx, "mise:mark", st);
+      mise_mark_kernel<<<gc, 256, 0, st>>>(d, ctx->d_mise_pstate, ctx->d_mise_val, ctx->d_mise_level, ctx->d_mise_active, threshold); }
+    { LaunchScope ls(ctx, "mise:subdivide", st);
+      mise_apply_kernel<<<gc, 256, 0, st>>>(d, ctx->d_mise_pstate, ctx->d_mise_level, ctx->d_mise_active); }
+  }
+  const int gl = (int)((L * L + 255) / 256);
+  { LaunchScope ls(ctx, "mise:dense", st);
+    mise_dense_kernel<0><<<gl, 256, 0, st>>>(d, ctx->d_mise_pstate, ctx->d_mise_val, value_grid);
+    mise_dense_kernel<1><<<gl, 256, 0, st>>>(d, ctx->d_mise_pstate, ctx->d_mise_val, value_grid);
+    mise_dense_kernel<2><<<gl, 256, 0, st>>>(d, ctx->d_mise_pstate, ctx->d_mise_val, value_grid);
+    ctx->launches += 2; }
+  CU_TRY(cudaGetLastError());
+  if (stats) { stats[0] = iters; stats[1] = (int)total; }
   return GIGA_OK;
 }
 

@@ -179,6 +179,20 @@ int giga_detect(giga_ctx *ctx, const float *tsdf, const float *tsdf_process, int
 int giga_detect_host(giga_ctx *ctx, const float *tsdf, const float *tsdf_process, int B, const giga_select_params *prm, int K,
                      int *count, float *score, int *index, float *out_rot, float *out_width, void *stream);
 
+/* Generator3D occupancy sweep ----------------------------------------------
+ * Replaces the MISE loop of `Generator3D.generate_from_latent` (ConvONets/conv_onet/generation.py:127-143) together with the Cython
+ * octree it drives (ConvONets/utils/libmise/mise.pyx): query -> eval_points/decode_occ -> update/subdivide until no grid point is
+ * unknown, then to_dense.  The reference moves every query batch and every value through the host; here the bookkeeping (dense
+ * restatement of the octree on the finest lattice), the point arithmetic (float64, rounded to fp32 as torch.FloatTensor does) and the
+ * TSDF-head evaluation stay on the device and only the per-level point COUNT (4 bytes) is read back.
+ * planes = the plane features of ONE scene ([3][1][40][40][32], as giga_encode writes them); resolution0 / upsampling_steps (>= 1) =
+ * Generator3D's arguments (16 / 3 by default: a 129^3 lattice); threshold = log(th) - log(1 - th) as generation.py:110 computes it;
+ * box_size = 1 + padding.  value_grid (device, fp32 [(R+1)^3], R = resolution0 << upsampling_steps) receives mesh_extractor.to_dense()
+ * (the reference's float64 grid holds the same fp32 values widened).  stats (host, optional) = {iterations, points evaluated}.
+ * Synchronises `stream` once per level. */
+int giga_mise_sweep(giga_ctx *ctx, const float *planes, int resolution0, int upsampling_steps, double threshold, double box_size,
+                    float *value_grid, int *stats, void *stream);
+
 /* introspection ------------------------------------------------------------------- */
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 long giga_ctx_launch_count(const giga_ctx *ctx);
