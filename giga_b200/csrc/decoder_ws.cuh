@@ -62,10 +62,10 @@ constexpr int WD_OFF_HC = WD_OFF_TINFO + WD_PTS * 24 * 4;        // 198,912: hea
 constexpr int WD_OFF_PTS = WD_OFF_HC + 4 * HC_SIZE * 4;          // 203,648: [2 buffers][128] float4 query points of the gathered tiles
 constexpr int WD_OFF_FIN = WD_OFF_PTS + 2 * WD_PTS * 16;         // 207,744: [3 chains][128] float4 partial fc_out sums of the second column half
 constexpr int WD_OFF_BAR = WD_OFF_FIN + 3 * WD_PTS * 16;         // 213,888
-constexpr int WD_NBAR = 22;
+constexpr int WD_NBAR = 27;
 constexpr int WD_SMEM_BYTES = WD_OFF_BAR + WD_NBAR * 8 + 32;
 constexpr int WD_THREADS = 448;
-constexpr int WD_TMEM_COLS = 256;                      // X[c] = 32c, Y[c] = 96 + 32c
+constexpr int WD_TMEM_COLS = 512;                      // two item sets (item k uses set k & 1 at column 256 (k & 1)): X[c] = 32c, Y[c] = 96 + 32c
 constexpr int WD_MAX_JOBS = 4;
 
 struct DecJob {
@@ -188,24 +188,29 @@ __device__ __forceinline__ void job_of_item(const DecArgs& a, int item, int& j, 
 
 
 // barriers (arrival counts; thread groups arrive once per WARP): 0-1 feat_ready[buf] (4 gather warps) | 2-3 feat_free[buf] (1) | 4-6 a_ready[c]
-//           (8 compute warps) | 7-9 acc_full[c] (1) | 10 wfull_fcc | 11 wempty_fcc (1) | 12-13 wfull_ch[2] | 14-15 wempty_ch[2] (1) | 16-19 item_bar[4] (1)
-//           | 20 tmem_free (8) | 21 fin_bar (4)
-constexpr int WB_FEAT_READY = 0, WB_FEAT_FREE = 2, WB_A_READY = 4, WB_ACC_FULL = 7, WB_WFULL_FCC = 10, WB_WEMPTY_FCC = 11, WB_WFULL_CH = 12,
-              WB_WEMPTY_CH = 14, WB_ITEM = 16, WB_TMEM_FREE = 20, WB_FIN = 21;
+//           (8 compute warps) | 7-12 acc_full[set][c] (1) | 13 wfull_fcc | 14 wempty_fcc (1) | 15-16 wfull_ch[2] | 17-18 wempty_ch[2] (1)
+//           | 19-22 item_bar[4] (1) | 23-24 tmem_free[set] (8) | 25 fin_bar (4) | 26 feat_first (12: the CTA's first tile is gathered by
+//           all twelve compute + gather warps -- at kernel start every SM gathers at once and nothing else can run yet)
+// Items alternate between two TMEM column sets and two acc_full barrier sets: the first contraction of item k + 1 (fc_c of block 0) is issued
+// while the compute threads are still in the fc_out epilogue of item k (which reads item k's set), and its completion must not advance a
+// barrier the compute threads have not yet waited on for item k's last layer (an mbarrier may not run two phases ahead of a waiter).
+constexpr int WB_FEAT_READY = 0, WB_FEAT_FREE = 2, WB_A_READY = 4, WB_ACC_FULL = 7, WB_WFULL_FCC = 13, WB_WEMPTY_FCC = 14, WB_WFULL_CH = 15,
+              WB_WEMPTY_CH = 17, WB_ITEM = 19, WB_TMEM_FREE = 23, WB_FIN = 25, WB_FEAT_FIRST = 26;
 
 // ---- gather warpgroup: one tile's 96 tri-plane features -> shared-memory A operand (hi | lo) of the fc_c contractions --------------
-__device__ __forceinline__ void wd_gather_item(const DecArgs& args, const DecJob& job, int b, int tile, uint8_t* smem, uint8_t* feat, float4* pout,
-                                               int wtid) {
-  const int warp4 = wtid >> 5, lane = wtid & 31;
+// One WARP gathers rows [row0, row0 + nrows) of the tile (nrows <= 32, a multiple of 4).
+__device__ __forceinline__ void wd_gather_rows(const DecArgs& args, const DecJob& job, int b, int tile, uint8_t* smem, uint8_t* feat, float4* pout,
+                                               int row0, int nrows) {
+  const int lane = threadIdx.x & 31;
   const int N = job.N;
   const int n0 = tile * WD_PTS;
-  float* tw_ = reinterpret_cast<float*>(smem + WD_OFF_TINFO) + warp4 * 32 * 24;
-  {
-    const int nq = min(n0 + warp4 * 32 + lane, N - 1);   // rows beyond N evaluate the last point (their outputs are not stored)
+  float* tw_ = reinterpret_cast<float*>(smem + WD_OFF_TINFO) + row0 * 24;
+  if (lane < nrows) {
+    const int nq = min(n0 + row0 + lane, N - 1);   // rows beyond N evaluate the last point (their outputs are not stored)
     TexInfo t;
     const float* pq = job.pts + ((size_t)b * N + nq) * 3;
     point_taps(pq, t);
-    pout[warp4 * 32 + lane] = make_float4(pq[0], pq[1], pq[2], 0.f);   // the compute thread of this row reads it back (fc_p)
+    pout[row0 + lane] = make_float4(pq[0], pq[1], pq[2], 0.f);   // the compute thread of this row reads it back (fc_p)
     int* ti = reinterpret_cast<int*>(tw_) + lane * 24;
     float* tf = tw_ + lane * 24 + 12;
 #pragma unroll
@@ -220,13 +225,13 @@ __device__ __forceinline__ void wd_gather_item(const DecArgs& args, const DecJob
   const float* pb[3];
 #pragma unroll
   for (int pl = 0; pl < 3; ++pl) pb[pl] = args.planes + ((size_t)pl * args.B + b) * (G2 * C) + lane;
-  uint8_t* fa = feat + (lane >> 3) * WD_KS_F + (lane & 7) * 2 + (warp4 * 32) * 16;
+  uint8_t* fa = feat + (lane >> 3) * WD_KS_F + (lane & 7) * 2 + row0 * 16;
   // lane = channel: every texel is one coalesced 128 B read.  Batches of 8 points: all 96 texel loads of a batch are issued before the
   // first dependent use (the feature stores below could alias the tap table as far as the compiler knows, so without the explicit
   // batching only one point's loads are in flight).
   constexpr int GB = 4;   // 48 loads in flight per warp (register budget: 448 threads -> 128 registers)
 #pragma unroll 1
-  for (int q0 = 0; q0 < ((args.debug & 1u) ? 0 : 32); q0 += GB) {
+  for (int q0 = 0; q0 < ((args.debug & 1u) ? 0 : nrows); q0 += GB) {
     float tex[GB][12];
 #pragma unroll
     for (int qq = 0; qq < GB; ++qq) {
@@ -264,8 +269,9 @@ __device__ __forceinline__ void wd_gather_item(const DecArgs& args, const DecJob
 template <int NH>
 __device__ __forceinline__ void wd_compute_item(const DecArgs& args, const DecJob& job, int b, int tile, uint8_t* smem, int wtid, int half, uint32_t tmem,
                                                 uint64_t* bars, uint32_t& pf, uint32_t u0, int k, unsigned long long* tlc, int& tslot) {
+  const int set = k & 1;
   uint64_t* a_ready = bars + WB_A_READY;
-  uint64_t* acc_full = bars + WB_ACC_FULL;
+  uint64_t* acc_full = bars + WB_ACC_FULL + 3 * set;
   uint64_t* wfull_ch = bars + WB_WFULL_CH;
   const int warp4 = wtid >> 5;
   const int N = job.N;
@@ -275,13 +281,14 @@ __device__ __forceinline__ void wd_compute_item(const DecArgs& args, const DecJo
   const float* hcs = reinterpret_cast<const float*>(smem + WD_OFF_HC);
   const int col0 = 16 * half;
   auto stamp = [&]() {
-    if (tlc && wtid == 0 && half == 0 && tslot < 28) tlc[tslot] = globaltimer_ns();
+    if (tlc && wtid == 0 && half == 0 && tslot < 21) tlc[tslot] = globaltimer_ns();
     ++tslot;
   };
   stamp();
 
   // ---- fc_p on CUDA cores; the point was parked in shared memory by the gather thread of this row ----
-  tc::mbar_wait(&bars[WB_FEAT_READY + (k & 1)], (uint32_t)((k >> 1) & 1));
+  if (k == 0) tc::mbar_wait(&bars[WB_FEAT_FIRST], 0u);
+  else tc::mbar_wait(&bars[WB_FEAT_READY + (k & 1)], (uint32_t)(((k >> 1) - (1 - (k & 1))) & 1));
   const float4 pxyz = reinterpret_cast<const float4*>(smem + WD_OFF_PTS)[(k & 1) * WD_PTS + wtid];
   const float px = pxyz.x, py = pxyz.y, pz = pxyz.z;
   float h[NH][16];
@@ -300,7 +307,7 @@ __device__ __forceinline__ void wd_compute_item(const DecArgs& args, const DecJo
     }
   }
 
-  const uint32_t trow = tmem + ((uint32_t)(warp4 * 32) << 16) + col0;
+  const uint32_t trow = tmem + ((uint32_t)(warp4 * 32) << 16) + 256 * set + col0;
 #pragma unroll 1
   for (int blk = 0; blk < 5; ++blk) {
     const uint32_t u = u0 + blk;
@@ -313,8 +320,8 @@ __device__ __forceinline__ void wd_compute_item(const DecArgs& args, const DecJo
       const bool e1 = ph < NH;
       const uint32_t t_cur = trow + (e1 ? 96 : 0) + 32 * c;
       const float* bias = cb + (e1 ? NH * 32 : 0) + c * 32;
-      tc::mbar_wait(&acc_full[c], (pf >> c) & 1u);
-      pf ^= 1u << c;
+      tc::mbar_wait(&acc_full[c], (pf >> (3 * set + c)) & 1u);
+      pf ^= 1u << (3 * set + c);
       tc::fence_after_sync();
       uint32_t va[16];
       wd::tmem_ld16_async(t_cur, va);
@@ -335,15 +342,15 @@ __device__ __forceinline__ void wd_compute_item(const DecArgs& args, const DecJo
   for (int c = 0; c < NH; ++c) {
     const int head = head0 + c;
     const float* W = hcs + head * HC_SIZE;
-    tc::mbar_wait(&acc_full[c], (pf >> c) & 1u);
-    pf ^= 1u << c;
+    tc::mbar_wait(&acc_full[c], (pf >> (3 * set + c)) & 1u);
+    pf ^= 1u << (3 * set + c);
     tc::fence_after_sync();
     uint32_t va[16];
     wd::tmem_ld16_async(trow + 96 + 32 * c, va);
     wd::tmem_ld_wait16(va);
     if (c == NH - 1) {   // this thread's last TMEM read of the item: the next item's first MMA may overwrite Y
       tc::fence_before_sync();
-      wd::warp_arrive(&bars[WB_TMEM_FREE]);
+      wd::warp_arrive(&bars[WB_TMEM_FREE + set]);
     }
     float v[16];
 #pragma unroll
@@ -384,8 +391,8 @@ __device__ __forceinline__ void wd_compute_item(const DecArgs& args, const DecJo
           args.qual[idx] = args.raw ? r.x : 1.f / (1.f + expf(-r.x));
         } else if (head == 1) {
           const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
-          const float d = args.raw ? 1.f : fmaxf(nrm, 1e-12f);
-          st4(args.rot + idx * 4, make_float4(r.x / d, r.y / d, r.z / d, r.w / d));
+          const float inv = args.raw ? 1.f : 1.f / fmaxf(nrm, 1e-12f);   // one IEEE division, four multiplies (<= 1 ulp from x / d)
+          st4(args.rot + idx * 4, make_float4(r.x * inv, r.y * inv, r.z * inv, r.w * inv));
         } else if (head == 2) {
           args.width[idx] = r.x;
         } else {
@@ -399,11 +406,11 @@ __device__ __forceinline__ void wd_compute_item(const DecArgs& args, const DecJo
 
 // ---- the MMA-issue lane's work on one item ---------------------------------------------------------------------------------
 template <int NH>
-__device__ __forceinline__ void wd_issue_item(uint8_t* smem, uint32_t tmem, uint64_t* bars, uint32_t& pa, uint32_t u0, int k, unsigned debug) {
+__device__ __forceinline__ void wd_issue_item(uint8_t* smem, uint32_t tmem, uint64_t* bars, uint32_t& pa, uint32_t u0, int k, unsigned debug, long long* iacc) {
   uint64_t* feat_ready = bars + WB_FEAT_READY;
   uint64_t* feat_free = bars + WB_FEAT_FREE;
   uint64_t* a_ready = bars + WB_A_READY;
-  uint64_t* acc_full = bars + WB_ACC_FULL;
+  uint64_t* acc_full = bars + WB_ACC_FULL + 3 * (k & 1);
   uint64_t* wfull_fcc = bars + WB_WFULL_FCC;
   uint64_t* wempty_fcc = bars + WB_WEMPTY_FCC;
   uint64_t* wfull_ch = bars + WB_WFULL_CH;
@@ -413,14 +420,16 @@ __device__ __forceinline__ void wd_issue_item(uint8_t* smem, uint32_t tmem, uint
   const int buf = k & 1;
   const uint32_t f_hi = tc::smem_u32(smem + WD_OFF_FEAT + buf * WD_FEAT_BYTES), f_lo = f_hi + 12 * WD_KS_F;
   const uint32_t wc_hi = tc::smem_u32(smem + WD_OFF_FCC), wc_lo = wc_hi + 12 * KS_WC;
-  const uint32_t X = tmem, Y = X + 96;
+  const uint32_t X = tmem + 256 * (k & 1), Y = X + 96;
   // descriptors are built once per item; advancing the start address by `bytes` is one add on the low word (addresses < 256 KB)
   const uint64_t d_fhi = tc::make_desc(f_hi, WD_KS_F, 128), d_flo = tc::make_desc(f_lo, WD_KS_F, 128);
   const uint64_t d_wchi = tc::make_desc(wc_hi, KS_WC, 128), d_wclo = tc::make_desc(wc_lo, KS_WC, 128);
   const uint64_t d_w = tc::make_desc(tc::smem_u32(smem + WD_OFF_CH), 512, 128);
   auto issue_fcc = [&](uint32_t u) {   // Y[0..NH) <- feat . Wc^T  (fresh)
+    const long long ta = iacc ? clock64() : 0;
     tc::mbar_wait(wfull_fcc, u & 1u);
     tc::fence_after_sync();
+    const long long tb = iacc ? clock64() : 0;
 #pragma unroll
     for (int ks = 0; ks < 6; ++ks) {
       if ((debug & 2u) && ks > 0) break;
@@ -431,6 +440,7 @@ __device__ __forceinline__ void wd_issue_item(uint8_t* smem, uint32_t tmem, uint
       tc::mma_f16(Y, ah, bl, IDESC_C, 1u);
     }
     tc::mma_commit(wempty_fcc);
+    if (iacc) { iacc[0] += tb - ta; iacc[1] += clock64() - tb; }
   };
   // D <- (+)= A . W^T with A at columns `a`: K-step ks has its hi halfs in 8 columns at a + 16 ks, its lo halfs in the next 8  (W at byte offset w_off of the chain stages: hi, lo at +2048; [k-chunk 4][n 32][8 halfs])
   auto issue_layer = [&](uint32_t d, uint32_t a, uint32_t w_off, uint32_t accumulate) {
@@ -442,9 +452,12 @@ __device__ __forceinline__ void wd_issue_item(uint8_t* smem, uint32_t tmem, uint
       wd::mma_ts(d, a + ks * 16, bl, IDESC_32, 1u);
     }
   };
-  tc::mbar_wait(&feat_ready[buf], (uint32_t)((k >> 1) & 1));   // features of this item are in shared memory
-  if (k > 0) tc::mbar_wait(&bars[WB_TMEM_FREE], (uint32_t)((k - 1) & 1));   // the compute threads have read the previous item's last results
+  const long long t_item = iacc ? clock64() : 0;
+  if (k == 0) tc::mbar_wait(&bars[WB_FEAT_FIRST], 0u);   // features of this item are in shared memory (the first tile has its own barrier)
+  else tc::mbar_wait(&feat_ready[buf], (uint32_t)(((k >> 1) - (1 - (k & 1))) & 1));
+  if (k > 1) tc::mbar_wait(&bars[WB_TMEM_FREE + (k & 1)], (uint32_t)(((k >> 1) - 1) & 1));   // the compute threads have read the last results of item k - 2 (same set)
   tc::fence_after_sync();
+  if (iacc) iacc[6] += clock64() - t_item;
   issue_fcc(u0);
 #pragma unroll
   for (int c = 0; c < NH; ++c) tc::mma_commit(&acc_full[c]);
@@ -455,11 +468,14 @@ __device__ __forceinline__ void wd_issue_item(uint8_t* smem, uint32_t tmem, uint
     const uint32_t w0 = (u & 1) * wd_chain_bytes(3), w1 = w0 + NH * 4096;   // byte offsets within the chain stages
 #pragma unroll
     for (int c = 0; c < NH; ++c) {   // fc_0: X[c] <- A(Y[c]) . W0^T
+      const long long ta = iacc ? clock64() : 0;
       tc::mbar_wait(&a_ready[c], (pa >> c) & 1u);
       pa ^= 1u << c;
       tc::fence_after_sync();
+      const long long tb = iacc ? clock64() : 0;
       issue_layer(X + 32 * c, Y + 32 * c, w0 + c * 4096, 0u);
       tc::mma_commit(&acc_full[c]);
+      if (iacc) { iacc[2] += tb - ta; iacc[3] += clock64() - tb; }
     }
     if (blk < 4) {   // fc_c of the next block: overwrites Y (its A contents were consumed by the fc_0 MMAs just issued); runs during E2
       issue_fcc(u + 1);
@@ -467,11 +483,14 @@ __device__ __forceinline__ void wd_issue_item(uint8_t* smem, uint32_t tmem, uint
     }
 #pragma unroll
     for (int c = 0; c < NH; ++c) {   // fc_1: Y[c] (+)= A(X[c]) . W1^T
+      const long long ta = iacc ? clock64() : 0;
       tc::mbar_wait(&a_ready[c], (pa >> c) & 1u);
       pa ^= 1u << c;
       tc::fence_after_sync();
+      const long long tb = iacc ? clock64() : 0;
       issue_layer(Y + 32 * c, X + 32 * c, w1 + c * 4096, blk < 4 ? 1u : 0u);
       tc::mma_commit(&acc_full[c]);
+      if (iacc) { iacc[4] += tb - ta; iacc[5] += clock64() - tb; }
     }
     tc::mma_commit(&wempty_ch[u & 1]);
   }
@@ -490,12 +509,15 @@ __global__ void __launch_bounds__(WD_THREADS, 1) decode_points_ws_kernel(const _
   if (warp == 13) tc::tmem_alloc(tmem_slot, WD_TMEM_COLS);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars[WB_FEAT_READY + i], 4); tc::mbar_init(&bars[WB_FEAT_FREE + i], 1); }   // counts in warps
-    for (int i = 0; i < 3; ++i) { tc::mbar_init(&bars[WB_A_READY + i], 8); tc::mbar_init(&bars[WB_ACC_FULL + i], 1); }
+    for (int i = 0; i < 3; ++i) tc::mbar_init(&bars[WB_A_READY + i], 8);
+    for (int i = 0; i < 6; ++i) tc::mbar_init(&bars[WB_ACC_FULL + i], 1);
     tc::mbar_init(&bars[WB_WFULL_FCC], 1); tc::mbar_init(&bars[WB_WEMPTY_FCC], 1);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars[WB_WFULL_CH + i], 1); tc::mbar_init(&bars[WB_WEMPTY_CH + i], 1); }
     for (int i = 0; i < 4; ++i) tc::mbar_init(&item_bar[i], 1);
     tc::mbar_init(&bars[WB_TMEM_FREE], 8);
+    tc::mbar_init(&bars[WB_TMEM_FREE + 1], 8);
     tc::mbar_init(&bars[WB_FIN], 4);
+    tc::mbar_init(&bars[WB_FEAT_FIRST], 12);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int e = tid; e < 4 * HC_SIZE / 4; e += WD_THREADS)   // head constants (parameters: not written by the preceding kernels)
@@ -544,7 +566,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) decode_points_ws_kernel(const _
         if (u % 5 == 0) item_at((int)(u / 5) + 1);   // the gather warpgroup works one item ahead of the chains
         int nh;
         const uint8_t* blob = blob_of(item, nh);
-        if (u >= 1) tc::mbar_wait_relaxed(wempty_fcc, (u - 1) & 1u);
+        if (u >= 1) tc::mbar_wait(wempty_fcc, (u - 1) & 1u);   // tight poll: the single fc_c buffer's refill is on the issue lane's critical path
         tc::mbar_arrive_expect_tx(wfull_fcc, (uint32_t)wd_fcc_bytes(nh));
         tc::bulk_g2s(smem + WD_OFF_FCC, blob + (size_t)(u % 5) * wd_block_bytes(nh), (uint32_t)wd_fcc_bytes(nh), wfull_fcc);
         return true;
@@ -580,14 +602,21 @@ __global__ void __launch_bounds__(WD_THREADS, 1) decode_points_ws_kernel(const _
     // ============================ MMA issue ============================
     if (tc::elect_one()) {
       uint32_t pa = 0u;
+      long long iacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // debug cycle accounting of the issue lane (tools/decode_timeline.py)
+      long long* iacc = tlc ? iacc_ : nullptr;
+      const long long t_begin = clock64();
 #pragma unroll 1
       for (int k = 0;; ++k) {
         const int item = next_item(k);
         if (item < 0) break;
         int j, b, tile;
         wd::job_of_item(args, item, j, b, tile);
-        if (args.job[j].type == 0) wd_issue_item<3>(smem, tmem, bars, pa, (uint32_t)k * 5u, k, args.debug);
-        else wd_issue_item<1>(smem, tmem, bars, pa, (uint32_t)k * 5u, k, args.debug);
+        if (args.job[j].type == 0) wd_issue_item<3>(smem, tmem, bars, pa, (uint32_t)k * 5u, k, args.debug, iacc);
+        else wd_issue_item<1>(smem, tmem, bars, pa, (uint32_t)k * 5u, k, args.debug, iacc);
+      }
+      if (tlc) {
+        for (int i = 0; i < 7; ++i) tlc[i == 0 ? 28 : 20 + i] = (unsigned long long)iacc_[i];   // slots 28, 21..26
+        tlc[27] = (unsigned long long)(clock64() - t_begin);
       }
     }
     __syncwarp();
@@ -602,10 +631,13 @@ __global__ void __launch_bounds__(WD_THREADS, 1) decode_points_ws_kernel(const _
       int j, b, tile;
       wd::job_of_item(args, item, j, b, tile);
       if (k >= 2) tc::mbar_wait_relaxed(&bars[WB_FEAT_FREE + (k & 1)], (uint32_t)(((k >> 1) - 1) & 1));   // the fc_c MMAs of item k-2 have read this buffer
-      wd_gather_item(args, args.job[j], b, tile, smem, smem + WD_OFF_FEAT + (k & 1) * WD_FEAT_BYTES,
-                     reinterpret_cast<float4*>(smem + WD_OFF_PTS) + (k & 1) * WD_PTS, wtid);
+      // the CTA's first tile is gathered by all twelve warps: 16 rows per gather warp, 8 per compute warp
+      wd_gather_rows(args, args.job[j], b, tile, smem, smem + WD_OFF_FEAT + (k & 1) * WD_FEAT_BYTES,
+                     reinterpret_cast<float4*>(smem + WD_OFF_PTS) + (k & 1) * WD_PTS, k == 0 ? (wtid >> 5) * 16 : (wtid >> 5) * 32, k == 0 ? 16 : 32);
       tc::fence_smem_to_async();
-      wd::warp_arrive(&bars[WB_FEAT_READY + (k & 1)]);
+      wd::warp_arrive(&bars[k == 0 ? WB_FEAT_FIRST : WB_FEAT_READY + (k & 1)]);
+      if (k == 0) tc::mbar_wait(&bars[WB_FEAT_FIRST], 0u);   // the compute warps use tap-table rows 64..127 for the first tile: do not start the
+                                                             // next gather (which owns all 128 rows) before they are done
     }
   } else {
     // ============================ compute warpgroups (two threads per point: column halves) ============================
@@ -619,6 +651,11 @@ __global__ void __launch_bounds__(WD_THREADS, 1) decode_points_ws_kernel(const _
       int j, b, tile;
       wd::job_of_item(args, item, j, b, tile);
       const DecJob& job = args.job[j];
+      if (k == 0) {   // help gathering the CTA's first tile: rows 64 + 8 * warp
+        wd_gather_rows(args, job, b, tile, smem, smem + WD_OFF_FEAT, reinterpret_cast<float4*>(smem + WD_OFF_PTS), 64 + 8 * warp, 8);
+        tc::fence_smem_to_async();
+        wd::warp_arrive(&bars[WB_FEAT_FIRST]);
+      }
       if (job.type == 0) wd_compute_item<3>(args, job, b, tile, smem, wtid, half, tmem, bars, pf, (uint32_t)k * 5u, k, tlc, tslot);
       else wd_compute_item<1>(args, job, b, tile, smem, wtid, half, tmem, bars, pf, (uint32_t)k * 5u, k, tlc, tslot);
     }

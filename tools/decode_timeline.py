@@ -30,13 +30,15 @@ n = lib.giga_debug_copy(eng.h, b"timeline", C.c_void_p(buf.data_ptr()), buf.nume
 assert n > 0, lib.giga_last_error()
 torch.cuda.synchronize()
 t = buf[:n].cpu().numpy().view(np.uint64).reshape(-1, 32).astype(np.int64)
+acct = t[:, 21:29].copy()
+t[:, 21:32] = 0
 t0 = t[t > 0].min()
 rel = np.where(t > 0, (t - t0) / 1000.0, np.nan)
 print("decode_points_ws CTAs", len(t), "kernel span us %.2f" % np.nanmax(rel))
 ends = np.nanmax(rel, axis=1)
 print("CTA end times us: min %.1f median %.1f max %.1f" % (ends.min(), np.median(ends), ends.max()))
 lab = ["fc_p+blk0", "blk1", "blk2", "blk3", "blk4", "final"]
-for k in range(4):
+for k in range(3):
     seg = rel[:, 7 * k:7 * k + 7]
     ok = ~np.isnan(seg).any(axis=1)
     if not ok.any():
@@ -46,3 +48,8 @@ for k in range(4):
     print(f"item ordinal {k}: {ok.sum()} CTAs, start median {np.median(seg[ok, 0]):.1f} us (gap after previous item {np.median(gap):.2f}), "
           f"duration median {np.median(seg[ok, 6] - seg[ok, 0]):.2f} (min {np.min(seg[ok, 6] - seg[ok, 0]):.2f}, max {np.max(seg[ok, 6] - seg[ok, 0]):.2f})")
     print("   phases: " + "  ".join(f"{l} {np.median(d[:, i]):.2f}" for i, l in enumerate(lab)))
+m = np.median(acct, axis=0)
+print("MMA-issue lane cycle accounting (median over CTAs), total %.0f cycles:" % m[6])
+for n_, v in zip(["issue fc_c batch", "wait a_ready (E1 -> fc_0)", "issue fc_0", "wait a_ready (E2 -> fc_1)", "issue fc_1", "wait item start (features / TMEM free)", None, "wait fc_c weights"], m):
+    if n_:
+        print("   %-40s %8.0f  (%.1f %%)" % (n_, v, 100 * v / m[6]))
