@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """One bench step under a profiler: 3 warm-up steps + 1 profiled step of configs[1] (32 scenes, 2048 + 2048 points, all heads + arg-max),
 18 kernels per step, nothing else on the GPU.  Used by tools/gpu_r02_evidence.sh:
-    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:giga -s 54 -c 18 --csv --log-file launches.csv python tools/ncu_step.py
-    ncu --set full --clock-control none --import-source on -k regex:giga -s 54 -c 18 -o prof python tools/ncu_step.py"""
+    ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:conv_in_planes|xz_finish|conv_tall|pool_tall|decode_points|scene_argmax' -s 54 -c 18 --csv --log-file launches.csv python tools/ncu_step.py
+    ncu --set full --clock-control none --import-source on -k 'regex:conv_in_planes|xz_finish|conv_tall|pool_tall|decode_points|scene_argmax' -s 54 -c 18 -o prof python tools/ncu_step.py"""
 import os
 import sys
 
