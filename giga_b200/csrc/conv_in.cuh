@@ -53,9 +53,9 @@ struct ConvInCfg {
   static constexpr int SLAB_ROWS = TY + 2;           // iy rows of a staged slab (one halo row either side)
   static constexpr int SLAB_BYTES = SLAB_ROWS * CI_SLAB_W * 4;
   static constexpr int SLAB_STRIDE = (SLAB_BYTES + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
-  static constexpr int OFF_SLAB = (2 * RED * 4 + 127) / 128 * 128;
+  static constexpr int OFF_SLAB = (3 * RED * 4 + 127) / 128 * 128;   // red (two buffers) + xyacc
   static constexpr int OFF_BAR = OFF_SLAB + CI_NSTAGE * SLAB_STRIDE;
-  static constexpr int SMEM_BYTES = OFF_BAR + CI_NSTAGE * 8;     // red + xyacc + slab ring + mbarriers
+  static constexpr int SMEM_BYTES = OFF_BAR + CI_NSTAGE * 8;     // red x2 + xyacc + slab ring + mbarriers
   static_assert(CI_GROUP % TY == 0 && G % TY == 0, "tiles must nest in the canonical groups");
   static_assert(CPT % 2 == 0 && C % CS == 0, "channel pairs");
 };
@@ -76,8 +76,9 @@ __device__ __forceinline__ void conv_in_body(const CUtensorMap* tmap, float* __r
   using Cfg = ConvInCfg<CI_TY, CS>;
   constexpr int CI_NT = Cfg::NT, CI_THREADS = Cfg::THREADS, CI_RED = Cfg::RED, CPT = Cfg::CPT;
   constexpr int c0 = CZ * CPT;       // this CTA's first output channel
-  float* red = smem;                // [32*TY][44]
-  float* xyacc = red + CI_RED;      // [32*TY][44]  (col = ix)
+  float* red0 = smem;               // [2][32*TY][44]: step ix writes buffer ix & 1, so ONE CTA barrier per step suffices (the cross-thread
+                                    // sums of step ix overlap the FMA phase of step ix + 1 of the other warps)
+  float* xyacc = red0 + 2 * CI_RED; // [32*TY][44]  (col = ix)
 
   const int tile = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -133,6 +134,7 @@ __device__ __forceinline__ void conv_in_body(const CUtensorMap* tmap, float* __r
       win[1][t] = win[2][t];
     }
     read_slab(ix + 1, win[2]);
+    float* red = red0 + (ix & 1) * CI_RED;
     float2 f[CPT / 2];
 #pragma unroll
     for (int c = 0; c < CPT / 2; ++c) f[c] = P.b[c0 / 2 + c];
@@ -152,6 +154,7 @@ __device__ __forceinline__ void conv_in_body(const CUtensorMap* tmap, float* __r
       red[((2 * c + 1) * CI_TY + iyl) * CI_RED_STRIDE + iz] = r.y;
     }
     __syncthreads();
+    if (tid == 0 && ix + CI_NSTAGE <= G) fetch(ix + CI_NSTAGE);   // stage ix % 4 held slab ix, consumed by every thread at the top of step ix - 1
     // xy[c][iy][ix] = sum over iz (ascending, the reference's scatter order)
     if (tid < CPT * CI_TY) {
       const float* r = red + tid * CI_RED_STRIDE;
@@ -175,9 +178,9 @@ __device__ __forceinline__ void conv_in_body(const CUtensorMap* tmap, float* __r
       }
       st4(part + c * G + z, s);
     }
-    __syncthreads();
-    if (tid == 0 && ix + CI_NSTAGE <= G) fetch(ix + CI_NSTAGE);   // stage ix % 4 held slab ix, consumed by every thread at the top of step ix - 1
+    // no second barrier: the next step writes the OTHER red buffer, and a thread reaches the next barrier only after these sums
   }
+  __syncthreads();   // the last step's row sums (xyacc) are complete
 
   // ---- outputs as TALL pre-split operands of the first U-Net layer (unet_tall.cuh): image = plane * B + b, 16-byte elements of 8 channels ----
   // yz[c][iz][iy] = (sum over ix) / 40: this thread holds all CPT channels of pixel (row iz, col iy0 + iyl) of image 2B + b
