@@ -12,7 +12,10 @@ from .model import (ConvolutionalOccupancyNetwork, ConvolutionalOccupancyNetwork
 from .networks import get_network, load_network  # noqa: F401
 from . import detection_implicit  # noqa: F401
 from .detection_implicit import VGNImplicit  # noqa: F401
+from . import detection  # noqa: F401
+from .detection import VGN  # noqa: F401
 from . import generation  # noqa: F401
+from . import training  # noqa: F401
 from .generation import Generator3D  # noqa: F401
 
 __version__ = "0.1.0"

@@ -18,6 +18,8 @@
 #include "decoder.cuh"
 #include "decoder_ws.cuh"
 #include "mise.cuh"
+#include "vgn.cuh"
+#include "train.cuh"
 #include "planner.cuh"
 #include "unet.cuh"
 #include "unet_tall.cuh"
@@ -202,6 +204,15 @@ struct giga_ctx {
   struct DetGraph { unsigned long long key, epoch; cudaGraphExec_t exec; long launches; };
   std::vector<DetGraph> det_graphs;
   cudaStream_t st_graph = nullptr;
+  // VGN baseline (vgn.cuh)
+  bool has_vgn = false;
+  float* d_vgn = nullptr;        // packed parameters
+  float* d_vgn_act = nullptr;    // activations of vgn_cap_B scenes
+  int vgn_cap_B = 0;
+  // fused loss (train.cuh)
+  float* d_loss_part = nullptr;  // [loss_cap_B][4]
+  unsigned* d_loss_done = nullptr;
+  int loss_cap_B = 0;
   // Generator3D occupancy sweep (mise.cuh): dense MISE state for one scene
   int mise_R = 0;
   unsigned char *d_mise_pstate = nullptr, *d_mise_level = nullptr, *d_mise_active = nullptr;
@@ -594,6 +605,10 @@ void giga_ctx_destroy(giga_ctx* ctx) {
     for (void* q : mp)
       if (q) cudaFree(q);
   }
+  if (ctx->d_vgn) cudaFree(ctx->d_vgn);
+  if (ctx->d_vgn_act) cudaFree(ctx->d_vgn_act);
+  if (ctx->d_loss_part) cudaFree(ctx->d_loss_part);
+  if (ctx->d_loss_done) cudaFree(ctx->d_loss_done);
   if (ctx->d_hc) cudaFree(ctx->d_hc);
   if (ctx->d_sched) cudaFree(ctx->d_sched);
   if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
@@ -858,7 +873,37 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
   if (!ctx->d_heads) CU_TRY(cudaMalloc(&ctx->d_heads, sizeof(float) * 4 * DW_HEAD));
   CU_TRY(cudaMemcpy(ctx->d_heads, hb.data(), sizeof(float) * 4 * DW_HEAD, cudaMemcpyHostToDevice));
   ctx->heads = heads;
-  if (!ctx->has_encoder && !heads) return fail(GIGA_ESTATE, "giga_ctx_commit_params: no parameters were set");
+  // ---- VGN baseline (networks.py:48-63): encoder.conv{1,2,3}, decoder.conv{1,2,3}, conv_{qual,rot,width} ----
+  ctx->has_vgn = false;
+  if (ctx->raw.count("conv_qual.weight")) {
+    const VgnLayout VL = make_vgn_layout();
+    std::vector<float> vb(VL.total, 0.f);
+    const char* lname[6] = {"encoder.conv1", "encoder.conv2", "encoder.conv3", "decoder.conv1", "decoder.conv2", "decoder.conv3"};
+    for (int i = 0; i < 6; ++i) {
+      const int ci = kVgnCin[i], co = kVgnCout[i], k3 = kVgnK[i] * kVgnK[i] * kVgnK[i];
+      if (!get(ctx, std::string(lname[i]) + ".weight", (long)co * ci * k3, &w) || !get(ctx, std::string(lname[i]) + ".bias", co, &b))
+        return fail(GIGA_ESTATE, std::string(lname[i]) + ".{weight,bias}: missing or wrong size");
+      for (int o = 0; o < co; ++o)
+        for (int c = 0; c < ci; ++c)
+          for (int t = 0; t < k3; ++t) vb[VL.w[i] + ((long)c * k3 + t) * co + o] = w[((long)o * ci + c) * k3 + t];   // [co][ci][k^3] -> [ci][k^3][co]
+      memcpy(vb.data() + VL.b[i], b, sizeof(float) * co);
+    }
+    const char* hname[3] = {"conv_qual", "conv_rot", "conv_width"};
+    const int hch[3] = {1, 4, 1}, hoff[3] = {0, 1, 5};
+    for (int h = 0; h < 3; ++h) {
+      if (!get(ctx, std::string(hname[h]) + ".weight", (long)hch[h] * 16 * 125, &w) || !get(ctx, std::string(hname[h]) + ".bias", hch[h], &b))
+        return fail(GIGA_ESTATE, std::string(hname[h]) + ".{weight,bias}: missing or wrong size");
+      for (int o = 0; o < hch[h]; ++o) {
+        for (int c = 0; c < 16; ++c)
+          for (int t = 0; t < 125; ++t) vb[VL.w[6] + ((long)c * 125 + t) * 8 + hoff[h] + o] = w[((long)o * 16 + c) * 125 + t];
+        vb[VL.b[6] + hoff[h] + o] = b[o];
+      }
+    }
+    if (!ctx->d_vgn) CU_TRY(cudaMalloc(&ctx->d_vgn, sizeof(float) * VL.total));
+    CU_TRY(cudaMemcpy(ctx->d_vgn, vb.data(), sizeof(float) * VL.total, cudaMemcpyHostToDevice));
+    ctx->has_vgn = true;
+  }
+  if (!ctx->has_encoder && !heads && !ctx->has_vgn) return fail(GIGA_ESTATE, "giga_ctx_commit_params: no parameters were set");
   if (int r = ensure_attrs(ctx)) return r;
   CU_TRY(cudaDeviceSynchronize());   // pageable-source copies may still be in flight when cudaMemcpy returns
   ctx->committed = true;
@@ -1594,6 +1639,98 @@ int giga_detect_host(giga_ctx* ctx, const float* tsdf, const float* tsdf_process
   memcpy(out_width, ho + 5 * bk, sizeof(float) * bk);
   memcpy(index, ho + 6 * bk, sizeof(int) * bk);
   memcpy(count, ho + 7 * bk, sizeof(int) * B);
+  return GIGA_OK;
+}
+
+int giga_vgn_forward(giga_ctx* ctx, const float* tsdf, int B, float* qual, float* rot, float* width, void* stream) {
+  if (!ctx || !tsdf || !qual || !rot || !width || B <= 0) return fail(GIGA_EINVAL, "giga_vgn_forward: bad argument");
+  if (!ctx->committed || !ctx->has_vgn) return fail(GIGA_ESTATE, "giga_vgn_forward: VGN parameters not committed");
+  if (reinterpret_cast<uintptr_t>(rot) & 15) return fail(GIGA_EINVAL, "giga_vgn_forward: rot must be 16-byte aligned");
+  if (int r = set_device(ctx)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);
+  long act_per = 0;
+  for (long a : kVgnAct) act_per += a;
+  if (B > ctx->vgn_cap_B) {
+    CU_TRY(cudaDeviceSynchronize());
+    if (ctx->d_vgn_act) cudaFree(ctx->d_vgn_act);
+    ctx->d_vgn_act = nullptr;
+    ctx->vgn_cap_B = 0;
+    CU_TRY(cudaMalloc(&ctx->d_vgn_act, sizeof(float) * act_per * B));
+    ctx->vgn_cap_B = B;
+    ctx->graph_epoch++;
+  }
+  const VgnLayout VL = make_vgn_layout();
+  const float* P = ctx->d_vgn;
+  float* a[6];
+  {
+    float* q = ctx->d_vgn_act;
+    for (int i = 0; i < 6; ++i) { a[i] = q; q += kVgnAct[i] * B; }
+  }
+  auto grid = [&](int v) { return dim3((unsigned)ceil_div(v, 128), (unsigned)B); };
+  // <CIN, COUT, K, STRIDE, UPIN, DIN, DOUT, CI_CH, EPI>
+  { LaunchScope ls(ctx, "vgn:enc1", st); conv3d_kernel<1, 16, 5, 2, false, 40, 20, 1, 0><<<grid(8000), 128, 0, st>>>(tsdf, P + VL.w[0], P + VL.b[0], a[0], nullptr, nullptr); }
+  { LaunchScope ls(ctx, "vgn:enc2", st); conv3d_kernel<16, 32, 3, 2, false, 20, 10, 8, 0><<<grid(1000), 128, 0, st>>>(a[0], P + VL.w[1], P + VL.b[1], a[1], nullptr, nullptr); }
+  { LaunchScope ls(ctx, "vgn:enc3", st); conv3d_kernel<32, 64, 3, 2, false, 10, 5, 4, 0><<<grid(125), 128, 0, st>>>(a[1], P + VL.w[2], P + VL.b[2], a[2], nullptr, nullptr); }
+  { LaunchScope ls(ctx, "vgn:dec1", st); conv3d_kernel<64, 64, 3, 1, false, 5, 5, 4, 0><<<grid(125), 128, 0, st>>>(a[2], P + VL.w[3], P + VL.b[3], a[3], nullptr, nullptr); }
+  { LaunchScope ls(ctx, "vgn:dec2", st); conv3d_kernel<64, 32, 3, 1, true, 5, 10, 8, 0><<<grid(1000), 128, 0, st>>>(a[3], P + VL.w[4], P + VL.b[4], a[4], nullptr, nullptr); }
+  { LaunchScope ls(ctx, "vgn:dec3", st); conv3d_kernel<32, 16, 5, 1, true, 10, 20, 4, 0><<<grid(8000), 128, 0, st>>>(a[4], P + VL.w[5], P + VL.b[5], a[5], nullptr, nullptr); }
+  { LaunchScope ls(ctx, "vgn:heads", st); conv3d_kernel<16, 8, 5, 1, true, 20, 40, 8, 1><<<grid(G3), 128, 0, st>>>(a[5], P + VL.w[6], P + VL.b[6], qual, rot, width); }
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+int giga_loss(giga_ctx* ctx, const float* label_pred, const float* rot_pred, const float* width_pred, const float* occ_pred, const float* label,
+              const float* rotations, const float* width, const float* occ, int B, int M, float* loss_out, float* g_label, float* g_rot, float* g_width,
+              float* g_occ, void* stream) {
+  if (!ctx || !label_pred || !rot_pred || !width_pred || !label || !rotations || !width || !loss_out || B <= 0 || M < 0 || (M > 0 && (!occ_pred || !occ)))
+    return fail(GIGA_EINVAL, "giga_loss: bad argument");
+  if (int r = set_device(ctx)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);
+  if (B > ctx->loss_cap_B) {
+    CU_TRY(cudaDeviceSynchronize());
+    if (ctx->d_loss_part) cudaFree(ctx->d_loss_part);
+    ctx->d_loss_part = nullptr;
+    ctx->loss_cap_B = 0;
+    CU_TRY(cudaMalloc(&ctx->d_loss_part, sizeof(float) * 4 * B));
+    if (!ctx->d_loss_done) {
+      CU_TRY(cudaMalloc(&ctx->d_loss_done, sizeof(unsigned)));
+      CU_TRY(cudaMemset(ctx->d_loss_done, 0, sizeof(unsigned)));
+    }
+    ctx->loss_cap_B = B;
+  }
+  {
+    LaunchScope ls(ctx, "train:loss", st);
+    giga_loss_kernel<<<B, 256, 0, st>>>(label_pred, rot_pred, width_pred, occ_pred, label, rotations, width, occ, B, M, ctx->d_loss_part, ctx->d_loss_done,
+                                        loss_out, g_label, g_rot, g_width, g_occ);
+  }
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+int giga_adam_step(giga_ctx* ctx, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int step, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, void* stream) {
+  if (!ctx || !param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return fail(GIGA_EINVAL, "giga_adam_step: bad argument");
+  if (!(lr >= 0) || !(beta1 >= 0 && beta1 < 1) || !(beta2 >= 0 && beta2 < 1) || !(eps >= 0) || !(weight_decay >= 0))
+    return fail(GIGA_EINVAL, "giga_adam_step: invalid hyper-parameter");     // torch/optim/adam.py:52-62 raises ValueError for the same
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+    return fail(GIGA_EINVAL, "giga_adam_step: buffers must be 16-byte aligned");
+  if (int r = set_device(ctx)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);
+  // the scalar arithmetic of torch/optim/adam.py _single_tensor_adam, in Python floats (double), rounded to fp32 where ATen does
+  const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+  AdamScalars S;
+  S.beta1 = (float)beta1; S.beta2 = (float)beta2; S.one_minus_beta1 = (float)(1.0 - beta1); S.one_minus_beta2 = (float)(1.0 - beta2);
+  S.step_size = (float)(lr / bc1); S.bc2_sqrt = (float)std::sqrt(bc2); S.eps = (float)eps; S.weight_decay = (float)weight_decay;
+  const long n4 = n >> 2;
+  const int blocks = (int)std::max(1L, std::min((n4 + 255) / 256, (long)ctx->num_sms * 8));
+  {
+    LaunchScope ls(ctx, "train:adam", st);
+    adam_step_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, S);
+  }
+  CU_TRY(cudaGetLastError());
   return GIGA_OK;
 }
 

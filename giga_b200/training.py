@@ -14,14 +14,25 @@ falls back silently.  The bridge never runs on the CPU and is never used for inf
 
 Also here: `allreduce_gradients` -- the single flat all-reduce of the 581,863-element gradient buffer
 (2.33 MB) that a scene-sharded data-parallel step needs, one process per GPU.
+
+The training-step TAIL is native (csrc/train.cuh): `select(out)` (train_giga.py:153-158) and
+`loss_fn(y_pred, y)` (:161-174) with the reference's signatures and return values -- ONE CUDA launch that produces the loss terms and the
+gradient of loss.mean() with respect to the predictions (giga_loss), wired into autograd so `loss.backward()` hands those gradients to
+whatever produced the predictions -- and `Adam`, torch.optim.Adam's constructor for the arguments train_giga.py uses (:67), which keeps
+every parameter, gradient and moment in four flat buffers (the parameters and their .grad become views) and steps them in ONE launch
+(giga_adam_step); its `allreduce_gradients()` all-reduces that flat gradient buffer in place (no gather / scatter copies).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check, lib
 
 PLANES = ("xz", "xy", "yz")
 _AX = {"xz": (0, 2), "xy": (0, 1), "yz": (1, 2)}
@@ -165,3 +176,133 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, averag
             p.grad.copy_(g)
         off += n
     return flat
+
+
+# ------------------------------------------------------------------------------------------------------
+# the native training-step tail: fused loss (value + gradient) and flat Adam (csrc/train.cuh)
+# ------------------------------------------------------------------------------------------------------
+_ENGINES = {}
+
+
+def _engine(device: torch.device):
+    from .model import _Engine
+    if device.type != "cuda":
+        raise _lib.GigaError("giga_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _ENGINES:
+        _ENGINES[idx] = _Engine(torch.device("cuda", idx))
+    return _ENGINES[idx]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def select(out):
+    """train_giga.py:153-158"""
+    qual_out, rot_out, width_out, occ = out
+    return qual_out.squeeze(-1), rot_out.squeeze(1), width_out.squeeze(-1), torch.sigmoid(occ)
+
+
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, label_pred, rot_pred, width_pred, occ_pred, label, rotations, width, occ):
+        dev = label_pred.device
+        eng = _engine(dev)
+        f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        lp, rp, wp, op, la, ro, wi, oc = (f(t) for t in (label_pred, rot_pred, width_pred, occ_pred, label, rotations, width, occ))
+        B = lp.numel()
+        if rp.shape != (B, 4) or wp.numel() != B or ro.shape != (B, 2, 4) or op.dim() != 2 or op.shape[0] != B or oc.shape != op.shape \
+                or la.numel() != B or wi.numel() != B:
+            raise _lib.GigaError("loss_fn: label_pred/width_pred (B,), rotation_pred (B,4), occ_pred (B,M); label/width (B,), rotations (B,2,4), occ (B,M)")
+        M = op.shape[1]
+        out = torch.empty(5, device=dev, dtype=torch.float32)
+        grads = [torch.empty_like(t) for t in (lp, rp, wp, op)]
+        check(lib.giga_loss(eng.h, _ptr(lp), _ptr(rp), _ptr(wp), _ptr(op), _ptr(la), _ptr(ro), _ptr(wi), _ptr(oc), B, M, _ptr(out),
+                            *[_ptr(g) for g in grads], C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "giga_loss")
+        ctx.save_for_backward(*grads)
+        ctx.shapes = [t.shape for t in (label_pred, rot_pred, width_pred, occ_pred)]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        # only loss_all (element 4) is a training objective; the other four entries are the detached-by-use loss_dict means
+        scale = g[4]
+        return tuple((gr * scale).reshape(sh) for gr, sh in zip(ctx.saved_tensors, ctx.shapes)) + (None,) * 4
+
+
+def loss_fn(y_pred, y):
+    """train_giga.py:161-174 -> (loss, loss_dict)"""
+    label_pred, rotation_pred, width_pred, occ_pred = y_pred
+    label, rotations, width, occ = y
+    out = _FusedLoss.apply(label_pred, rotation_pred, width_pred, occ_pred, label, rotations, width, occ)
+    d = out.detach()
+    loss_dict = {"loss_qual": d[0], "loss_rot": d[1], "loss_width": d[2], "loss_occ": d[3], "loss_all": d[4]}
+    return out[4], loss_dict
+
+
+class Adam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0) for CUDA fp32 parameters, one launch per step.
+    The parameters are re-pointed at one flat buffer at construction (their values are kept; `.data` stays a live view, so the model sees
+    every update), and their `.grad` at a flat gradient buffer: backward() accumulates straight into it and zero_grad() is one memset."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameter")     # torch/optim/adam.py:52-62
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._flat = []
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.requires_grad]
+            if not ps:
+                continue
+            dev = ps[0].device
+            if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in ps):
+                raise _lib.GigaError("giga_b200.training.Adam takes fp32 parameters on one CUDA device")
+            n = sum((p.numel() + 3) // 4 * 4 for p in ps)
+            buf = {k: torch.zeros(n, device=dev, dtype=torch.float32) for k in ("param", "grad", "exp_avg", "exp_avg_sq")}
+            off = 0
+            with torch.no_grad():
+                for p in ps:
+                    m = p.numel()
+                    view = buf["param"][off:off + m].view(p.shape)
+                    view.copy_(p)
+                    p.data = view
+                    p.grad = buf["grad"][off:off + m].view(p.shape)
+                    off += (m + 3) // 4 * 4
+            self._flat.append((group, buf, n, dev))
+        self._steps = 0
+
+    def allreduce_gradients(self, group=None, average: bool = True):
+        """data-parallel exchange on the flat gradient buffer itself: one all-reduce per parameter group, in place"""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        for _, buf, _, _ in self._flat:
+            dist.all_reduce(buf["grad"], op=dist.ReduceOp.SUM, group=group)
+            if average:
+                buf["grad"] /= dist.get_world_size(group)
+
+    def zero_grad(self, set_to_none: bool = False):
+        """keeps the flat gradient buffer bound (set_to_none would detach the views)"""
+        for _, buf, _, _ in self._flat:
+            buf["grad"].zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self._steps += 1
+        for group, buf, n, dev in self._flat:
+            for p in group["params"]:
+                if p.requires_grad and (p.grad is None or p.grad.data_ptr() < buf["grad"].data_ptr()
+                                        or p.grad.data_ptr() >= buf["grad"].data_ptr() + 4 * n):
+                    raise _lib.GigaError("a parameter's .grad no longer views the flat gradient buffer (use this optimizer's zero_grad())")
+            b1, b2 = group["betas"]
+            check(lib.giga_adam_step(_engine(dev).h, _ptr(buf["param"]), _ptr(buf["grad"]), _ptr(buf["exp_avg"]), _ptr(buf["exp_avg_sq"]), n,
+                                     self._steps, float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "giga_adam_step")
+            # the kernel wrote through raw pointers: bump the autograd version counters so that readers which key on them (this package's
+            # parameter cache, autograd's saved-tensor checks) see the update
+            torch.autograd.graph.increment_version([p for p in group["params"] if p.requires_grad])
+        return loss

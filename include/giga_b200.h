@@ -179,6 +179,31 @@ int giga_detect(giga_ctx *ctx, const float *tsdf, const float *tsdf_process, int
 int giga_detect_host(giga_ctx *ctx, const float *tsdf, const float *tsdf_process, int B, const giga_select_params *prm, int K,
                      int *count, float *score, int *index, float *out_rot, float *out_width, void *stream);
 
+/* VGN baseline network -----------------------------------------------------
+ * Replaces `ConvNet.forward` (networks.py:48-63 with Encoder :172-188 and Decoder :191-212; `get_network("vgn")`): three stride-2
+ * Conv3d + ReLU, three Conv3d + ReLU with nearest up-sampling, the three k=5 heads with sigmoid / normalise / raw epilogues.
+ * Parameters are set by their reference state_dict keys (encoder.conv1.weight ... conv_width.bias) with giga_ctx_set_param*.
+ * tsdf [B][40][40][40] -> qual [B][64000], rot [B][64000][4] (the reference's (B,4,40,40,40) with the quaternion innermost: the layout
+ * giga_select_grasps takes), width [B][64000]; flat voxel index (ix*40 + iy)*40 + iz.  Device pointers, nothing synchronises. */
+int giga_vgn_forward(giga_ctx *ctx, const float *tsdf, int B, float *qual, float *rot, float *width, void *stream);
+
+/* Training-step tail ----------------------------------------------------------
+ * giga_loss replaces `loss_fn` of scripts/train_giga.py:161-195 and its autograd graph: the value AND the gradient of loss.mean() with
+ * respect to the four (post-`select`, :153-158) predictions in one launch.  label_pred [B] (probability), rot_pred [B][4], width_pred [B],
+ * occ_pred [B][M] (probability, sigmoid already applied); targets label [B], rotations [B][2][4], width [B], occ [B][M].
+ * loss_out [5] = loss_dict's means in its order: loss_qual, loss_rot, loss_width, loss_occ, loss_all.  g_* (each optional) receive
+ * d loss_all / d prediction with the shapes of the predictions.  F.binary_cross_entropy semantics (log clamp -100, backward
+ * (x - t) / max((1 - x) x, 1e-12)); torch.min's tie rule (half to each operand).  Device pointers, nothing synchronises. */
+int giga_loss(giga_ctx *ctx, const float *label_pred, const float *rot_pred, const float *width_pred, const float *occ_pred,
+              const float *label, const float *rotations, const float *width, const float *occ, int B, int M, float *loss_out,
+              float *g_label, float *g_rot, float *g_width, float *g_occ, void *stream);
+/* giga_adam_step replaces `torch.optim.Adam(net.parameters(), lr=args.lr).step()` (scripts/train_giga.py:67, 208-209; update rule of
+ * torch/optim/adam.py, amsgrad=False, maximize=False) over ONE flat fp32 buffer of n elements holding every parameter (and the same
+ * layout for grad / exp_avg / exp_avg_sq; 16-byte aligned device pointers): one launch instead of the optimizer's per-tensor lists.
+ * step = the 1-based step count (bias corrections are computed on the host in double like the Python implementation). */
+int giga_adam_step(giga_ctx *ctx, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long n, int step, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, void *stream);
+
 /* Generator3D occupancy sweep ----------------------------------------------
  * Replaces the MISE loop of `Generator3D.generate_from_latent` (ConvONets/conv_onet/generation.py:127-143) together with the Cython
  * octree it drives (ConvONets/utils/libmise/mise.pyx): query -> eval_points/decode_occ -> update/subdivide until no grid point is

@@ -41,8 +41,7 @@ def test_state_dict_matches_reference_inventory(golden):
         assert list(sd.keys()) == list(golden[f"keys_{name}"])
         assert [str(tuple(v.shape)) for v in sd.values()] == list(golden[f"shapes_{name}"])
     assert sum(p.numel() for p in giga_b200.get_network("giga").parameters()) == 581863
-    with pytest.raises(NotImplementedError):
-        giga_b200.get_network("vgn")
+    assert sum(p.numel() for p in giga_b200.get_network("vgn").parameters()) == 313238      # the baseline ConvNet (networks.py:48-63)
     with pytest.raises(KeyError):
         giga_b200.get_network("nope")
 
