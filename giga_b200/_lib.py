@@ -50,6 +50,10 @@ SYMBOLS = {
     "giga_vgn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_loss": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p]),
     "giga_adam_step": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_long, C.c_int] + [C.c_double] * 5 + [C.c_void_p]),
+    "giga_train_bind": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_train_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_mise_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "giga_ctx_launch_count": (C.c_long, [C.c_void_p]),
     "giga_ctx_overflow_count": (C.c_long, [C.c_void_p, C.c_int]),

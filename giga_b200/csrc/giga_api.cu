@@ -20,6 +20,7 @@
 #include "mise.cuh"
 #include "vgn.cuh"
 #include "train.cuh"
+#include "train_bwd.cuh"
 #include "planner.cuh"
 #include "unet.cuh"
 #include "unet_tall.cuh"
@@ -213,6 +214,32 @@ struct giga_ctx {
   float* d_loss_part = nullptr;  // [loss_cap_B][4]
   unsigned* d_loss_done = nullptr;
   int loss_cap_B = 0;
+  // native training step (train_bwd.cuh): bound parameter / gradient tensors, device-packed operands, gradient workspaces
+  struct Train {
+    static constexpr int kSlots = 28 + 4 * 34;
+    const float* val[kSlots] = {};
+    float* grad[kSlots] = {};
+    bool bound = false, table_dirty = true;
+    unsigned heads = 0;
+    PackEntry* d_tab = nullptr;
+    int n_tab = 0;
+    float* d_blob = nullptr;      // fp32 packed encoder operands (EncLayout's fp32 prefix) + data-gradient weights
+    long dg[10] = {};             // data-gradient weights of conv i: [co][9][ci] (concat layers: two blocks, one per source)
+    long blob_floats = 0;
+    float* d_heads = nullptr;     // [4][DW_HEAD]
+    float* d_cin = nullptr;       // conv_in [27][32] + [32]
+    int cap_B = 0;
+    float* d_g[kNumActs] = {};    // gradients w.r.t. the pre-activations of kActs[i] (same shapes as d_act)
+    float* d_gpre = nullptr;      // [3][B][32][1600]
+    float* d_gplanes = nullptr;   // [3][B][1600][32]
+    float* d_planes = nullptr;    // forward plane features
+    float* d_save = nullptr;      // decoder backward scratch
+    size_t save_cap = 0;
+    // the forward this backward belongs to
+    const float *x = nullptr, *p = nullptr, *pt = nullptr;
+    int B = 0, Ng = 0, No = 0, detach = 0;
+    bool fwd_valid = false;
+  } tr;
   // Generator3D occupancy sweep (mise.cuh): dense MISE state for one scene
   int mise_R = 0;
   unsigned char *d_mise_pstate = nullptr, *d_mise_level = nullptr, *d_mise_active = nullptr;
@@ -1938,3 +1965,5 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
 }
 
 }  // extern "C"
+
+#include "train_api.cuh"

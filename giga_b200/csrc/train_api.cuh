@@ -1,0 +1,460 @@
+// C-ABI entry points of the native training step (giga_train_bind / giga_train_forward / giga_train_backward); kernels in train_bwd.cuh.
+// Included at the end of giga_api.cu (same translation unit: the kernels' __constant__ symbol and the ctx helpers live there).
+#pragma once
+
+namespace {
+
+// slot table: [0] conv_in.weight [1] conv_in.bias; 2 + 2i / 3 + 2i: U-Net conv i weight / bias (kConvName order); 22 + 2i / 23 + 2i: upconv i;
+// 26 / 27 conv_final; 28 + 34 h: head h = fc_p (w, b), 5 x (fc_c, fc_0, fc_1) (w, b), fc_out (w, b)
+constexpr int TS_HEAD0 = 28, TS_HEAD = 34;
+
+std::string train_slot_name(int s) {
+  if (s == 0) return "encoder.conv_in.weight";
+  if (s == 1) return "encoder.conv_in.bias";
+  if (s < 22) return std::string("encoder.unet.") + kConvName[(s - 2) / 2] + ((s & 1) ? ".bias" : ".weight");
+  if (s < 26) return "encoder.unet.up_convs." + std::to_string((s - 22) / 2) + ".upconv" + ((s & 1) ? ".bias" : ".weight");
+  if (s < 28) return std::string("encoder.unet.conv_final") + ((s & 1) ? ".bias" : ".weight");
+  const int h = (s - TS_HEAD0) / TS_HEAD, r = (s - TS_HEAD0) % TS_HEAD;
+  const std::string pre = std::string("decoder_") + kHeadName[h] + ".";
+  const char* wb = (r & 1) ? ".bias" : ".weight";
+  if (r < 2) return pre + "fc_p" + wb;
+  if (r >= 32) return pre + "fc_out" + wb;
+  const int i = (r - 2) / 6, f = ((r - 2) % 6) / 2;
+  if (f == 0) return pre + "fc_c." + std::to_string(i) + wb;
+  return pre + "blocks." + std::to_string(i) + ".fc_" + std::to_string(f - 1) + wb;
+}
+
+long train_slot_numel(int s) {
+  if (s == 0) return 32 * 27;
+  if (s == 1) return 32;
+  if (s < 22) { const int i = (s - 2) / 2; return (s & 1) ? kConvCout[i] : (long)kConvCout[i] * kConvCin[i] * 9; }
+  if (s < 26) { const int i = (s - 22) / 2; return (s & 1) ? kUpCout[i] : (long)kUpCin[i] * kUpCout[i] * 4; }
+  if (s < 28) return (s & 1) ? 32 : 1024;
+  const int h = (s - TS_HEAD0) / TS_HEAD, r = (s - TS_HEAD0) % TS_HEAD, od = h == 1 ? 4 : 1;
+  if (r < 2) return (r & 1) ? 32 : 96;
+  if (r >= 32) return (r & 1) ? od : od * 32;
+  const int f = ((r - 2) % 6) / 2;
+  return (r & 1) ? 32 : (f == 0 ? 32 * 96 : 32 * 32);
+}
+
+// data-gradient instances of the forward conv kernel (HW, C of the incoming gradient, 0, C of the outgoing gradient, ...)
+using G_40 = Conv3x3Cfg<40, 32, 0, 32, 4, 32, 4, 16, false, 1>;
+using G_20a = Conv3x3Cfg<20, 64, 0, 32, 4, 32, 4, 16, false, 1>;
+using G_20b = Conv3x3Cfg<20, 64, 0, 64, 4, 64, 4, 16, false, 1>;
+using G_10a = Conv3x3Cfg<10, 128, 0, 64, 10, 32, 4, 16, false, 1>;
+using G_10b = Conv3x3Cfg<10, 128, 0, 128, 10, 32, 4, 16, false, 1>;
+using W_40 = WgradCfg<40, 4>;
+using W_20 = WgradCfg<20, 4>;
+using W_10 = WgradCfg<10, 10>;
+using TB_u0 = ConvTBwdCfg<10, 128, 64>;
+using TB_u1 = ConvTBwdCfg<20, 64, 32>;
+
+template <class K> constexpr int convT_wgrad_smem() { return (32 * K::PSX + 32 * 2 * K::R * K::GSW) * 4; }
+template <class K> constexpr int convT_dgrad_smem() { return (32 * K::COUT * 4 + 32 * K::PSG) * 4; }
+
+int train_attrs(giga_ctx* ctx) {
+  static bool done[64] = {};
+  if (done[ctx->device & 63]) return GIGA_OK;
+#define SET_G(K) CU_TRY(cudaFuncSetAttribute(conv3x3_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES))
+  SET_G(G_40); SET_G(G_20a); SET_G(G_20b); SET_G(G_10a); SET_G(G_10b);
+#undef SET_G
+  CU_TRY(cudaFuncSetAttribute(conv3x3_wgrad_kernel<W_40>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_40::SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(conv3x3_wgrad_kernel<W_20>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_20::SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(conv3x3_wgrad_kernel<W_10>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_10::SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(convT2x2_wgrad_kernel<TB_u0>, cudaFuncAttributeMaxDynamicSharedMemorySize, convT_wgrad_smem<TB_u0>()));
+  CU_TRY(cudaFuncSetAttribute(convT2x2_wgrad_kernel<TB_u1>, cudaFuncAttributeMaxDynamicSharedMemorySize, convT_wgrad_smem<TB_u1>()));
+  CU_TRY(cudaFuncSetAttribute(convT2x2_dgrad_kernel<TB_u0>, cudaFuncAttributeMaxDynamicSharedMemorySize, convT_dgrad_smem<TB_u0>()));
+  CU_TRY(cudaFuncSetAttribute(convT2x2_dgrad_kernel<TB_u1>, cudaFuncAttributeMaxDynamicSharedMemorySize, convT_dgrad_smem<TB_u1>()));
+  CU_TRY(cudaFuncSetAttribute(decode_points_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(conv_in_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(conv_in_planes_train_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvInCfg<5, 1>::SMEM_BYTES));
+  CU_TRY(cudaFuncSetAttribute(conv_in_planes_train_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvInCfg<1, 4>::SMEM_BYTES));
+  done[ctx->device & 63] = true;
+  return GIGA_OK;
+}
+
+// (re)build the packing table for the bound tensors and upload it
+int train_build_table(giga_ctx* ctx) {
+  auto& T = ctx->tr;
+  const EncLayout& L = ctx->el;
+  if (!T.d_blob) {
+    long o = L.tc_conv[0];   // the fp32 prefix of the inference blob layout: conv[i], bias[i], up_w, up_b, fin_w, fin_b
+    for (int i = 0; i < 10; ++i) { T.dg[i] = o; o += (long)kConvCin[i] * 9 * kConvCout[i]; }
+    T.blob_floats = o;
+    CU_TRY(cudaMalloc(&T.d_blob, sizeof(float) * o));
+    CU_TRY(cudaMemset(T.d_blob, 0, sizeof(float) * o));
+    CU_TRY(cudaMalloc(&T.d_heads, sizeof(float) * 4 * DW_HEAD));
+    CU_TRY(cudaMemset(T.d_heads, 0, sizeof(float) * 4 * DW_HEAD));
+    CU_TRY(cudaMalloc(&T.d_cin, sizeof(ConvInParams)));
+    CU_TRY(cudaMalloc(&T.d_tab, sizeof(PackEntry) * 256));
+  }
+  std::vector<PackEntry> tab;
+  auto add = [&](const float* src, float* dst, int O, int I, int Tt, int mode, int ld, int i0 = 0, int In = 0) {
+    PackEntry e = {src, dst, O, I, Tt, mode, ld, i0, In, 0};
+    tab.push_back(e);
+  };
+  float* E = T.d_blob;
+  add(T.val[0], T.d_cin, 32, 1, 27, 0, 32);
+  add(T.val[1], T.d_cin + 27 * 32, 32, 1, 1, 2, 0);
+  for (int i = 0; i < 10; ++i) {
+    const int ci = kConvCin[i], co = kConvCout[i];
+    add(T.val[2 + 2 * i], E + L.conv[i], co, ci, 9, 0, co);
+    add(T.val[3 + 2 * i], E + L.bias[i], co, 1, 1, 2, 0);
+    if (i == 6 || i == 8) {   // concat layers: one data-gradient block per source (upsampled | skip)
+      const int half = ci / 2;
+      add(T.val[2 + 2 * i], E + T.dg[i], co, ci, 9, 1, 0, 0, half);
+      add(T.val[2 + 2 * i], E + T.dg[i] + (long)co * 9 * half, co, ci, 9, 1, 0, half, half);
+    } else {
+      add(T.val[2 + 2 * i], E + T.dg[i], co, ci, 9, 1, 0, 0, ci);
+    }
+  }
+  for (int i = 0; i < 2; ++i) {
+    add(T.val[22 + 2 * i], E + L.up_w[i], kUpCin[i] * kUpCout[i] * 4, 1, 1, 2, 0);
+    add(T.val[23 + 2 * i], E + L.up_b[i], kUpCout[i], 1, 1, 2, 0);
+  }
+  add(T.val[26], E + L.fin_w, 32, 32, 1, 0, 32);
+  add(T.val[27], E + L.fin_b, 32, 1, 1, 2, 0);
+  for (int h = 0; h < 4; ++h) {
+    if (!(T.heads & (1u << h))) continue;
+    const float* const* v = T.val + TS_HEAD0 + TS_HEAD * h;
+    float* H = T.d_heads + (size_t)h * DW_HEAD;
+    const int od = h == 1 ? 4 : 1;
+    add(v[0], H + DW_FCP, 32, 3, 1, 0, 32);
+    add(v[1], H + DW_FCP + 96, 32, 1, 1, 2, 0);
+    for (int i = 0; i < 5; ++i) {
+      float* Bk = H + DW_BLOCK0 + i * DW_BLK;
+      add(v[2 + 6 * i], Bk + DW_BLK_FCC, 32, 96, 1, 0, 32);
+      add(v[3 + 6 * i], Bk + DW_BLK_BC, 32, 1, 1, 2, 0);
+      add(v[4 + 6 * i], Bk + DW_BLK_W0, 32, 32, 1, 0, 32);
+      add(v[5 + 6 * i], Bk + DW_BLK_B0, 32, 1, 1, 2, 0);
+      add(v[6 + 6 * i], Bk + DW_BLK_W1, 32, 32, 1, 0, 32);
+      add(v[7 + 6 * i], Bk + DW_BLK_B1, 32, 1, 1, 2, 0);
+    }
+    add(v[32], H + DW_OUT, od, 32, 1, 0, 4);
+    add(v[33], H + DW_OUT + 128, od, 1, 1, 2, 0);
+  }
+  if (tab.size() > 256) return fail(GIGA_ESTATE, "giga_train: packing table overflow");
+  CU_TRY(cudaDeviceSynchronize());   // a previous step's packing kernel may still read the table
+  CU_TRY(cudaMemcpy(T.d_tab, tab.data(), sizeof(PackEntry) * tab.size(), cudaMemcpyHostToDevice));
+  T.n_tab = (int)tab.size();
+  T.table_dirty = false;
+  return GIGA_OK;
+}
+
+int train_workspace(giga_ctx* ctx, int B) {
+  auto& T = ctx->tr;
+  if (B <= T.cap_B) return GIGA_OK;
+  CU_TRY(cudaDeviceSynchronize());
+  for (auto& p : T.d_g) { if (p) cudaFree(p); p = nullptr; }
+  float** one[] = {&T.d_gpre, &T.d_gplanes, &T.d_planes};
+  for (float** q : one) { if (*q) cudaFree(*q); *q = nullptr; }
+  T.cap_B = 0;
+  for (int i = 0; i < kNumActs; ++i) CU_TRY(cudaMalloc(&T.d_g[i], sizeof(float) * 3 * (size_t)B * kActs[i].ch * kActs[i].hw * kActs[i].hw));
+  CU_TRY(cudaMalloc(&T.d_gpre, sizeof(float) * 3 * (size_t)B * C * G2));
+  CU_TRY(cudaMalloc(&T.d_gplanes, sizeof(float) * 3 * (size_t)B * C * G2));
+  CU_TRY(cudaMalloc(&T.d_planes, sizeof(float) * 3 * (size_t)B * C * G2));
+  T.cap_B = B;
+  return GIGA_OK;
+}
+
+float* gact(giga_ctx* ctx, const char* name) {
+  for (int i = 0; i < kNumActs; ++i)
+    if (!strcmp(kActs[i].name, name)) return ctx->tr.d_g[i];
+  return nullptr;
+}
+
+template <class K>
+void launch_dgrad(giga_ctx* ctx, const char* name, int n_img, const float* gz, const float* w, const float* mask, float* out, cudaStream_t st) {
+  dim3 grid(K::NB * K::NCT, n_img);
+  LaunchScope ls(ctx, name, st);
+  conv3x3_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(gz, nullptr, w, mask, out, nullptr);
+}
+
+template <class K>
+void launch_wgrad(giga_ctx* ctx, const char* name, int n_img, const float* gz, const float* in, int cout, int cin_src, float* dW, int cin_total,
+                  float* db, cudaStream_t st) {
+  const int n_cc = (cout / 32) * (cin_src / 32), n_tiles = n_img * K::NB;
+  const int P = std::max(1, std::min(n_tiles, (3 * ctx->num_sms + n_cc - 1) / n_cc));
+  LaunchScope ls(ctx, name, st);
+  conv3x3_wgrad_kernel<K><<<dim3(n_cc, P), 256, K::SMEM_BYTES, st>>>(gz, in, n_img, cout, cin_src, dW, cin_total, db);
+}
+
+template <class K>
+void launch_convT_bwd(giga_ctx* ctx, const char* name, int n_img, const float* in, const float* gout, const float* w, float* gin, float* dW, float* db,
+                      cudaStream_t st) {
+  {
+    const int n_cc = (K::CIN / 32) * (K::COUT / 32), n_tiles = n_img * K::NB;
+    const int P = std::max(1, std::min(n_tiles, (2 * ctx->num_sms + n_cc - 1) / n_cc));
+    LaunchScope ls(ctx, name, st);
+    convT2x2_wgrad_kernel<K><<<dim3(n_cc, P), 256, convT_wgrad_smem<K>(), st>>>(in, gout, n_img, dW, db);
+  }
+  {
+    LaunchScope ls(ctx, name, st);
+    convT2x2_dgrad_kernel<K><<<dim3(K::NB * (K::CIN / 32), n_img), 256, convT_dgrad_smem<K>(), st>>>(gout, w, in, gin);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int giga_train_bind(giga_ctx* ctx, int n, const char* const* names, const float* const* values, float* const* grads) {
+  if (!ctx || n <= 0 || !names || !values || !grads) return fail(GIGA_EINVAL, "giga_train_bind: bad argument");
+  if (int r = set_device(ctx)) return r;
+  auto& T = ctx->tr;
+  std::map<std::string, int> slot;
+  for (int s = 0; s < giga_ctx::Train::kSlots; ++s) slot[train_slot_name(s)] = s;
+  const float* val[giga_ctx::Train::kSlots] = {};
+  float* grad[giga_ctx::Train::kSlots] = {};
+  for (int i = 0; i < n; ++i) {
+    if (!names[i] || !values[i]) return fail(GIGA_EINVAL, "giga_train_bind: null name or tensor");
+    auto it = slot.find(names[i]);
+    if (it == slot.end()) return fail(GIGA_EINVAL, std::string("giga_train_bind: unknown parameter '") + names[i] + "'");
+    if ((reinterpret_cast<uintptr_t>(values[i]) & 15) || (reinterpret_cast<uintptr_t>(grads[i]) & 15))
+      return fail(GIGA_EINVAL, std::string("giga_train_bind: '") + names[i] + "' is not 16-byte aligned");
+    val[it->second] = values[i];
+    grad[it->second] = grads[i];
+  }
+  for (int s = 0; s < 28; ++s)
+    if (!val[s]) return fail(GIGA_ESTATE, "giga_train_bind: missing encoder parameter '" + train_slot_name(s) + "'");
+  unsigned heads = 0;
+  for (int h = 0; h < 4; ++h) {
+    int have = 0;
+    for (int r = 0; r < TS_HEAD; ++r) have += val[TS_HEAD0 + TS_HEAD * h + r] != nullptr;
+    if (have == TS_HEAD) heads |= 1u << h;
+    else if (have) return fail(GIGA_ESTATE, std::string("giga_train_bind: decoder_") + kHeadName[h] + " is incomplete");
+  }
+  if (!heads) return fail(GIGA_ESTATE, "giga_train_bind: no decoder head");
+  bool same = T.bound && heads == T.heads;
+  for (int s = 0; same && s < giga_ctx::Train::kSlots; ++s) same = val[s] == T.val[s];
+  memcpy(T.val, val, sizeof val);
+  memcpy(T.grad, grad, sizeof grad);
+  T.heads = heads;
+  T.bound = true;
+  if (!same) T.table_dirty = true;
+  return GIGA_OK;
+}
+
+int giga_train_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, int Ng, const float* p_tsdf, int No, int detach_tsdf, float* qual,
+                       float* rot, float* width, float* occ, void* stream) {
+  if (!ctx || !tsdf || B <= 0) return fail(GIGA_EINVAL, "giga_train_forward: bad argument");
+  auto& T = ctx->tr;
+  if (!T.bound) return fail(GIGA_ESTATE, "giga_train_forward: no parameters bound (giga_train_bind)");
+  const bool grasp = p && Ng > 0, geo = p_tsdf && No > 0;
+  if (!grasp && !geo) return fail(GIGA_EINVAL, "giga_train_forward: no query points");
+  const unsigned hm = T.heads & 7u;
+  if (grasp && (hm != 7u || !qual || !rot || !width)) return fail(GIGA_EINVAL, "giga_train_forward: grasp points need the three grasp heads and their outputs");
+  if (geo && (!(T.heads & 8u) || !occ)) return fail(GIGA_EINVAL, "giga_train_forward: p_tsdf needs the TSDF head and its output");
+  if (int r = set_device(ctx)) return r;
+  if (int r = ensure_attrs(ctx)) return r;
+  if (int r = train_attrs(ctx)) return r;
+  if (T.table_dirty)
+    if (int r = train_build_table(ctx)) return r;
+  if (int r = ensure_workspace(ctx, B)) return r;
+  if (int r = train_workspace(ctx, B)) return r;
+  if (int r = ensure_tsdf_maps(ctx, tsdf, B)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);
+  T.fwd_valid = false;
+  // ---- operands from the live parameters (device to device; nothing crosses the host) ----
+  {
+    LaunchScope ls(ctx, "train:pack", st);
+    train_pack_kernel<<<dim3(T.n_tab, 4), 256, 0, st>>>(T.d_tab);
+  }
+  CU_TRY(cudaMemcpyToSymbolAsync(c_conv_in_train, T.d_cin, sizeof(ConvInParams), 0, cudaMemcpyDeviceToDevice, st));
+  // ---- encoder: the inference conv_in body (weights from constant memory) + the fp32 FMA-pipe U-Net, every activation kept ----
+  const int n_img = 3 * B;
+  float* tall_pre = ctx->d_tall[0];
+  const long ps_pre = ctx->tall_ps[0];
+  {
+    LaunchScope ls(ctx, "train:conv_in", st);
+    if (conv_in_ty(B) == 1) {
+      using Cf = ConvInCfg<1, 4>;
+      conv_in_planes_train_kernel<1, 4><<<dim3(Cf::NT, B, 4), Cf::THREADS, Cf::SMEM_BYTES, st>>>(ctx->tsdf_map[1], tall_pre, ps_pre, ctx->d_xzpart, B);
+    } else {
+      using Cf = ConvInCfg<5, 1>;
+      conv_in_planes_train_kernel<5, 1><<<dim3(Cf::NT, B, 1), Cf::THREADS, Cf::SMEM_BYTES, st>>>(ctx->tsdf_map[0], tall_pre, ps_pre, ctx->d_xzpart, B);
+    }
+  }
+  {
+    LaunchScope ls(ctx, "train:xz_finish", st);
+    const int blocks = ceil_div((int)std::max((long)B * 4 * G2, 9 * ctx->flags_stride + 16), 256);
+    if (conv_in_ty(B) == 5)
+      xz_finish_tall_kernel<G / 5><<<blocks, 256, 0, st>>>((const float*)ctx->d_xzpart, tall_pre, ps_pre, B, ctx->d_flags, (int)(9 * ctx->flags_stride + 16));
+    else
+      xz_finish_tall_kernel<G><<<blocks, 256, 0, st>>>((const float*)ctx->d_xzpart, tall_pre, ps_pre, B, ctx->d_flags, (int)(9 * ctx->flags_stride + 16));
+  }
+  {
+    LaunchScope ls(ctx, "train:tall_to_nchw", st);
+    tall_to_nchw_kernel<40, 4><<<ceil_div(n_img * 4 * G2, 256), 256, 0, st>>>(tall_pre, ctx->d_pre, ps_pre, n_img);
+  }
+  float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"), *d1c2 = act(ctx, "d1c2"),
+        *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"), *u0 = act(ctx, "u0"), *u0c1 = act(ctx, "u0c1"),
+        *u0c2 = act(ctx, "u0c2"), *u1 = act(ctx, "u1"), *u1c1 = act(ctx, "u1c1"), *u1c2 = act(ctx, "u1c2");
+  const float* E = T.d_blob;
+  const EncLayout& L = ctx->el;
+  auto conv = [&](auto kcfg, const char* name, const float* s0, const float* s1, int layer, float* out, float* pooled) {
+    using K = decltype(kcfg);
+    dim3 grid(K::NB * K::NCT, n_img);
+    LaunchScope ls(ctx, name, st);
+    conv3x3_kernel<K><<<grid, K::NTHREADS, K::SMEM_BYTES, st>>>(s0, s1, E + L.conv[layer], E + L.bias[layer], out, pooled);
+  };
+  conv(K_d0c1{}, "train:conv:d0c1", ctx->d_pre, nullptr, 0, d0c1, nullptr);
+  conv(K_d0c2{}, "train:conv:d0c2", d0c1, nullptr, 1, d0c2, p0);
+  conv(K_d1c1{}, "train:conv:d1c1", p0, nullptr, 2, d1c1, nullptr);
+  conv(K_d1c2{}, "train:conv:d1c2", d1c1, nullptr, 3, d1c2, p1);
+  conv(K_d2c1{}, "train:conv:d2c1", p1, nullptr, 4, d2c1, nullptr);
+  conv(K_d2c2{}, "train:conv:d2c2", d2c1, nullptr, 5, d2c2, nullptr);
+  {
+    LaunchScope ls(ctx, "train:convT:u0", st);
+    convT2x2_kernel<K_u0up><<<dim3(K_u0up::NB * K_u0up::NCT, n_img), K_u0up::NTHREADS, K_u0up::SMEM_BYTES, st>>>(d2c2, E + L.up_w[0], E + L.up_b[0], u0);
+  }
+  conv(K_u0c1{}, "train:conv:u0c1", u0, d1c2, 6, u0c1, nullptr);
+  conv(K_u0c2{}, "train:conv:u0c2", u0c1, nullptr, 7, u0c2, nullptr);
+  {
+    LaunchScope ls(ctx, "train:convT:u1", st);
+    convT2x2_kernel<K_u1up><<<dim3(K_u1up::NB * K_u1up::NCT, n_img), K_u1up::NTHREADS, K_u1up::SMEM_BYTES, st>>>(u0c2, E + L.up_w[1], E + L.up_b[1], u1);
+  }
+  conv(K_u1c1{}, "train:conv:u1c1", u1, d0c2, 8, u1c1, nullptr);
+  conv(K_u1c2{}, "train:conv:u1c2", u1c1, nullptr, 9, u1c2, nullptr);
+  {
+    LaunchScope ls(ctx, "train:conv_final", st);
+    conv1x1_nhwc_kernel<<<dim3(G2 / F_PIX, n_img), 256, 0, st>>>(u1c2, E + L.fin_w, E + L.fin_b, T.d_planes);
+  }
+  ctx->last_B = B;
+  ctx->last_impl = 0;
+  // ---- heads (fp32 FMA-pipe decoder on the device-packed parameters) ----
+  if (grasp) {
+    LaunchScope ls(ctx, "train:decode:grasp", st);
+    decode_points_kernel<<<dim3(ceil_div(Ng, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(T.d_planes, p, T.d_heads, B, Ng, 7u, qual, rot, width, nullptr);
+  }
+  if (geo) {
+    LaunchScope ls(ctx, "train:decode:tsdf", st);
+    decode_points_kernel<<<dim3(ceil_div(No, DEC_PTS), B), DEC_PTS, DEC_SMEM_BYTES, st>>>(T.d_planes, p_tsdf, T.d_heads, B, No, 8u, nullptr, nullptr, nullptr, occ);
+  }
+  CU_TRY(cudaGetLastError());
+  T.x = tsdf; T.p = grasp ? p : nullptr; T.pt = geo ? p_tsdf : nullptr;
+  T.B = B; T.Ng = grasp ? Ng : 0; T.No = geo ? No : 0; T.detach = detach_tsdf ? 1 : 0;
+  T.fwd_valid = true;
+  return GIGA_OK;
+}
+
+int giga_train_backward(giga_ctx* ctx, const float* g_qual, const float* g_rot, const float* g_width, const float* g_occ, void* stream) {
+  if (!ctx) return fail(GIGA_EINVAL, "giga_train_backward: ctx is null");
+  auto& T = ctx->tr;
+  if (!T.fwd_valid) return fail(GIGA_ESTATE, "giga_train_backward: no forward to differentiate (giga_train_forward must precede; one backward per forward)");
+  if ((g_qual || g_rot || g_width) && !T.p) return fail(GIGA_EINVAL, "giga_train_backward: grasp-head gradients without grasp points in the forward");
+  if (g_occ && !T.pt) return fail(GIGA_EINVAL, "giga_train_backward: TSDF-head gradient without p_tsdf in the forward");
+  if (g_rot && (reinterpret_cast<uintptr_t>(g_rot) & 15)) return fail(GIGA_EINVAL, "giga_train_backward: g_rot must be 16-byte aligned");
+  for (int s = 0; s < giga_ctx::Train::kSlots; ++s)
+    if (T.val[s] && !T.grad[s]) return fail(GIGA_ESTATE, "giga_train_backward: '" + train_slot_name(s) + "' has no gradient buffer bound");
+  if (int r = set_device(ctx)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  OrderScope order(ctx, st);
+  T.fwd_valid = false;
+  const int B = T.B, n_img = 3 * B;
+  const float* gouts[4] = {g_qual, g_rot, g_width, g_occ};
+  bool enc_grad = false;
+  for (int h = 0; h < 4; ++h) enc_grad |= gouts[h] && !(h == 3 && T.detach);
+  if (enc_grad) CU_TRY(cudaMemsetAsync(T.d_gplanes, 0, sizeof(float) * 3 * (size_t)B * C * G2, st));
+  // ---- heads ----
+  for (int h = 0; h < 4; ++h) {
+    if (!gouts[h]) continue;
+    const float* pts = h == 3 ? T.pt : T.p;
+    const int N = h == 3 ? T.No : T.Ng;
+    const int tiles = ceil_div(N, DB_PTS);
+    const size_t need = (size_t)B * tiles * DB_SAVE;
+    if (need > T.save_cap) {
+      CU_TRY(cudaStreamSynchronize(st));
+      if (T.d_save) cudaFree(T.d_save);
+      T.d_save = nullptr;
+      T.save_cap = 0;
+      CU_TRY(cudaMalloc(&T.d_save, sizeof(float) * need));
+      T.save_cap = need;
+    }
+    HeadGrads GR;
+    float* const* g = T.grad + TS_HEAD0 + TS_HEAD * h;
+    GR.fcp_w = g[0]; GR.fcp_b = g[1];
+    for (int i = 0; i < 5; ++i) {
+      GR.fcc_w[i] = g[2 + 6 * i]; GR.fcc_b[i] = g[3 + 6 * i];
+      GR.w0[i] = g[4 + 6 * i]; GR.b0[i] = g[5 + 6 * i];
+      GR.w1[i] = g[6 + 6 * i]; GR.b1[i] = g[7 + 6 * i];
+    }
+    GR.out_w = g[32]; GR.out_b = g[33];
+    LaunchScope ls(ctx, h == 3 ? "train:decode_bwd:tsdf" : "train:decode_bwd:grasp", st);
+    decode_points_bwd_kernel<<<dim3(tiles, B), DB_PTS, DB_SMEM_BYTES, st>>>(T.d_planes, pts, T.d_heads, B, N, h, gouts[h], GR, T.d_save,
+                                                                            (h == 3 && T.detach) ? nullptr : T.d_gplanes);
+  }
+  CU_TRY(cudaGetLastError());
+  if (!enc_grad) return GIGA_OK;
+  // ---- encoder ----
+  float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"), *d1c2 = act(ctx, "d1c2"),
+        *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"), *u0 = act(ctx, "u0"), *u0c1 = act(ctx, "u0c1"),
+        *u0c2 = act(ctx, "u0c2"), *u1 = act(ctx, "u1"), *u1c1 = act(ctx, "u1c1"), *u1c2 = act(ctx, "u1c2");
+  float *g_d0c1 = gact(ctx, "d0c1"), *g_d0c2 = gact(ctx, "d0c2"), *g_p0 = gact(ctx, "p0"), *g_d1c1 = gact(ctx, "d1c1"), *g_d1c2 = gact(ctx, "d1c2"),
+        *g_p1 = gact(ctx, "p1"), *g_d2c1 = gact(ctx, "d2c1"), *g_d2c2 = gact(ctx, "d2c2"), *g_u0 = gact(ctx, "u0"), *g_u0c1 = gact(ctx, "u0c1"),
+        *g_u0c2 = gact(ctx, "u0c2"), *g_u1 = gact(ctx, "u1"), *g_u1c1 = gact(ctx, "u1c1"), *g_u1c2 = gact(ctx, "u1c2");
+  const float* E = T.d_blob;
+  const EncLayout& L = ctx->el;
+  auto gw = [&](int layer) { return T.grad[2 + 2 * layer]; };
+  auto gb = [&](int layer) { return T.grad[3 + 2 * layer]; };
+  {
+    LaunchScope ls(ctx, "train:conv_final_bwd", st);
+    const int n_tiles = n_img * (G2 / FB_PIX);
+    conv_final_bwd_kernel<<<std::min(n_tiles, 4 * ctx->num_sms), 256, 0, st>>>(T.d_gplanes, u1c2, E + L.fin_w, g_u1c2, T.grad[26], T.grad[27], n_tiles);
+  }
+  // u1c2 (layer 9): in = u1c1
+  launch_wgrad<W_40>(ctx, "train:wgrad:u1c2", n_img, g_u1c2, u1c1, 32, 32, gw(9), 32, gb(9), st);
+  launch_dgrad<G_40>(ctx, "train:dgrad:u1c2", n_img, g_u1c2, E + T.dg[9], u1c1, g_u1c1, st);
+  // u1c1 (layer 8): in = cat(u1, d0c2)
+  launch_wgrad<W_40>(ctx, "train:wgrad:u1c1", n_img, g_u1c1, u1, 32, 32, gw(8), 64, gb(8), st);
+  launch_wgrad<W_40>(ctx, "train:wgrad:u1c1", n_img, g_u1c1, d0c2, 32, 32, gw(8) + 32 * 9, 64, nullptr, st);
+  launch_dgrad<G_40>(ctx, "train:dgrad:u1c1", n_img, g_u1c1, E + T.dg[8], nullptr, g_u1, st);
+  launch_dgrad<G_40>(ctx, "train:dgrad:u1c1", n_img, g_u1c1, E + T.dg[8] + 32L * 9 * 32, d0c2, g_d0c2, st);
+  // upconv 1: u1 = convT(u0c2)
+  launch_convT_bwd<TB_u1>(ctx, "train:convT_bwd:u1", n_img, u0c2, g_u1, E + L.up_w[1], g_u0c2, T.grad[24], T.grad[25], st);
+  // u0c2 (layer 7): in = u0c1
+  launch_wgrad<W_20>(ctx, "train:wgrad:u0c2", n_img, g_u0c2, u0c1, 64, 64, gw(7), 64, gb(7), st);
+  launch_dgrad<G_20b>(ctx, "train:dgrad:u0c2", n_img, g_u0c2, E + T.dg[7], u0c1, g_u0c1, st);
+  // u0c1 (layer 6): in = cat(u0, d1c2)
+  launch_wgrad<W_20>(ctx, "train:wgrad:u0c1", n_img, g_u0c1, u0, 64, 64, gw(6), 128, gb(6), st);
+  launch_wgrad<W_20>(ctx, "train:wgrad:u0c1", n_img, g_u0c1, d1c2, 64, 64, gw(6) + 64 * 9, 128, nullptr, st);
+  launch_dgrad<G_20b>(ctx, "train:dgrad:u0c1", n_img, g_u0c1, E + T.dg[6], nullptr, g_u0, st);
+  launch_dgrad<G_20b>(ctx, "train:dgrad:u0c1", n_img, g_u0c1, E + T.dg[6] + 64L * 9 * 64, d1c2, g_d1c2, st);
+  // upconv 0: u0 = convT(d2c2)
+  launch_convT_bwd<TB_u0>(ctx, "train:convT_bwd:u0", n_img, d2c2, g_u0, E + L.up_w[0], g_d2c2, T.grad[22], T.grad[23], st);
+  // d2c2 (layer 5): in = d2c1;  d2c1 (layer 4): in = p1
+  launch_wgrad<W_10>(ctx, "train:wgrad:d2c2", n_img, g_d2c2, d2c1, 128, 128, gw(5), 128, gb(5), st);
+  launch_dgrad<G_10b>(ctx, "train:dgrad:d2c2", n_img, g_d2c2, E + T.dg[5], d2c1, g_d2c1, st);
+  launch_wgrad<W_10>(ctx, "train:wgrad:d2c1", n_img, g_d2c1, p1, 128, 64, gw(4), 64, gb(4), st);
+  launch_dgrad<G_10a>(ctx, "train:dgrad:d2c1", n_img, g_d2c1, E + T.dg[4], nullptr, g_p1, st);
+  {
+    LaunchScope ls(ctx, "train:pool_bwd:p1", st);
+    const long total = (long)n_img * 64 * 100;
+    pool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d1c2, g_p1, g_d1c2, 10, total);
+  }
+  // d1c2 (layer 3): in = d1c1;  d1c1 (layer 2): in = p0
+  launch_wgrad<W_20>(ctx, "train:wgrad:d1c2", n_img, g_d1c2, d1c1, 64, 64, gw(3), 64, gb(3), st);
+  launch_dgrad<G_20b>(ctx, "train:dgrad:d1c2", n_img, g_d1c2, E + T.dg[3], d1c1, g_d1c1, st);
+  launch_wgrad<W_20>(ctx, "train:wgrad:d1c1", n_img, g_d1c1, p0, 64, 32, gw(2), 32, gb(2), st);
+  launch_dgrad<G_20a>(ctx, "train:dgrad:d1c1", n_img, g_d1c1, E + T.dg[2], nullptr, g_p0, st);
+  {
+    LaunchScope ls(ctx, "train:pool_bwd:p0", st);
+    const long total = (long)n_img * 32 * 400;
+    pool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d0c2, g_p0, g_d0c2, 20, total);
+  }
+  // d0c2 (layer 1): in = d0c1;  d0c1 (layer 0): in = the pre-U-Net planes
+  launch_wgrad<W_40>(ctx, "train:wgrad:d0c2", n_img, g_d0c2, d0c1, 32, 32, gw(1), 32, gb(1), st);
+  launch_dgrad<G_40>(ctx, "train:dgrad:d0c2", n_img, g_d0c2, E + T.dg[1], d0c1, g_d0c1, st);
+  launch_wgrad<W_40>(ctx, "train:wgrad:d0c1", n_img, g_d0c1, ctx->d_pre, 32, 32, gw(0), 32, gb(0), st);
+  launch_dgrad<G_40>(ctx, "train:dgrad:d0c1", n_img, g_d0c1, E + T.dg[0], nullptr, T.d_gpre, st);
+  {
+    LaunchScope ls(ctx, "train:conv_in_bwd", st);
+    conv_in_bwd_kernel<<<std::min(B * G, 2 * ctx->num_sms), CB_THREADS, CB_SMEM_BYTES, st>>>(T.x, T.d_cin, T.d_gpre, B, T.grad[0], T.grad[1]);
+  }
+  (void)u0; (void)u1; (void)p0; (void)p1;
+  CU_TRY(cudaGetLastError());
+  return GIGA_OK;
+}
+
+}  // extern "C"

@@ -18,8 +18,12 @@
 
 namespace giga {
 
-template <int HW_, int CIN0_, int CIN1_, int COUT_, int R_, int CT_, int TCO_, int CC_, bool POOL_>
+// EPI 0: forward epilogue (bias + ReLU, optional pooled copy).  EPI 1: the kernel runs as the DATA GRADIENT of a 3x3 conv (train_bwd.cuh):
+// src0 = gradient w.r.t. the conv's pre-activation, wp = flipped / role-swapped weights, `bias` = the activation the gradient flows
+// into (its ReLU mask; null = no mask), no bias, no ReLU.
+template <int HW_, int CIN0_, int CIN1_, int COUT_, int R_, int CT_, int TCO_, int CC_, bool POOL_, int EPI_ = 0>
 struct Conv3x3Cfg {
+  static constexpr int EPI = EPI_;
   static constexpr int HW = HW_, CIN0 = CIN0_, CIN1 = CIN1_, CIN = CIN0_ + CIN1_, COUT = COUT_;
   static constexpr int R = R_, CT = CT_, TCO = TCO_, CC = CC_;
   static constexpr bool POOL = POOL_;
@@ -137,6 +141,20 @@ conv3x3_kernel(const float* __restrict__ src0,  // [n_img][CIN0][HW][HW]
   }
 
   if (!active) return;
+  if constexpr (K::EPI == 1) {
+#pragma unroll
+    for (int k = 0; k < TCO; ++k) {
+      const int co = co_base + (k < 4 ? 4 * tc + k : CT / 2 + 4 * tc + (k - 4));
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const size_t base = (((size_t)img * K::COUT + co) * HW + y0 + 2 * j + r) * HW + 4 * g;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (4 * g + p < HW) out[base + p] = (!bias || __ldg(bias + base + p) > 0.f) ? acc[r][p][k] : 0.f;
+      }
+    }
+    return;
+  }
   // epilogue: bias + ReLU, full-resolution store, optional 2x2 max-pool of the thread's patch
 #pragma unroll
   for (int k = 0; k < TCO; ++k) {

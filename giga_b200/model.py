@@ -249,6 +249,24 @@ class _GigaBase(nn.Module):
         eng.sync_params(self)
         return eng
 
+    def _engine_raw(self) -> _Engine:
+        """the engine WITHOUT committing the parameters to the inference operand blobs (the native training step reads the live
+        parameter tensors on the device; the next inference call re-commits because the optimizer bumps the version counters)"""
+        dev = next(self.parameters()).device
+        eng = self.__dict__.get("_eng")
+        if eng is None or eng.device != dev:
+            eng = _Engine(dev)
+            self.__dict__["_eng"] = eng
+        return eng
+
+    def _train_active(self, *inputs) -> bool:
+        """autograd semantics of an ordinary nn.Module: with gradient mode on and parameters that require gradients the outputs are
+        differentiable -- through the native training step (csrc/train_bwd.cuh).  Query positions that require a gradient
+        (grad_refine) go through the bridge."""
+        if not torch.is_grad_enabled() or any(t is not None and t.requires_grad for t in inputs):
+            return False
+        return any(p.requires_grad for p in self.parameters())
+
     def to(self, device):
         """models/__init__.py:126-134"""
         model = super().to(device)
@@ -531,6 +549,9 @@ class ConvolutionalOccupancyNetwork(_GigaBase):
             eng = self._engine()
             return bridged_forward(self, _prep(inputs, eng.device), _prep(p, eng.device),
                                    _prep(p_tsdf, eng.device) if p_tsdf is not None else None)
+        if self._train_active(p, p_tsdf):
+            from .training import native_forward
+            return native_forward(self, inputs, p, p_tsdf)
         return self._forward_native(inputs, p, p_tsdf)
 
     def decode(self, p, c, **kwargs):
@@ -601,4 +622,7 @@ class ConvolutionalOccupancyNetworkGeometry(_GigaBase):
             eng = self._engine()
             pt = _prep(p_tsdf, eng.device)
             return bridged_forward(self, _prep(inputs, eng.device), pt, pt)[0]
+        if self._train_active(p_tsdf):
+            from .training import native_forward
+            return native_forward(self, inputs, None, p_tsdf)[0]
         return self.infer_geo(inputs, p_tsdf)

@@ -153,6 +153,105 @@ def bridged_forward(net, x, p, p_tsdf):
 
 
 # ------------------------------------------------------------------------------------------------------
+# the native training step (csrc/train_bwd.cuh): differentiable forward + hand-written backward kernels
+# ------------------------------------------------------------------------------------------------------
+class _NativeStep(torch.autograd.Function):
+    """forward: giga_train_forward (fp32 FMA-pipe kernels on the live parameter tensors, activations kept in the engine);
+    backward: giga_train_backward (decoder / grid-sample / conv / transpose-conv / pool / conv_in backward kernels).  Parameter
+    gradients are accumulated by the kernels either straight into `.grad` (parameters owned by `training.Adam`: one flat buffer) or
+    into a fresh flat buffer whose views are handed to autograd."""
+
+    @staticmethod
+    def forward(ctx, net, x, p, p_tsdf, names, *params):
+        from .model import _prep, GRID
+        eng = net._engine_raw()
+        dev = eng.device
+        x = _prep(x, dev)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (GRID, GRID, GRID):
+            raise _lib.GigaError(f"inputs must be (B,{GRID},{GRID},{GRID}), got {tuple(x.shape)}")
+        B = x.shape[0]
+
+        def pts(t, what):
+            if t is None:
+                return None, 0
+            t = _prep(t, dev)
+            if t.dim() != 3 or t.shape[2] != 3 or t.shape[0] != B:
+                raise _lib.GigaError(f"{what} must be (B,N,3) with B={B}, got {tuple(t.shape)}")
+            return t, t.shape[1]
+
+        p, Ng = pts(p, "points")
+        p_tsdf, No = pts(p_tsdf, "p_tsdf")
+        if p_tsdf is not None and not hasattr(net, "decoder_tsdf"):
+            raise AttributeError("this model has no decoder_tsdf")      # as the reference (models/__init__.py:64)
+        if any(q.device != dev or q.dtype != torch.float32 or not q.is_contiguous() for q in params):
+            raise _lib.GigaError("the native training step takes contiguous fp32 parameters on the model's device")
+        direct = all(getattr(q, "_giga_direct", False) and q.grad is not None and q.grad.is_contiguous() and q.grad.data_ptr() % 16 == 0
+                     for q in params if q.requires_grad)
+        flat = None
+        if direct:
+            grads = [q.grad if q.requires_grad else None for q in params]
+        else:
+            sizes = [(q.numel() + 3) // 4 * 4 for q in params]
+            flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+            grads, off = [], 0
+            for q, m in zip(params, sizes):
+                grads.append(flat[off:off + q.numel()].view(q.shape))
+                off += m
+        frozen = None
+        if any(g is None for g in grads):     # parameters with requires_grad = False still need somewhere to write
+            frozen = torch.zeros(max(q.numel() for q in params), device=dev, dtype=torch.float32)
+            grads = [g if g is not None else frozen for g in grads]
+        n = len(params)
+        key = (tuple(q.data_ptr() for q in params), tuple(g.data_ptr() for g in grads))
+        if eng.__dict__.get("_train_key") != key:
+            c_names = (C.c_char_p * n)(*[k.encode() for k in names])
+            vals = (C.c_void_p * n)(*[q.data_ptr() for q in params])
+            gptr = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
+            check(lib.giga_train_bind(eng.h, n, c_names, vals, gptr), "giga_train_bind")
+            eng.__dict__["_train_key"] = key
+        mk = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        qual = rot = width = occ = None
+        if p is not None:
+            qual, rot, width = mk(B, Ng), mk(B, Ng, 4), mk(B, Ng)
+        if p_tsdf is not None:
+            occ = mk(B, No)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(lib.giga_train_forward(eng.h, _ptr(x), B, _ptr(p), Ng, _ptr(p_tsdf), No, int(bool(getattr(net, "detach_tsdf", False))),
+                                     _ptr(qual), _ptr(rot), _ptr(width), _ptr(occ), st), "giga_train_forward")
+        eng.__dict__["_train_token"] = eng.__dict__.get("_train_token", 0) + 1
+        ctx.eng, ctx.token, ctx.direct, ctx.grads, ctx.flat, ctx.frozen = eng, eng.__dict__["_train_token"], direct, grads, flat, frozen
+        ctx.keep = (x, p, p_tsdf)       # the backward kernels re-read the inputs
+        ctx.slots = [o is not None for o in (qual, rot, width, occ)]
+        ctx.params_rg = [q.requires_grad for q in params]
+        return tuple(o for o in (qual, rot, width, occ) if o is not None)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        eng = ctx.eng
+        if eng.__dict__.get("_train_token") != ctx.token:
+            raise _lib.GigaError("backward() of a forward that is no longer the engine's latest training forward "
+                                 "(one giga_b200 model keeps the activations of ONE forward at a time)")
+        dev = eng.device
+        it = iter(gouts)
+        gs = []
+        for present in ctx.slots:
+            g = next(it) if present else None
+            gs.append(g.to(device=dev, dtype=torch.float32).contiguous() if g is not None else None)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(lib.giga_train_backward(eng.h, _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), st), "giga_train_backward")
+        eng.__dict__["_train_token"] += 1      # consumed
+        if ctx.direct:
+            return (None,) * 5 + (None,) * len(ctx.grads)
+        return (None,) * 5 + tuple(g if rg else None for g, rg in zip(ctx.grads, ctx.params_rg))
+
+
+def native_forward(net, x, p, p_tsdf):
+    """differentiable forward through the native training step; returns the tuple forward() returns"""
+    named = list(net.named_parameters())
+    return _NativeStep.apply(net, x, p, p_tsdf, [k for k, _ in named], *[v for _, v in named])
+
+
+# ------------------------------------------------------------------------------------------------------
 # data-parallel gradient exchange (one process per GPU, scenes sharded by the data loader)
 # ------------------------------------------------------------------------------------------------------
 def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, average: bool = True) -> Optional[torch.Tensor]:
@@ -268,6 +367,7 @@ class Adam(torch.optim.Optimizer):
                     view.copy_(p)
                     p.data = view
                     p.grad = buf["grad"][off:off + m].view(p.shape)
+                    p._giga_direct = True      # the native backward accumulates straight into this flat gradient buffer
                     off += (m + 3) // 4 * 4
             self._flat.append((group, buf, n, dev))
         self._steps = 0

@@ -204,6 +204,28 @@ int giga_loss(giga_ctx *ctx, const float *label_pred, const float *rot_pred, con
 int giga_adam_step(giga_ctx *ctx, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long n, int step, double lr,
                    double beta1, double beta2, double eps, double weight_decay, void *stream);
 
+/* Native training step ---------------------------------------------------------------------------
+ * Replaces the autograd graph of `_update` in scripts/train_giga.py:199-211 (net(x, pos, p_tsdf=pos_occ) ... loss.backward()): the
+ * differentiable forward of conv_onet/models/__init__.py:42-67 and its backward (ATen/cuDNN conv3d / conv2d / conv_transpose2d
+ * backward-data and backward-filter, max_pool2d_with_indices_backward, grid_sampler_2d_backward, addmm, threshold_backward) as
+ * hand-written kernels.  Parameters stay ON THE DEVICE in the reference's state-dict layouts: nothing is packed on the host.
+ *
+ * giga_train_bind: n tensors by reference state-dict key (`names`), `values[i]` / `grads[i]` = device pointers (fp32, 16-byte
+ *   aligned) of the parameter and of the buffer its gradient is ACCUMULATED into (+=, as autograd's AccumulateGrad; zero it to get
+ *   the plain gradient).  All encoder tensors are required; heads are optional but must be complete.  Cheap to call every step
+ *   (the device-side packing table is rebuilt only when a pointer changes).
+ * giga_train_forward: same arguments / outputs as giga_forward (qual = sigmoid, rot = normalised, width, occupancy logits) computed
+ *   from the bound parameters' CURRENT values on the fp32 FMA-pipe kernels; every activation is kept in the ctx.  detach_tsdf != 0 =
+ *   the `giga_detach` variant (models/__init__.py:61-62: the TSDF head's features carry no gradient to the encoder).
+ * giga_train_backward: g_* = gradients of the loss w.r.t. the four outputs of the LAST giga_train_forward ([B][Ng], [B][Ng][4],
+ *   [B][Ng], [B][No]; NULL = that output does not contribute); adds the parameter gradients into the bound buffers.  tsdf / p /
+ *   p_tsdf of the forward must still be alive.  One backward per forward.  Weight-gradient sums use floating-point atomics (run-to-run
+ *   differences at the 1e-6 relative level, as PyTorch's default cuDNN algorithms). */
+int giga_train_bind(giga_ctx *ctx, int n, const char *const *names, const float *const *values, float *const *grads);
+int giga_train_forward(giga_ctx *ctx, const float *tsdf, int B, const float *p, int Ng, const float *p_tsdf, int No, int detach_tsdf,
+                       float *qual, float *rot, float *width, float *occ, void *stream);
+int giga_train_backward(giga_ctx *ctx, const float *g_qual, const float *g_rot, const float *g_width, const float *g_occ, void *stream);
+
 /* Generator3D occupancy sweep ----------------------------------------------
  * Replaces the MISE loop of `Generator3D.generate_from_latent` (ConvONets/conv_onet/generation.py:127-143) together with the Cython
  * octree it drives (ConvONets/utils/libmise/mise.pyx): query -> eval_points/decode_occ -> update/subdivide until no grid point is

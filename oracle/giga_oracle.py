@@ -195,12 +195,14 @@ def decode(sd: Mapping[str, Tensor], p: Tensor, planes: Mapping[str, Tensor]):
     return qual, rot, width
 
 
-def forward(sd: Mapping[str, Tensor], x: Tensor, p: Tensor, p_tsdf: Optional[Tensor] = None):
-    """ConvolutionalOccupancyNetwork.forward, models/__init__.py:42-67."""
+def forward(sd: Mapping[str, Tensor], x: Tensor, p: Tensor, p_tsdf: Optional[Tensor] = None, detach_tsdf: bool = False):
+    """ConvolutionalOccupancyNetwork.forward, models/__init__.py:42-67 (detach_tsdf: :61-63, the `giga_detach` variant)."""
     planes = encode_inputs(sd, x)
     qual, rot, width = decode(sd, p, planes)
     if p_tsdf is None:
         return qual, rot, width
+    if detach_tsdf:
+        planes = {k: v.detach() for k, v in planes.items()}
     tsdf = local_decoder(sd, "tsdf", p_tsdf, planes)
     return qual, rot, width, tsdf
 

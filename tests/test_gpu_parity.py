@@ -342,9 +342,12 @@ def test_training_bridge_matches_reference_gradients(oracle_sd):
         l = l + (label.to(dev) * (1.0 - (rot.squeeze(1) * tgt).sum(-1).abs())).mean() + 0.01 * F.mse_loss(40 * width.squeeze(-1), torch.ones(4, device=dev))
         return l + F.binary_cross_entropy(torch.sigmoid(occ), occ_t.to(dev))
 
-    # without the opt-in nothing is differentiable (and nothing falls back silently)
+    # frozen parameters: nothing is differentiable; trainable ones take the native training step (tests/test_gpu_train_native.py); the
+    # bridge (PyTorch recompute) is what grad_refine uses for position gradients and stays available behind its opt-in
+    net.requires_grad_(False)
     out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
     assert not any(o.requires_grad for o in out)
+    net.requires_grad_(True)
     net.enable_training_bridge()
     out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
     ref_leaves = {k: v.clone().requires_grad_(True) for k, v in oracle_sd.items()}
