@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="scenes per GPU")
     ap.add_argument("--points", type=int, default=2048, help="grasp and occupancy query points per scene")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[3] training-step leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     B, N = args.batch, args.points
@@ -352,10 +353,59 @@ def main():
                 planner["cpu_postprocess_note"] = "numpy restatement of scipy.ndimage process/bound/select on the host, post-processing only (no network)"
             net.load_state_dict(O.seeded_state_dict(seed=1))
 
-    t = torch.tensor([ms_total, e2e_s, c3 or 0.0], device=dev, dtype=torch.float64)
+    # ---- configs[3] leg: a scripts/train_giga.py step (forward + loss + backward + Adam) on this library's kernels only: global batch 64
+    #      sharded over the ranks (strong scaling, as the config states), one grasp point + 2048 occupancy points per sample, one flat
+    #      NCCL all-reduce of the 581,863-element gradient buffer per step ----
+    train_ms = 0.0
+    train_info = None
+    if not args.no_train and 64 % world == 0:
+        import torch.nn.functional as F
+        from giga_b200 import training
+        TB, TNo = 64 // world, 2048
+        tnet = giga_b200.get_network("giga")
+        tnet.load_state_dict(O.seeded_state_dict(seed=1))
+        tnet = tnet.to(dev)
+        opt = training.Adam(tnet.parameters(), lr=2e-4)
+        tx = xs[0][:TB] if TB <= B else torch.rand((TB, 40, 40, 40), device=dev, generator=g)
+        tpos = torch.rand((TB, 1, 3), device=dev, generator=g) - 0.5
+        tocc = torch.rand((TB, TNo, 3), device=dev, generator=g) - 0.5
+        ty = ((torch.rand(TB, device=dev, generator=g) > 0.5).float(), F.normalize(torch.randn(TB, 2, 4, device=dev, generator=g), dim=2),
+              torch.rand(TB, device=dev, generator=g) * 0.1, (torch.rand(TB, TNo, device=dev, generator=g) > 0.5).float())
+        teng = tnet._engine_raw()
+
+        def train_step():
+            opt.zero_grad()
+            loss, _ = training.loss_fn(training.select(tnet(tx, tpos, p_tsdf=tocc)), ty)
+            loss.backward()
+            opt.allreduce_gradients()
+            opt.step()
+            return loss
+
+        for _ in range(3):
+            train_step()
+        fence()
+        tl0 = teng.launches
+        ta, tb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ta.record()
+        for _ in range(args.steps):
+            tloss = train_step()
+        tb_.record()
+        fence()
+        train_ms = ta.elapsed_time(tb_)
+        train_info = {"launches_per_step": (teng.launches - tl0) // args.steps, "loss": float(tloss.detach())}
+        if world == 1:
+            teng.set_timing(True)
+            train_step()
+            torch.cuda.synchronize()
+            rep = teng.timing_report()
+            teng.set_timing(False)
+            train_info["kernels_us"] = {k: round(1e3 * v[1], 1) for k, v in rep.items()}
+        del tnet, opt
+
+    t = torch.tensor([ms_total, e2e_s, c3 or 0.0, train_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s, c3 = t[0].item(), t[1].item(), t[2].item()
+    ms_total, e2e_s, c3, train_ms = t[0].item(), t[1].item(), t[2].item(), t[3].item()
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
     e2e_value = world * B * args.steps / e2e_s
@@ -421,6 +471,13 @@ def main():
             out["configs2"] = {"workload": f"configs[2]: {B} scenes/GPU x {world} GPUs, 4096 grasp pts x qual/rot/width + 4096 occupancy pts x tsdf head",
                                "value": world * B * args.steps / (c3 * 1e-3), "unit": UNIT, "ms_per_step": c3 / args.steps,
                                "query_points_per_sec": world * B * args.steps / (c3 * 1e-3) * 2 * 4096}
+        if train_info is not None and train_ms > 0:
+            # fwd+bwd ~ 3x the forward's FLOPs: 3.72 GFLOP per sample
+            tps = 64 * args.steps / (train_ms * 1e-3)
+            out["train"] = {"workload": f"configs[3]: train_giga.py step, global batch 64 ({64 // world}/GPU x {world}), 1 grasp pt + 2048 occupancy pts per sample, "
+                                        "native forward + fused loss + native backward + flat all-reduce + flat Adam, fp32 (FMA pipe)",
+                            "value": tps, "unit": "samples/s", "ms_per_step": train_ms / args.steps, "scaling": "strong",
+                            "tflops_fp32": round(3.72e9 * tps / 1e12, 2), **train_info}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

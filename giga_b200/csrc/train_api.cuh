@@ -24,19 +24,6 @@ std::string train_slot_name(int s) {
   return pre + "blocks." + std::to_string(i) + ".fc_" + std::to_string(f - 1) + wb;
 }
 
-long train_slot_numel(int s) {
-  if (s == 0) return 32 * 27;
-  if (s == 1) return 32;
-  if (s < 22) { const int i = (s - 2) / 2; return (s & 1) ? kConvCout[i] : (long)kConvCout[i] * kConvCin[i] * 9; }
-  if (s < 26) { const int i = (s - 22) / 2; return (s & 1) ? kUpCout[i] : (long)kUpCin[i] * kUpCout[i] * 4; }
-  if (s < 28) return (s & 1) ? 32 : 1024;
-  const int h = (s - TS_HEAD0) / TS_HEAD, r = (s - TS_HEAD0) % TS_HEAD, od = h == 1 ? 4 : 1;
-  if (r < 2) return (r & 1) ? 32 : 96;
-  if (r >= 32) return (r & 1) ? od : od * 32;
-  const int f = ((r - 2) % 6) / 2;
-  return (r & 1) ? 32 : (f == 0 ? 32 * 96 : 32 * 32);
-}
-
 // data-gradient instances of the forward conv kernel (HW, C of the incoming gradient, 0, C of the outgoing gradient, ...)
 using G_40 = Conv3x3Cfg<40, 32, 0, 32, 4, 32, 4, 16, false, 1>;
 using G_20a = Conv3x3Cfg<20, 64, 0, 32, 4, 32, 4, 16, false, 1>;
@@ -357,13 +344,29 @@ int giga_train_backward(giga_ctx* ctx, const float* g_qual, const float* g_rot, 
   bool enc_grad = false;
   for (int h = 0; h < 4; ++h) enc_grad |= gouts[h] && !(h == 3 && T.detach);
   if (enc_grad) CU_TRY(cudaMemsetAsync(T.d_gplanes, 0, sizeof(float) * 3 * (size_t)B * C * G2, st));
-  // ---- heads ----
-  for (int h = 0; h < 4; ++h) {
-    if (!gouts[h]) continue;
-    const float* pts = h == 3 ? T.pt : T.p;
-    const int N = h == 3 ? T.No : T.Ng;
+  // ---- heads: one launch per point set (the grasp heads with a gradient share a launch, blockIdx.z = head) ----
+  for (int set = 0; set < 2; ++set) {
+    DecBwdArgs A = {};
+    int nj = 0;
+    for (int h = set == 0 ? 0 : 3; h < (set == 0 ? 3 : 4); ++h) {
+      if (!gouts[h]) continue;
+      DecBwdJob& J = A.job[nj++];
+      J.head = h;
+      J.gout = gouts[h];
+      float* const* g = T.grad + TS_HEAD0 + TS_HEAD * h;
+      J.GR.fcp_w = g[0]; J.GR.fcp_b = g[1];
+      for (int i = 0; i < 5; ++i) {
+        J.GR.fcc_w[i] = g[2 + 6 * i]; J.GR.fcc_b[i] = g[3 + 6 * i];
+        J.GR.w0[i] = g[4 + 6 * i]; J.GR.b0[i] = g[5 + 6 * i];
+        J.GR.w1[i] = g[6 + 6 * i]; J.GR.b1[i] = g[7 + 6 * i];
+      }
+      J.GR.out_w = g[32]; J.GR.out_b = g[33];
+    }
+    if (!nj) continue;
+    const float* pts = set ? T.pt : T.p;
+    const int N = set ? T.No : T.Ng;
     const int tiles = ceil_div(N, DB_PTS);
-    const size_t need = (size_t)B * tiles * DB_SAVE;
+    const size_t need = (size_t)nj * B * tiles * DB_SAVE;
     if (need > T.save_cap) {
       CU_TRY(cudaStreamSynchronize(st));
       if (T.d_save) cudaFree(T.d_save);
@@ -372,18 +375,9 @@ int giga_train_backward(giga_ctx* ctx, const float* g_qual, const float* g_rot, 
       CU_TRY(cudaMalloc(&T.d_save, sizeof(float) * need));
       T.save_cap = need;
     }
-    HeadGrads GR;
-    float* const* g = T.grad + TS_HEAD0 + TS_HEAD * h;
-    GR.fcp_w = g[0]; GR.fcp_b = g[1];
-    for (int i = 0; i < 5; ++i) {
-      GR.fcc_w[i] = g[2 + 6 * i]; GR.fcc_b[i] = g[3 + 6 * i];
-      GR.w0[i] = g[4 + 6 * i]; GR.b0[i] = g[5 + 6 * i];
-      GR.w1[i] = g[6 + 6 * i]; GR.b1[i] = g[7 + 6 * i];
-    }
-    GR.out_w = g[32]; GR.out_b = g[33];
-    LaunchScope ls(ctx, h == 3 ? "train:decode_bwd:tsdf" : "train:decode_bwd:grasp", st);
-    decode_points_bwd_kernel<<<dim3(tiles, B), DB_PTS, DB_SMEM_BYTES, st>>>(T.d_planes, pts, T.d_heads, B, N, h, gouts[h], GR, T.d_save,
-                                                                            (h == 3 && T.detach) ? nullptr : T.d_gplanes);
+    LaunchScope ls(ctx, set ? "train:decode_bwd:tsdf" : "train:decode_bwd:grasp", st);
+    decode_points_bwd_kernel<<<dim3(tiles, B, nj), DB_PTS, DB_SMEM_BYTES, st>>>(T.d_planes, pts, T.d_heads, B, N, A, T.d_save,
+                                                                               (set && T.detach) ? nullptr : T.d_gplanes);
   }
   CU_TRY(cudaGetLastError());
   if (!enc_grad) return GIGA_OK;

@@ -154,14 +154,23 @@ __device__ __forceinline__ void matvec32(const float* Wt, const float* x, float*
   }
 }
 
+struct DecBwdJob {
+  int head;
+  const float* gout;   // gradient of the loss w.r.t. this head's output: [B][N] or [B][N][4] (rot)
+  HeadGrads GR;
+};
+struct DecBwdArgs { DecBwdJob job[3]; };   // the heads evaluated at one point set: blockIdx.z picks the job
+
 __global__ void __launch_bounds__(DB_PTS, 2)
 decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][32]
                          const float* __restrict__ pts,      // [B][N][3]
                          const float* __restrict__ hw,       // [4][DW_HEAD] packed head parameters (input-major)
-                         int B, int N, int head,
-                         const float* __restrict__ gout,     // gradient of the loss w.r.t. this head's output: [B][N] or [B][N][4] (rot)
-                         HeadGrads GR, float* __restrict__ save,   // [B * tiles][DB_SAVE]
+                         int B, int N, const __grid_constant__ DecBwdArgs A,
+                         float* __restrict__ save,           // [jobs][B * tiles][DB_SAVE]
                          float* __restrict__ gplanes) {      // [3][B][40][40][32] (+=), or null (detached features)
+  const int head = A.job[blockIdx.z].head;
+  const float* __restrict__ gout = A.job[blockIdx.z].gout;
+  const HeadGrads& GR = A.job[blockIdx.z].GR;
   extern __shared__ __align__(16) float smem[];
   float* feat = smem;                     // [96][DB_ST]
   float* wbuf = feat + 96 * DB_ST;        // [DW_BLK]
@@ -178,7 +187,7 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
   const float* pp = pts + ((size_t)b * N + nc) * 3;
   const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
   const float* W = hw + (size_t)head * DW_HEAD;
-  float* sv = save + ((size_t)b * gridDim.x + blockIdx.x) * DB_SAVE + tid;   // [6][32][128], this thread's column
+  float* sv = save + (((size_t)blockIdx.z * B + b) * gridDim.x + blockIdx.x) * DB_SAVE + tid;   // [6][32][128], this thread's column
 
   // ---- forward recompute (decode_points_kernel's arithmetic), keeping the hidden state that enters each ResNet block ----
   float h[32];

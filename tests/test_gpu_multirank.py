@@ -68,3 +68,63 @@ def test_sharded_argmax_allgather_equals_unsharded_nccl(n_scenes):
     out = mp.Manager().dict()
     mp.spawn(_worker, args=(2, port, n_scenes, out), nprocs=2, join=True)
     assert [out[r] for r in range(2)] == [1, 1]
+
+
+def _train_worker(rank, world, port, out):
+    """data-parallel training step: each rank differentiates its shard of the batch with the native backward, the flat gradient buffer is
+    all-reduced (sum / world) over NCCL in place, Adam steps -- gradients and updated parameters must equal the single-GPU step on the
+    whole batch (DDP grads == single-GPU grads of the global batch)."""
+    import torch.distributed as dist
+
+    from giga_b200 import training
+    from oracle import giga_oracle as O
+    from tests.test_gpu_train_native import _batch
+    from tests.util import make_net
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        Bg = 8
+        x, p, pt, y = _batch(Bg, 200, seed=31)
+        to = lambda t: t.to(dev)
+
+        def grads_and_params(sl, allreduce):
+            net = make_net("giga", device=dev, frozen=False)
+            opt = training.Adam(net.parameters(), lr=1e-3)
+            opt.zero_grad()
+            out_ = net(to(x[sl]), to(p[sl]), p_tsdf=to(pt[sl]))
+            loss, _ = training.loss_fn(training.select(out_), tuple(to(t[sl]) for t in y))
+            loss.backward()
+            if allreduce:
+                opt.allreduce_gradients()
+            g = torch.cat([q.grad.reshape(-1) for q in net.parameters()]).clone()
+            opt.step()
+            return g, torch.cat([q.detach().reshape(-1) for q in net.parameters()]).clone()
+
+        per = Bg // world
+        g_ddp, p_ddp = grads_and_params(slice(rank * per, (rank + 1) * per), True)
+        g_one, p_one = grads_and_params(slice(0, Bg), False)
+        scale = float(g_one.abs().max())
+        ok = float((g_ddp - g_one).abs().max()) <= 2e-4 * scale
+        # every rank holds the same reduced gradients and parameters
+        gathered = [torch.empty_like(p_ddp) for _ in range(world)]
+        dist.all_gather(gathered, p_ddp)
+        ok = ok and all(torch.equal(gathered[0], t) for t in gathered)
+        ok = ok and float((p_ddp - p_one).abs().max()) <= 2.1e-3       # one Adam step moves a weight by at most lr (sign flips at the noise level: 2 lr)
+        ok = ok and float(((p_ddp - p_one).abs() > 1e-4).float().mean()) < 1e-3
+        out[rank] = int(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_training_step_equals_single_gpu_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    port = _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_train_worker, args=(2, port, out), nprocs=2, join=True)
+    assert [out[r] for r in range(2)] == [1, 1]

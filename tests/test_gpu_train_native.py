@@ -102,7 +102,8 @@ def test_gradients_accumulate_and_upstream_scale(oracle_sd):
     g1 = {k: v.grad.clone() for k, v in net.named_parameters()}
     (2.0 * _loss(net(xd, pd, p_tsdf=ptd), y, DEV)).backward()
     for k, v in net.named_parameters():
-        torch.testing.assert_close(v.grad, 3.0 * g1[k], rtol=2e-4, atol=1e-7 * float(g1[k].abs().max()) + 1e-12)
+        # the sums run through floating-point atomics: two evaluations differ at the 1e-6 level of the tensor's largest entry
+        assert float((v.grad - 3.0 * g1[k]).abs().max()) <= 2e-5 * 3.0 * float(g1[k].abs().max()) + 1e-12, k
 
 
 @pytest.mark.parametrize("name", ["giga_aff", "giga_geo", "giga_detach"])
