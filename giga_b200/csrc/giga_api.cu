@@ -21,6 +21,7 @@
 #include "vgn.cuh"
 #include "train.cuh"
 #include "train_bwd.cuh"
+#include "tsdf.cuh"
 #include "planner.cuh"
 #include "unet.cuh"
 #include "unet_tall.cuh"
@@ -1967,3 +1968,4 @@ long giga_debug_copy(giga_ctx* ctx, const char* name, float* dst, long capacity,
 }  // extern "C"
 
 #include "train_api.cuh"
+#include "tsdf_api.cuh"

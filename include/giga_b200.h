@@ -226,6 +226,20 @@ int giga_train_forward(giga_ctx *ctx, const float *tsdf, int B, const float *p, 
                        float *qual, float *rot, float *width, float *occ, void *stream);
 int giga_train_backward(giga_ctx *ctx, const float *g_qual, const float *g_rot, const float *g_width, const float *g_occ, void *stream);
 
+/* TSDF integration / read-out -------------------------------------------------
+ * Replaces `TSDFVolume.integrate` / `get_grid` of vgn/perception.py:79-115, i.e. open3d.pipelines.integration.UniformTSDFVolume
+ * (open3d==0.12.0, third party) `integrate` on an RGBD image created with depth_scale / depth_trunc, and extract_voxel_grid + the
+ * Python voxel loop.  tsdf / weight: device fp32 [R][R][R] (x, y, z), zero-initialised by the caller for a new volume and updated in
+ * place; depth: device fp32 [n_views][height][width] (metres * depth_scale); extrinsics: HOST double [n_views][16], row-major 4x4
+ * T_eye_task as `Transform.as_matrix()` gives it; size = edge length of the volume (origin 0), sdf_trunc as perception.py:72 (4 voxels).
+ * Views are folded into the running average in submission order (one launch per 16 views).  giga_tsdf_grid writes the network's input
+ * grid ([R][R][R]: (tsdf + 1) / 2 where the voxel was observed and -0.98 <= tsdf < 0.98, else 0) -- it stays on the device, so
+ * perception -> giga_forward needs no host round trip. */
+int giga_tsdf_integrate(giga_ctx *ctx, float *tsdf, float *weight, int resolution, double size, double sdf_trunc, const float *depth,
+                        int n_views, int width, int height, double fx, double fy, double cx, double cy, const double *extrinsics,
+                        double depth_scale, double depth_trunc, void *stream);
+int giga_tsdf_grid(giga_ctx *ctx, const float *tsdf, const float *weight, int resolution, float *grid, void *stream);
+
 /* Generator3D occupancy sweep ----------------------------------------------
  * Replaces the MISE loop of `Generator3D.generate_from_latent` (ConvONets/conv_onet/generation.py:127-143) together with the Cython
  * octree it drives (ConvONets/utils/libmise/mise.pyx): query -> eval_points/decode_occ -> update/subdivide until no grid point is
