@@ -92,9 +92,13 @@ struct HeadGrads {   // parameter gradients in the reference's layouts (Linear w
 };
 
 constexpr int DB_PTS = 128;
-constexpr int DB_ST = 132;   // staging row stride: points contiguous, rows 16-byte aligned
+constexpr int DB_ST = 140;   // staging row stride: points contiguous, rows 16-byte aligned, room for the skew below
+// Row r of a staging tile starts at r * DB_ST + 4 * ((r >> 3) & 3): in the tile-wide outer products a warp reads rows 8 kg + i (kg = 0..3)
+// of the input tile at once, and without the skew those four rows share their banks (8 * stride = 0 mod 32): a 4-way conflict on every load
+// (ncu: 57 % of the shared-memory wavefronts were conflicts).
+__device__ __forceinline__ int db_row(int r) { return r * DB_ST + 4 * ((r >> 3) & 3); }
 constexpr int DB_SMEM_FLOATS = 96 * DB_ST + DW_BLK + 64 * DB_ST;
-constexpr int DB_SMEM_BYTES = DB_SMEM_FLOATS * 4;   // 105,344 B -> two CTAs per SM
+constexpr int DB_SMEM_BYTES = DB_SMEM_FLOATS * 4;   // 110,464 B -> two CTAs per SM
 constexpr int DB_SAVE = 6 * 32 * DB_PTS;            // floats of scratch per tile: the hidden state before each block + the final one
 
 // dW[j][k0 + 8 kg + i] += sum_pt sG[j][pt] * sA[8 kg + i][pt]   (thread = (j, kg)); bias: db[j] += sum_pt sG[j][pt]
@@ -104,8 +108,8 @@ __device__ __forceinline__ void wgrad_tile32(const float* sA, const float* sG, f
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   float bs = 0.f;
-  const float* gr = sG + j * DB_ST;
-  const float* ar = sA + (8 * kg) * DB_ST;
+  const float* gr = sG + db_row(j);
+  const float* ar = sA + db_row(8 * kg);      // rows 8 kg .. 8 kg + 7 share one skew
 #pragma unroll 2
   for (int p = 0; p < DB_PTS; p += 4) {
     const float4 g = ld4(gr + p);
@@ -154,6 +158,43 @@ __device__ __forceinline__ void matvec32(const float* Wt, const float* x, float*
   }
 }
 
+// warp_gather (decoder.cuh) writing the skewed row layout: feat[db_row(plane * 32 + channel) + point]
+__device__ __forceinline__ void warp_gather_skew(const float* __restrict__ planes, int B, int b, const float* __restrict__ pts, int n0, int N,
+                                                 float* feat, int pt0, float* tinfo_w) {
+  const int lane = threadIdx.x & 31;
+  {
+    const int n = min(n0 + lane, N - 1);
+    TexInfo t;
+    point_taps(pts + ((size_t)b * N + n) * 3, t);
+    int* ti = reinterpret_cast<int*>(tinfo_w) + lane * 24;
+    float* tf = tinfo_w + lane * 24 + 12;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ti[pl * 4 + q] = t.off[pl][q];
+        tf[pl * 4 + q] = t.w[pl][q];
+      }
+  }
+  __syncwarp();
+  const float* pb[3];
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) pb[pl] = planes + ((size_t)pl * B + b) * (G2 * C) + lane;
+#pragma unroll 2
+  for (int q = 0; q < 32; ++q) {
+    const int4* oi = reinterpret_cast<const int4*>(tinfo_w + q * 24);
+    const float4* wf = reinterpret_cast<const float4*>(tinfo_w + q * 24 + 12);
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const int4 o = oi[pl];
+      const float4 w = wf[pl];
+      const float v0 = __ldg(pb[pl] + o.x), v1 = __ldg(pb[pl] + o.y), v2 = __ldg(pb[pl] + o.z), v3 = __ldg(pb[pl] + o.w);
+      feat[db_row(pl * 32 + lane) + pt0 + q] = v0 * w.x + v1 * w.y + v2 * w.z + v3 * w.w;   // ATen order (as warp_gather)
+    }
+  }
+  __syncwarp();
+}
+
 struct DecBwdJob {
   int head;
   const float* gout;   // gradient of the loss w.r.t. this head's output: [B][N] or [B][N][4] (rot)
@@ -183,7 +224,7 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
   const int nc = valid ? n : N - 1;
   const int od = head == 1 ? 4 : 1;
 
-  warp_gather(planes, B, b, pts, n0 + warp * 32, N, feat, DB_ST, warp * 32, tinfo + warp * 32 * 24);
+  warp_gather_skew(planes, B, b, pts, n0 + warp * 32, N, feat, warp * 32, tinfo + warp * 32 * 24);
   const float* pp = pts + ((size_t)b * N + nc) * 3;
   const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
   const float* W = hw + (size_t)head * DW_HEAD;
@@ -204,7 +245,7 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
     for (int j = 0; j < 32; ++j) h[j] += wbuf[DW_BLK_BC + j];
 #pragma unroll 4
     for (int k = 0; k < 96; ++k) {
-      const float f = feat[k * DB_ST + tid];
+      const float f = feat[db_row(k) + tid];
       const float4* wr = reinterpret_cast<const float4*>(wbuf + DW_BLK_FCC + k * 32);
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
@@ -261,15 +302,15 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
   float g[32];
   __syncthreads();   // every thread is done with the block-4 weights and (long ago) with the gather scratch
 #pragma unroll
-  for (int k = 0; k < 32; ++k) sA[k * DB_ST + tid] = fmaxf(h[k], 0.f);
+  for (int k = 0; k < 32; ++k) sA[db_row(k) + tid] = fmaxf(h[k], 0.f);
 #pragma unroll
-  for (int m = 0; m < 4; ++m) sG[m * DB_ST + tid] = go[m];
+  for (int m = 0; m < 4; ++m) sG[db_row(m) + tid] = go[m];
   __syncthreads();
   {
     const int m = tid >> 5, k = tid & 31;
     float acc = 0.f, bs = 0.f;
     for (int p = 0; p < DB_PTS; p += 4) {
-      const float4 gv = ld4(sG + m * DB_ST + p), av = ld4(sA + k * DB_ST + p);
+      const float4 gv = ld4(sG + db_row(m) + p), av = ld4(sA + db_row(k) + p);
       acc = fmaf(gv.x, av.x, acc); acc = fmaf(gv.y, av.y, acc); acc = fmaf(gv.z, av.z, acc); acc = fmaf(gv.w, av.w, acc);
       bs += (gv.x + gv.y) + (gv.z + gv.w);
     }
@@ -303,7 +344,7 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
     }
     // fc_1: out += W1 relu(t) + b1
 #pragma unroll
-    for (int k = 0; k < 32; ++k) { sA[k * DB_ST + tid] = fmaxf(t[k], 0.f); sG[k * DB_ST + tid] = g[k]; }
+    for (int k = 0; k < 32; ++k) { sA[db_row(k) + tid] = fmaxf(t[k], 0.f); sG[db_row(k) + tid] = g[k]; }
     __syncthreads();
     wgrad_tile32(sA, sG, GR.w1[blk], 32, GR.b1[blk], tid);
     float gt[32];
@@ -313,7 +354,7 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
     __syncthreads();
     // fc_0: t = W0 relu(hb) + b0
 #pragma unroll
-    for (int k = 0; k < 32; ++k) { sA[k * DB_ST + tid] = fmaxf(hb[k], 0.f); sG[k * DB_ST + tid] = gt[k]; }
+    for (int k = 0; k < 32; ++k) { sA[db_row(k) + tid] = fmaxf(hb[k], 0.f); sG[db_row(k) + tid] = gt[k]; }
     __syncthreads();
     wgrad_tile32(sA, sG, GR.w0[blk], 32, GR.b0[blk], tid);
     {
@@ -325,7 +366,7 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
     __syncthreads();
     // fc_c[blk]: hb = (state leaving block blk - 1) + Wc feat + bc   ->  the same g flows on to block blk - 1
 #pragma unroll
-    for (int k = 0; k < 32; ++k) sG[k * DB_ST + tid] = g[k];
+    for (int k = 0; k < 32; ++k) sG[db_row(k) + tid] = g[k];
     __syncthreads();
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl)
@@ -336,17 +377,17 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
 
   // ---- fc_p: h0 = Wp p + bp ----
   __syncthreads();
-  sA[0 * DB_ST + tid] = px; sA[1 * DB_ST + tid] = py; sA[2 * DB_ST + tid] = pz;
+  sA[db_row(0) + tid] = px; sA[db_row(1) + tid] = py; sA[db_row(2) + tid] = pz;
 #pragma unroll
-  for (int k = 0; k < 32; ++k) sG[k * DB_ST + tid] = g[k];
+  for (int k = 0; k < 32; ++k) sG[db_row(k) + tid] = g[k];
   __syncthreads();
   {
     const int j = tid >> 2, c = tid & 3;
     float acc = 0.f;
     for (int p = 0; p < DB_PTS; p += 4) {
-      const float4 gv = ld4(sG + j * DB_ST + p);
+      const float4 gv = ld4(sG + db_row(j) + p);
       if (c < 3) {
-        const float4 av = ld4(sA + c * DB_ST + p);
+        const float4 av = ld4(sA + db_row(c) + p);
         acc = fmaf(gv.x, av.x, acc); acc = fmaf(gv.y, av.y, acc); acc = fmaf(gv.z, av.z, acc); acc = fmaf(gv.w, av.w, acc);
       } else {
         acc += (gv.x + gv.y) + (gv.z + gv.w);
@@ -409,7 +450,7 @@ conv_final_bwd_kernel(const float* __restrict__ gpl,    // [n_img][1600][32]  pl
                       float* __restrict__ dW,           // [co][ci]
                       float* __restrict__ db, int n_tiles) {
   __shared__ __align__(16) float Gs[FB_PIX * 33];   // [p][co]
-  __shared__ __align__(16) float As[C * (FB_PIX + 4)];   // [ci][p]
+  __shared__ __align__(16) float As[C * (FB_PIX + 1)];   // [ci][p]
   __shared__ __align__(16) float Ws[C * 33];        // [ci][co] (padded)
   const int tid = threadIdx.x;
   for (int e = tid; e < C * C; e += 256) Ws[(e / C) * 33 + (e % C)] = __ldg(wt + e);
@@ -420,7 +461,7 @@ conv_final_bwd_kernel(const float* __restrict__ gpl,    // [n_img][1600][32]  pl
     const int img = tile / TPI, pix0 = (tile % TPI) * FB_PIX;
     __syncthreads();
     for (int e = tid; e < FB_PIX * C; e += 256) Gs[(e / C) * 33 + (e % C)] = __ldg(gpl + ((size_t)img * G2 + pix0) * C + e);
-    for (int e = tid; e < C * FB_PIX; e += 256) As[(e / FB_PIX) * (FB_PIX + 4) + (e % FB_PIX)] = __ldg(act + ((size_t)img * C + e / FB_PIX) * G2 + pix0 + e % FB_PIX);
+    for (int e = tid; e < C * FB_PIX; e += 256) As[(e / FB_PIX) * (FB_PIX + 1) + (e % FB_PIX)] = __ldg(act + ((size_t)img * C + e / FB_PIX) * G2 + pix0 + e % FB_PIX);
     __syncthreads();
     {   // data gradient: thread = (pixel p, 8 ci)
       const int p = tid & 63, cg = tid >> 6;
@@ -436,7 +477,7 @@ conv_final_bwd_kernel(const float* __restrict__ gpl,    // [n_img][1600][32]  pl
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int ci = cg * 8 + k;
-        gin[((size_t)img * C + ci) * G2 + pix0 + p] = As[ci * (FB_PIX + 4) + p] > 0.f ? acc[k] : 0.f;
+        gin[((size_t)img * C + ci) * G2 + pix0 + p] = As[ci * (FB_PIX + 1) + p] > 0.f ? acc[k] : 0.f;
       }
     }
     {   // filter gradient
@@ -444,7 +485,7 @@ conv_final_bwd_kernel(const float* __restrict__ gpl,    // [n_img][1600][32]  pl
       for (int p = 0; p < FB_PIX; ++p) {
         const float gv = Gs[p * 33 + wco];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) wacc[k] = fmaf(gv, As[(wcg * 4 + k) * (FB_PIX + 4) + p], wacc[k]);
+        for (int k = 0; k < 4; ++k) wacc[k] = fmaf(gv, As[(wcg * 4 + k) * (FB_PIX + 1) + p], wacc[k]);
         bacc += gv;
       }
     }
@@ -466,9 +507,10 @@ struct WgradCfg {
   static constexpr int GW = 4 * GPR;                 // gradient row (padded to whole groups)
   static constexpr int CS = 4 * GPR + 8;             // input row: pixel x at column x + 4
   static constexpr int PSX = ((R + 2) * CS / 4 % 2 == 1) ? (R + 2) * CS : (R + 2) * CS + 4;   // odd number of 16-byte units: conflict-free lane stride
-  static constexpr int PSG = R * GW;
+  static constexpr int GST = 36;                     // gradient tile: [row][pixel][32 co] with a 36-float pixel stride (16-byte aligned, staging
+                                                     // stores at most 4-way conflicted)
   static constexpr int NB = HW / R;
-  static constexpr int SMEM_BYTES = (32 * PSX + 32 * PSG) * 4;
+  static constexpr int SMEM_BYTES = (32 * PSX + R * GW * GST) * 4;
   static_assert(HW % R == 0, "row band");
 };
 
@@ -479,19 +521,20 @@ conv3x3_wgrad_kernel(const float* __restrict__ gz,    // [n_img][COUT][HW][HW]  
                      int n_img, int COUT, int CIN_SRC,
                      float* __restrict__ dW,          // [COUT][CIN_TOTAL][3][3], already offset to this source's first input channel
                      int CIN_TOTAL, float* __restrict__ db) {   // db: null for the second source of a concat
-  constexpr int HW = K::HW, R = K::R, GPR = K::GPR, GW = K::GW, CS = K::CS, PSX = K::PSX, PSG = K::PSG;
+  constexpr int HW = K::HW, R = K::R, GPR = K::GPR, GW = K::GW, CS = K::CS, PSX = K::PSX, GST = K::GST;
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;                 // [32 ci][R + 2][CS]
-  float* gs = smem + 32 * PSX;      // [32 co][R][GW]
+  float* gs = smem + 32 * PSX;      // [R][GW][GST]: the 32 output channels of a pixel are contiguous
   const int n_ci = CIN_SRC / 32;
   const int co0 = (blockIdx.x / n_ci) * 32, ci0 = (blockIdx.x % n_ci) * 32;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  float acc[4][9];
+  // output-channel pairs (4w, 4w+1), (4w+2, 4w+3): the inner loop is FFMA2 (bit-identical to scalar fma, half the issue slots)
+  float2 acc[2][9];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < 2; ++k)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
-  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < 9; ++t) acc[k][t] = make_float2(0.f, 0.f);
+  float2 bacc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   const int n_tiles = n_img * K::NB;
 #pragma unroll 1
   for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
@@ -506,11 +549,11 @@ conv3x3_wgrad_kernel(const float* __restrict__ gz,    // [n_img][COUT][HW][HW]  
     }
     for (int e = tid; e < 32 * R * GW; e += 256) {
       const int c = e / (R * GW), rem = e % (R * GW), r = rem / GW, xx = rem % GW;
-      gs[c * PSG + r * GW + xx] = xx < HW ? __ldg(gz + (((size_t)img * COUT + co0 + c) * HW + y0 + r) * HW + xx) : 0.f;
+      gs[(r * GW + xx) * GST + c] = xx < HW ? __ldg(gz + (((size_t)img * COUT + co0 + c) * HW + y0 + r) * HW + xx) : 0.f;
     }
     __syncthreads();
     const float* xl = xs + lane * PSX;
-    const float* gl = gs + (4 * w) * PSG;
+    const float* gl = gs + 4 * w;
 #pragma unroll 1
     for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -522,14 +565,15 @@ conv3x3_wgrad_kernel(const float* __restrict__ gz,    // [n_img][COUT][HW][HW]  
           const float4 nxt = ld4(xrow + 4 * (xg + 2));
           const float xv[6] = {prev.w, cur.x, cur.y, cur.z, cur.w, nxt.x};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 gq = ld4(gl + k * PSG + r * GW + 4 * xg);
-            const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
-            if (dy == 0) bacc[k] += (gq.x + gq.y) + (gq.z + gq.w);
+          for (int p = 0; p < 4; ++p) {
+            const float4 gq = ld4(gl + (r * GW + 4 * xg + p) * GST);   // 4 output channels at pixel 4 xg + p (warp-uniform address)
+            const float2 g01 = make_float2(gq.x, gq.y), g23 = make_float2(gq.z, gq.w);
+            if (dy == 0) { add2(bacc[0], g01); add2(bacc[1], g23); }
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-              for (int p = 0; p < 4; ++p) acc[k][dy * 3 + dx] = fmaf(gv[p], xv[p + dx], acc[k][dy * 3 + dx]);
+            for (int dx = 0; dx < 3; ++dx) {
+              fma2(acc[0][dy * 3 + dx], g01, xv[p + dx]);
+              fma2(acc[1][dy * 3 + dx], g23, xv[p + dx]);
+            }
           }
           prev = cur;
           cur = nxt;
@@ -541,8 +585,8 @@ conv3x3_wgrad_kernel(const float* __restrict__ gz,    // [n_img][COUT][HW][HW]  
   for (int k = 0; k < 4; ++k) {
     float* d = dW + ((size_t)(co0 + 4 * w + k) * CIN_TOTAL + ci0 + lane) * 9;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) red_add(d + t, acc[k][t]);
-    if (db && ci0 == 0 && lane == 0) red_add(db + co0 + 4 * w + k, bacc[k]);
+    for (int t = 0; t < 9; ++t) red_add(d + t, (k & 1) ? acc[k >> 1][t].y : acc[k >> 1][t].x);
+    if (db && ci0 == 0 && lane == 0) red_add(db + co0 + 4 * w + k, (k & 1) ? bacc[k >> 1].y : bacc[k >> 1].x);
   }
 }
 
@@ -777,7 +821,9 @@ conv_in_bwd_kernel(const float* __restrict__ x,       // [B][40 ix][40 iy][40 iz
       __syncthreads();   // staging complete / previous sub-tile's phase 2 done
       {   // phase 1: voxel (iy = tid % 40, iz = 8 zt + tid / 40)
         const int iy = tid % G, izl = tid / G, iz = 8 * zt + izl;
-        float z[32];
+        float z[32], gy[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) gy[c] = __ldg(gyz + (size_t)c * G2 + iz * G + iy);   // in flight during the 864 FMAs below
 #pragma unroll
         for (int c = 0; c < 32; ++c) z[c] = ws[27 * 32 + c];
 #pragma unroll
@@ -797,7 +843,7 @@ conv_in_bwd_kernel(const float* __restrict__ x,       // [B][40 ix][40 iy][40 iz
             }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float gsum = (gxz[c * 40 + iz] + gxy[c * 40 + iy]) + __ldg(gyz + (size_t)c * G2 + iz * G + iy);
+          const float gsum = (gxz[c * 40 + iz] + gxy[c * 40 + iy]) + gy[c];
           gfs[c * CB_GF + tid] = z[c] > 0.f ? gsum / 40.0f : 0.f;
         }
       }

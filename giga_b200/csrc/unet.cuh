@@ -67,13 +67,15 @@ conv3x3_kernel(const float* __restrict__ src0,  // [n_img][CIN0][HW][HW]
   const bool active = tp < K::NPT;
   const int j = active ? tp / K::GPR : 0, g = active ? tp % K::GPR : 0;
 
-  float acc[2][4][TCO];
+  // output-channel PAIRS: the inner loop is FFMA2 (packed fp32 pairs: each component an IEEE fma, bit-identical to the scalar loop, half
+  // the issue slots -- the loop competes with its own shared-memory loads for issue)
+  float2 acc2[2][4][TCO / 2];
 #pragma unroll
   for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int k = 0; k < TCO; ++k) acc[r][p][k] = 0.f;
+      for (int k = 0; k < TCO / 2; ++k) acc2[r][p][k] = make_float2(0.f, 0.f);
 
 #pragma unroll 1
   for (int c0 = 0; c0 < K::CIN; c0 += CC) {
@@ -117,22 +119,22 @@ conv3x3_kernel(const float* __restrict__ src0,  // [n_img][CIN0][HW][HW]
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
-            float w[TCO];
+            float2 w[TCO / 2];
             {
               const float4 w0 = ld4(bp + (dy * 3 + dx) * CT);
-              w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
+              w[0] = make_float2(w0.x, w0.y); w[1] = make_float2(w0.z, w0.w);
               if constexpr (TCO == 8) {
                 const float4 w1 = ld4(bp + (dy * 3 + dx) * CT + CT / 2);
-                w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+                w[2] = make_float2(w1.x, w1.y); w[3] = make_float2(w1.z, w1.w);
               }
             }
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
               const float v0 = a[dy][p + dx], v1 = a[dy + 1][p + dx];
 #pragma unroll
-              for (int k = 0; k < TCO; ++k) {
-                acc[0][p][k] = fmaf(v0, w[k], acc[0][p][k]);
-                acc[1][p][k] = fmaf(v1, w[k], acc[1][p][k]);
+              for (int k = 0; k < TCO / 2; ++k) {
+                fma2(acc2[0][p][k], w[k], v0);
+                fma2(acc2[1][p][k], w[k], v1);
               }
             }
           }
@@ -141,6 +143,7 @@ conv3x3_kernel(const float* __restrict__ src0,  // [n_img][CIN0][HW][HW]
   }
 
   if (!active) return;
+  auto accv = [&](int r, int p, int k) { return (k & 1) ? acc2[r][p][k >> 1].y : acc2[r][p][k >> 1].x; };
   if constexpr (K::EPI == 1) {
 #pragma unroll
     for (int k = 0; k < TCO; ++k) {
@@ -150,7 +153,7 @@ conv3x3_kernel(const float* __restrict__ src0,  // [n_img][CIN0][HW][HW]
         const size_t base = (((size_t)img * K::COUT + co) * HW + y0 + 2 * j + r) * HW + 4 * g;
 #pragma unroll
         for (int p = 0; p < 4; ++p)
-          if (4 * g + p < HW) out[base + p] = (!bias || __ldg(bias + base + p) > 0.f) ? acc[r][p][k] : 0.f;
+          if (4 * g + p < HW) out[base + p] = (!bias || __ldg(bias + base + p) > 0.f) ? accv(r, p, k) : 0.f;
       }
     }
     return;
@@ -164,7 +167,7 @@ conv3x3_kernel(const float* __restrict__ src0,  // [n_img][CIN0][HW][HW]
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int p = 0; p < 4; ++p) v[r][p] = fmaxf(acc[r][p][k] + bv, 0.f);
+      for (int p = 0; p < 4; ++p) v[r][p] = fmaxf(accv(r, p, k) + bv, 0.f);
     float* o = out + ((size_t)img * K::COUT + co) * (HW * HW);
 #pragma unroll
     for (int r = 0; r < 2; ++r) {

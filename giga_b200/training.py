@@ -1,26 +1,18 @@
-"""Training bridge (opt-in) and data-parallel gradient exchange for `scripts/train_giga.py`-style steps.
+"""Training on the library's own kernels: the native training step, the fused loss / flat Adam tail, the gradient exchange -- and the
+round-1 recompute bridge, kept only for gradients with respect to query positions.
 
-STATUS -- read this first.  The hand-written sm_100a kernels in libgiga_b200.so implement the FORWARD of
-the hot path.  Native backward kernels (MLP dgrad/wgrad, grid-sample scatter, conv/convT dgrad+wgrad,
-max-pool and plane-mean backward) are not built yet.  Until they are, a model can
-opt in to this bridge with `net.enable_training_bridge()`:
-
-  * forward values ALWAYS come from the CUDA library (identical to inference, parity-tested);
-  * backward re-evaluates the same function with PyTorch ops on the GPU under autograd and returns the
-    parameter gradients -- i.e. library (ATen/cuDNN) kernels, GPU only, gradients only.
-
-Without the opt-in the model's outputs carry no autograd graph and `loss.backward()` raises, so nothing
-falls back silently.  The bridge never runs on the CPU and is never used for inference.
-
-Also here: `allreduce_gradients` -- the single flat all-reduce of the 581,863-element gradient buffer
-(2.33 MB) that a scene-sharded data-parallel step needs, one process per GPU.
-
-The training-step TAIL is native (csrc/train.cuh): `select(out)` (train_giga.py:153-158) and
-`loss_fn(y_pred, y)` (:161-174) with the reference's signatures and return values -- ONE CUDA launch that produces the loss terms and the
-gradient of loss.mean() with respect to the predictions (giga_loss), wired into autograd so `loss.backward()` hands those gradients to
-whatever produced the predictions -- and `Adam`, torch.optim.Adam's constructor for the arguments train_giga.py uses (:67), which keeps
-every parameter, gradient and moment in four flat buffers (the parameters and their .grad become views) and steps them in ONE launch
-(giga_adam_step); its `allreduce_gradients()` all-reduces that flat gradient buffer in place (no gather / scatter copies).
+  * `native_forward` / `_NativeStep` (csrc/train_bwd.cuh, giga_train_forward / giga_train_backward): what `net(...)` runs when gradient
+    mode is on and parameters require gradients -- replaces the autograd graph of scripts/train_giga.py:199-211 (`_update`).  Forward on
+    the fp32 kernels from the live parameter tensors (packed on the device), backward = hand-written kernels for every layer; gradients
+    are accumulated either straight into `.grad` (parameters owned by `Adam` below: one flat buffer) or handed to autograd.
+  * `select(out)` (train_giga.py:153-158), `loss_fn(y_pred, y)` (:161-174) with the reference's signatures and return values -- ONE CUDA
+    launch for the loss terms and the gradient of loss.mean() w.r.t. the predictions (giga_loss) -- and `Adam`, torch.optim.Adam's
+    constructor for the arguments train_giga.py uses (:67): parameters, gradients and moments in four flat buffers, ONE launch per step
+    (giga_adam_step); `Adam.allreduce_gradients()` = one in-place NCCL all-reduce of the flat 581,863-element gradient buffer
+    (SURVEY.md section 8e), `allreduce_gradients(params)` the same for a plain torch optimizer.
+  * `bridged_forward` / `_Bridge` (opt-in, `net.enable_training_bridge()`): forward by the CUDA library, backward = PyTorch autograd
+    recompute on the GPU.  Used by `grad_refine` (gradients w.r.t. the query positions) and by the tests as a second
+    gradient reference; never on the training path, never on the CPU.
 """
 from __future__ import annotations
 

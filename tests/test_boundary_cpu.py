@@ -104,3 +104,35 @@ def test_planner_host_mirror_surface():
         assert lib.giga_select_grasps(None, None, None, None, None, 1, C.byref(p), 8, None, None, None, None, None, None, None) == -1
         assert lib.giga_detect_host(None, None, None, 1, C.byref(p), 8, None, None, None, None, None, None) == -1
         assert lib.giga_forward(None, None, 1, None, 0, None, 0, None, None, None, None, None, None, None, None) == -1
+
+
+def test_training_and_perception_host_surface():
+    """The training step and the perception mirror keep the reference's surface (train_giga.py:67,153-174; perception.py:10-126) and
+    refuse to compute without a device: no PyTorch / CPU path stands in for the kernels."""
+    import inspect
+
+    import numpy as np
+
+    import giga_b200
+    from giga_b200 import perception, training
+    from giga_b200._lib import lib
+
+    assert list(inspect.signature(training.loss_fn).parameters) == ["y_pred", "y"]
+    assert list(inspect.signature(training.select).parameters) == ["out"]
+    assert list(inspect.signature(training.Adam.__init__).parameters)[:6] == ["self", "params", "lr", "betas", "eps", "weight_decay"]
+    assert list(inspect.signature(perception.TSDFVolume.__init__).parameters)[:3] == ["self", "size", "resolution"]
+    assert list(inspect.signature(perception.TSDFVolume.integrate).parameters) == ["self", "depth_img", "intrinsic", "extrinsic"]
+    assert list(inspect.signature(perception.create_tsdf).parameters) == ["size", "resolution", "depth_imgs", "intrinsic", "extrinsics"]
+    intr = perception.CameraIntrinsic(640, 480, 540.0, 541.0, 320.0, 240.0)
+    assert (intr.fx, intr.fy, intr.cx, intr.cy) == (540.0, 541.0, 320.0, 240.0)
+    assert perception.CameraIntrinsic.from_dict(intr.to_dict()).K.tolist() == intr.K.tolist()
+    if not torch.cuda.is_available():
+        net = giga_b200.get_network("giga")                         # trainable parameters + gradient mode: the training path
+        assert net._train_active(torch.zeros(1, 4, 3))
+        with pytest.raises(giga_b200.GigaError):
+            net(torch.zeros(1, 40, 40, 40), torch.zeros(1, 1, 3), p_tsdf=torch.zeros(1, 8, 3))
+        with pytest.raises(giga_b200.GigaError):
+            perception.TSDFVolume(0.3, 40)
+        assert lib.giga_train_forward(None, None, 1, None, 0, None, 0, 0, None, None, None, None, None) == -1
+        assert lib.giga_train_backward(None, None, None, None, None, None) == -1
+        assert lib.giga_tsdf_grid(None, None, None, 40, None, None) == -1

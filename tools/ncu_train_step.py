@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """One native training step (configs[3]: B = 64, 1 grasp point + 2048 occupancy points per sample) under a profiler: 2 warm-up steps +
 1 profiled step (53 kernels: pack, forward, loss, backward, Adam).
-    ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:giga' -s 106 -c 53 --csv --log-file launches.csv python tools/ncu_train_step.py
-    ncu --set full --clock-control none -k 'regex:giga' -s 106 -c 53 -o prof python tools/ncu_train_step.py"""
+    ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:<the step kernels, see tools/gpu_r02_w.sh>' -s 106 -c 53 --csv --log-file launches.csv python tools/ncu_train_step.py
+    ncu --set full --clock-control none -k 'regex:<the step kernels, see tools/gpu_r02_w.sh>' -s 106 -c 53 -o prof python tools/ncu_train_step.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch, torch.nn.functional as F
