@@ -50,6 +50,8 @@ SYMBOLS = {
     "giga_vgn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_loss": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p]),
     "giga_adam_step": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_long, C.c_int] + [C.c_double] * 5 + [C.c_void_p]),
+    "giga_ctx_commit_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "giga_debug_blob": (C.c_long, [C.c_void_p, C.c_int, C.c_void_p, C.c_long]),
     "giga_train_bind": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "giga_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -22,6 +22,7 @@
 #include "train.cuh"
 #include "train_bwd.cuh"
 #include "tsdf.cuh"
+#include "pack_dev.cuh"
 #include "planner.cuh"
 #include "unet.cuh"
 #include "unet_tall.cuh"
@@ -106,6 +107,9 @@ const char* kConvName[10] = {"down_convs.0.conv1", "down_convs.0.conv2", "down_c
 const int kUpCin[2] = {128, 64}, kUpCout[2] = {64, 32};
 const char* kHeadName[4] = {"qual", "rot", "width", "tsdf"};
 
+// the encoder blob is allocated with room for the training step's data-gradient weights behind the inference layout (train_api.cuh)
+long enc_blob_floats(const EncLayout& L);
+
 EncLayout make_enc_layout() {
   EncLayout L;
   long o = 0;
@@ -119,6 +123,12 @@ EncLayout make_enc_layout() {
   L.tc_fin = o; o += 1024;
   L.total = o;
   return L;
+}
+
+long enc_blob_floats(const EncLayout& L) {
+  long o = L.total;
+  for (int i = 0; i < 10; ++i) o += (long)kConvCin[i] * 9 * kConvCout[i];
+  return o;
 }
 
 // activation workspace: name -> floats per image (3B images), in forward order
@@ -229,6 +239,10 @@ struct giga_ctx {
     long blob_floats = 0;
     float* d_heads = nullptr;     // [4][DW_HEAD]
     float* d_cin = nullptr;       // conv_in [27][32] + [32]
+    TcPackEntry* d_tctab = nullptr;   // device-side commit of the tensor-core operand layouts (pack_dev.cuh)
+    int n_tctab = 0;
+    float* d_hscale = nullptr;    // [4][2] per-head power-of-two pre-scale
+    bool tc_table_dirty = true;
     int cap_B = 0;
     float* d_g[kNumActs] = {};    // gradients w.r.t. the pre-activations of kActs[i] (same shapes as d_act)
     float* d_gpre = nullptr;      // [3][B][32][1600]
@@ -633,6 +647,14 @@ void giga_ctx_destroy(giga_ctx* ctx) {
     for (void* q : mp)
       if (q) cudaFree(q);
   }
+  {
+    auto& T = ctx->tr;   // (d_blob / d_heads alias ctx->d_enc / ctx->d_heads)
+    void* tp[] = {T.d_tab, T.d_cin, T.d_tctab, T.d_hscale, T.d_gpre, T.d_gplanes, T.d_planes, T.d_save};
+    for (void* q : tp)
+      if (q) cudaFree(q);
+    for (float* q : T.d_g)
+      if (q) cudaFree(q);
+  }
   if (ctx->d_vgn) cudaFree(ctx->d_vgn);
   if (ctx->d_vgn_act) cudaFree(ctx->d_vgn_act);
   if (ctx->d_loss_part) cudaFree(ctx->d_loss_part);
@@ -768,7 +790,7 @@ int giga_ctx_commit_params(giga_ctx* ctx) {
       get(ctx, "encoder.unet.up_convs.1.upconv.weight", (long)kUpCin[1] * kUpCout[1] * 4, &uw);
       pack_conv_tc<T_u1up>(uw, blob.data() + ctx->el.tc_up[1]);
     }
-    if (!ctx->d_enc) CU_TRY(cudaMalloc(&ctx->d_enc, sizeof(float) * ctx->el.total));
+    if (!ctx->d_enc) CU_TRY(cudaMalloc(&ctx->d_enc, sizeof(float) * enc_blob_floats(ctx->el)));   // + room for the training step's data-gradient weights
     CU_TRY(cudaMemcpy(ctx->d_enc, blob.data(), sizeof(float) * ctx->el.total, cudaMemcpyHostToDevice));
     ctx->has_encoder = true;
   }

@@ -64,17 +64,25 @@ int train_attrs(giga_ctx* ctx) {
 int train_build_table(giga_ctx* ctx) {
   auto& T = ctx->tr;
   const EncLayout& L = ctx->el;
-  if (!T.d_blob) {
-    long o = L.tc_conv[0];   // the fp32 prefix of the inference blob layout: conv[i], bias[i], up_w, up_b, fin_w, fin_b
+  if (!T.d_tab) {
+    // the training operands live in the SAME blobs as the inference path's (ctx->d_enc: fp32 prefix shared, data-gradient weights behind the
+    // inference layout; ctx->d_heads): one packing pass serves both
+    long o = L.total;
     for (int i = 0; i < 10; ++i) { T.dg[i] = o; o += (long)kConvCin[i] * 9 * kConvCout[i]; }
     T.blob_floats = o;
-    CU_TRY(cudaMalloc(&T.d_blob, sizeof(float) * o));
-    CU_TRY(cudaMemset(T.d_blob, 0, sizeof(float) * o));
-    CU_TRY(cudaMalloc(&T.d_heads, sizeof(float) * 4 * DW_HEAD));
-    CU_TRY(cudaMemset(T.d_heads, 0, sizeof(float) * 4 * DW_HEAD));
+    if (!ctx->d_enc) {
+      CU_TRY(cudaMalloc(&ctx->d_enc, sizeof(float) * o));
+      CU_TRY(cudaMemset(ctx->d_enc, 0, sizeof(float) * o));
+    }
+    if (!ctx->d_heads) {
+      CU_TRY(cudaMalloc(&ctx->d_heads, sizeof(float) * 4 * DW_HEAD));
+      CU_TRY(cudaMemset(ctx->d_heads, 0, sizeof(float) * 4 * DW_HEAD));
+    }
     CU_TRY(cudaMalloc(&T.d_cin, sizeof(ConvInParams)));
     CU_TRY(cudaMalloc(&T.d_tab, sizeof(PackEntry) * 256));
   }
+  T.d_blob = ctx->d_enc;
+  T.d_heads = ctx->d_heads;
   std::vector<PackEntry> tab;
   auto add = [&](const float* src, float* dst, int O, int I, int Tt, int mode, int ld, int i0 = 0, int In = 0) {
     PackEntry e = {src, dst, O, I, Tt, mode, ld, i0, In, 0};
@@ -181,44 +189,191 @@ void launch_convT_bwd(giga_ctx* ctx, const char* name, int n_img, const float* i
   }
 }
 
-}  // namespace
-
-extern "C" {
-
-int giga_train_bind(giga_ctx* ctx, int n, const char* const* names, const float* const* values, float* const* grads) {
-  if (!ctx || n <= 0 || !names || !values || !grads) return fail(GIGA_EINVAL, "giga_train_bind: bad argument");
-  if (int r = set_device(ctx)) return r;
-  auto& T = ctx->tr;
-  std::map<std::string, int> slot;
-  for (int s = 0; s < giga_ctx::Train::kSlots; ++s) slot[train_slot_name(s)] = s;
-  const float* val[giga_ctx::Train::kSlots] = {};
-  float* grad[giga_ctx::Train::kSlots] = {};
+// names -> slots; validates completeness (all encoder tensors, whole heads)
+int map_param_slots(const char* what, int n, const char* const* names, const float* const* values, float* const* grads,
+                    const float** val, float** grad, unsigned* heads_out) {
+  static std::map<std::string, int> slot;
+  if (slot.empty())
+    for (int s = 0; s < giga_ctx::Train::kSlots; ++s) slot[train_slot_name(s)] = s;
   for (int i = 0; i < n; ++i) {
-    if (!names[i] || !values[i]) return fail(GIGA_EINVAL, "giga_train_bind: null name or tensor");
+    if (!names[i] || !values[i]) return fail(GIGA_EINVAL, std::string(what) + ": null name or tensor");
     auto it = slot.find(names[i]);
-    if (it == slot.end()) return fail(GIGA_EINVAL, std::string("giga_train_bind: unknown parameter '") + names[i] + "'");
-    if ((reinterpret_cast<uintptr_t>(values[i]) & 15) || (reinterpret_cast<uintptr_t>(grads[i]) & 15))
-      return fail(GIGA_EINVAL, std::string("giga_train_bind: '") + names[i] + "' is not 16-byte aligned");
+    if (it == slot.end()) return fail(GIGA_EINVAL, std::string(what) + ": unknown parameter '" + names[i] + "'");
+    if ((reinterpret_cast<uintptr_t>(values[i]) & 15) || (grads && (reinterpret_cast<uintptr_t>(grads[i]) & 15)))
+      return fail(GIGA_EINVAL, std::string(what) + ": '" + names[i] + "' is not 16-byte aligned");
     val[it->second] = values[i];
-    grad[it->second] = grads[i];
+    if (grads) grad[it->second] = grads[i];
   }
   for (int s = 0; s < 28; ++s)
-    if (!val[s]) return fail(GIGA_ESTATE, "giga_train_bind: missing encoder parameter '" + train_slot_name(s) + "'");
+    if (!val[s]) return fail(GIGA_ESTATE, std::string(what) + ": missing encoder parameter '" + train_slot_name(s) + "'");
   unsigned heads = 0;
   for (int h = 0; h < 4; ++h) {
     int have = 0;
     for (int r = 0; r < TS_HEAD; ++r) have += val[TS_HEAD0 + TS_HEAD * h + r] != nullptr;
     if (have == TS_HEAD) heads |= 1u << h;
-    else if (have) return fail(GIGA_ESTATE, std::string("giga_train_bind: decoder_") + kHeadName[h] + " is incomplete");
+    else if (have) return fail(GIGA_ESTATE, std::string(what) + ": decoder_" + kHeadName[h] + " is incomplete");
   }
-  if (!heads) return fail(GIGA_ESTATE, "giga_train_bind: no decoder head");
+  if (!heads) return fail(GIGA_ESTATE, std::string(what) + ": no decoder head");
+  *heads_out = heads;
+  return GIGA_OK;
+}
+
+template <class K>
+TcPackEntry tc_entry(const float* src, float* dst_words) {
+  TcPackEntry e = {src, reinterpret_cast<uint16_t*>(dst_words), K::NNT, K::NC, K::NTAPS, K::NTILE, K::CIN, K::COUT, K::MODE, 0};
+  return e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int giga_ctx_commit_device(giga_ctx* ctx, int n, const char* const* names, const float* const* values, void* stream) {
+  if (!ctx || n <= 0 || !names || !values) return fail(GIGA_EINVAL, "giga_ctx_commit_device: bad argument");
+  if (int r = set_device(ctx)) return r;
+  auto& T = ctx->tr;
+  const float* val[giga_ctx::Train::kSlots] = {};
+  unsigned heads = 0;
+  if (int r = map_param_slots("giga_ctx_commit_device", n, names, values, nullptr, val, nullptr, &heads)) return r;
+  bool same = T.bound && heads == T.heads;
+  for (int s = 0; same && s < giga_ctx::Train::kSlots; ++s) same = val[s] == T.val[s];
+  if (!same) {
+    memcpy(T.val, val, sizeof val);
+    memset(T.grad, 0, sizeof T.grad);   // gradient buffers belong to a giga_train_bind of the same tensors
+    T.heads = heads;
+    T.bound = true;
+    T.table_dirty = T.tc_table_dirty = true;
+  }
+  if (int r = ensure_attrs(ctx)) return r;
+  // the packed blobs may still be read by kernels of this ctx on other streams (torch side streams, the pipelined host path)
+  CU_TRY(cudaDeviceSynchronize());
+  if (T.table_dirty)
+    if (int r = train_build_table(ctx)) return r;
+  const EncLayout& L = ctx->el;
+  float* E = ctx->d_enc;
+  if (!ctx->d_hc) {
+    CU_TRY(cudaMalloc(&ctx->d_hc, sizeof(float) * 4 * HC_SIZE));
+    CU_TRY(cudaMemset(ctx->d_hc, 0, sizeof(float) * 4 * HC_SIZE));
+  }
+  if (!ctx->d_sched) {
+    CU_TRY(cudaMalloc(&ctx->d_sched, sizeof(unsigned) * 4));
+    CU_TRY(cudaMemset(ctx->d_sched, 0, sizeof(unsigned) * 4));
+  }
+  for (int type = 0; type < 5; ++type) {
+    const int nh = type == 0 ? 3 : 1;
+    const unsigned need = type == 0 ? 7u : (1u << (type - 1));
+    if ((heads & need) != need) {
+      if (ctx->d_wblob[type]) { cudaFree(ctx->d_wblob[type]); ctx->d_wblob[type] = nullptr; }
+    } else if (!ctx->d_wblob[type]) {
+      CU_TRY(cudaMalloc(&ctx->d_wblob[type], (size_t)5 * wd_block_bytes(nh)));
+      CU_TRY(cudaMemset(ctx->d_wblob[type], 0, (size_t)5 * wd_block_bytes(nh)));
+    }
+  }
+  if (!T.d_tctab) {
+    CU_TRY(cudaMalloc(&T.d_tctab, sizeof(TcPackEntry) * 16));
+    CU_TRY(cudaMalloc(&T.d_hscale, sizeof(float) * 8));
+  }
+  if (T.tc_table_dirty) {
+    std::vector<TcPackEntry> tab;
+    auto cw = [&](int i) { return T.val[2 + 2 * i]; };
+    tab.push_back(tc_entry<T_c40>(cw(0), E + L.tc_conv[0]));
+    tab.push_back(tc_entry<T_c40>(cw(1), E + L.tc_conv[1]));
+    tab.push_back(tc_entry<T_d1c1>(cw(2), E + L.tc_conv[2]));
+    tab.push_back(tc_entry<T_c20>(cw(3), E + L.tc_conv[3]));
+    tab.push_back(tc_entry<T_d2c1>(cw(4), E + L.tc_conv[4]));
+    tab.push_back(tc_entry<T_d2c2>(cw(5), E + L.tc_conv[5]));
+    tab.push_back(tc_entry<T_u0c1>(cw(6), E + L.tc_conv[6]));
+    tab.push_back(tc_entry<T_c20>(cw(7), E + L.tc_conv[7]));
+    tab.push_back(tc_entry<T_u1c1>(cw(8), E + L.tc_conv[8]));
+    tab.push_back(tc_entry<T_u1c2>(cw(9), E + L.tc_conv[9]));
+    tab.push_back(tc_entry<T_u0up>(T.val[22], E + L.tc_up[0]));
+    tab.push_back(tc_entry<T_u1up>(T.val[24], E + L.tc_up[1]));
+    TcPackEntry fin = {T.val[26], reinterpret_cast<uint16_t*>(E + L.tc_fin), 0, 0, 0, 0, 0, 0, 2, 0};
+    tab.push_back(fin);
+    CU_TRY(cudaMemcpy(T.d_tctab, tab.data(), sizeof(TcPackEntry) * tab.size(), cudaMemcpyHostToDevice));
+    T.n_tctab = (int)tab.size();
+    T.tc_table_dirty = false;
+  }
+  DecPackArgs A = {};
+  A.heads = heads;
+  for (int h = 0; h < 4; ++h) {
+    if (!(heads & (1u << h))) continue;
+    const float* const* v = T.val + TS_HEAD0 + TS_HEAD * h;
+    for (int i = 0; i < 5; ++i) {
+      A.head[h].fcc_w[i] = v[2 + 6 * i]; A.head[h].fcc_b[i] = v[3 + 6 * i];
+      A.head[h].w0[i] = v[4 + 6 * i];   A.head[h].b0[i] = v[5 + 6 * i];
+      A.head[h].w1[i] = v[6 + 6 * i];   A.head[h].b1[i] = v[7 + 6 * i];
+    }
+  }
+  for (int t = 0; t < 5; ++t) A.wblob[t] = ctx->d_wblob[t];
+  A.hc = ctx->d_hc;
+  A.dheads = ctx->d_heads;
+  A.scale = T.d_hscale;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    LaunchScope ls(ctx, "commit:pack_fp32", st);
+    train_pack_kernel<<<dim3(T.n_tab, 4), 256, 0, st>>>(T.d_tab);
+  }
+  {
+    LaunchScope ls(ctx, "commit:pack_tc", st);
+    pack_conv_tc_kernel<<<dim3(T.n_tctab, 8), 256, 0, st>>>(T.d_tctab);
+  }
+  {
+    LaunchScope ls(ctx, "commit:head_scale", st);
+    head_scale_kernel<<<4, 256, 0, st>>>(A);
+  }
+  {
+    LaunchScope ls(ctx, "commit:pack_decoder", st);
+    pack_decoder_ws_kernel<<<dim3(5, 5), 256, 0, st>>>(A);
+  }
+  // conv_in's 27 x 32 taps are kernel parameters of the inference kernel (constant bank): 3.6 KB come back to the host
+  {
+    float cin[28 * 32];
+    CU_TRY(cudaMemcpyAsync(cin, T.d_cin, sizeof cin, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    memcpy(&ctx->conv_in.w[0][0].x, cin, sizeof(float) * 27 * 32);
+    memcpy(&ctx->conv_in.b[0].x, cin + 27 * 32, sizeof(float) * 32);
+  }
+  CU_TRY(cudaGetLastError());
+  ctx->has_encoder = true;
+  ctx->has_vgn = false;
+  ctx->heads = heads;
+  ctx->committed = true;
+  ctx->graph_epoch++;
+  return GIGA_OK;
+}
+
+long giga_debug_blob(giga_ctx* ctx, int which, void* dst, long capacity) {
+  if (!ctx || !dst || which < 0 || which > 7) return fail(GIGA_EINVAL, "giga_debug_blob: bad argument");
+  if (int r = set_device(ctx)) return r;
+  const void* src = nullptr;
+  long bytes = 0;
+  if (which == 0) { src = ctx->d_enc; bytes = sizeof(float) * ctx->el.total; }
+  else if (which == 1) { src = ctx->d_heads; bytes = sizeof(float) * 4 * DW_HEAD; }
+  else if (which == 2) { src = ctx->d_hc; bytes = sizeof(float) * 4 * HC_SIZE; }
+  else { src = ctx->d_wblob[which - 3]; bytes = (long)5 * wd_block_bytes(which == 3 ? 3 : 1); }
+  if (!src) return 0;
+  if (bytes > capacity) return fail(GIGA_EINVAL, "giga_debug_blob: capacity too small");
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return bytes;
+}
+
+int giga_train_bind(giga_ctx* ctx, int n, const char* const* names, const float* const* values, float* const* grads) {
+  if (!ctx || n <= 0 || !names || !values || !grads) return fail(GIGA_EINVAL, "giga_train_bind: bad argument");
+  if (int r = set_device(ctx)) return r;
+  auto& T = ctx->tr;
+  const float* val[giga_ctx::Train::kSlots] = {};
+  float* grad[giga_ctx::Train::kSlots] = {};
+  unsigned heads = 0;
+  if (int r = map_param_slots("giga_train_bind", n, names, values, grads, val, grad, &heads)) return r;
   bool same = T.bound && heads == T.heads;
   for (int s = 0; same && s < giga_ctx::Train::kSlots; ++s) same = val[s] == T.val[s];
   memcpy(T.val, val, sizeof val);
   memcpy(T.grad, grad, sizeof grad);
   T.heads = heads;
   T.bound = true;
-  if (!same) T.table_dirty = true;
+  if (!same) T.table_dirty = T.tc_table_dirty = true;
   return GIGA_OK;
 }
 

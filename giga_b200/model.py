@@ -158,6 +158,7 @@ class _Engine:
         self.param_names = None
         self.tensors = []
         self.struct_version = -1
+        self.commit_mode = "auto"      # "host": always pack on the host (A/B testing of the device-side packer)
 
     def __del__(self):
         try:
@@ -186,6 +187,17 @@ class _Engine:
         if key == self.param_key and names == self.param_names:
             return
         self.param_names = names
+        # parameters that already live on this device (the normal case) are packed BY KERNELS straight from the live tensors
+        # (giga_ctx_commit_device: no device -> host -> pack -> device round trip); anything else takes the host packer below
+        if self.commit_mode != "host" and "encoder.conv_in.weight" in names and all(
+                v.is_cuda and v.device == self.device and v.dtype == torch.float32 and v.is_contiguous() and v.data_ptr() % 16 == 0 for v in self.tensors):
+            n = len(params)
+            c_names = (C.c_char_p * n)(*[k.encode() for k, _ in params])
+            vals = (C.c_void_p * n)(*[v.data_ptr() for v in self.tensors])
+            check(lib.giga_ctx_commit_device(self.h, n, c_names, vals, _stream(self.device)), "giga_ctx_commit_device")
+            self.__dict__.pop("_train_key", None)      # the commit re-bound the value pointers: the training step binds its gradients again
+            self.param_key = key
+            return
         # one flattened upload (a training loop re-commits after every optimizer.step(): 164 separate copies cost 20 ms)
         with torch.no_grad():
             flat = torch.cat([v.detach().reshape(-1).float() for _, v in params]).contiguous()

@@ -204,6 +204,16 @@ int giga_loss(giga_ctx *ctx, const float *label_pred, const float *rot_pred, con
 int giga_adam_step(giga_ctx *ctx, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long n, int step, double lr,
                    double beta1, double beta2, double eps, double weight_decay, void *stream);
 
+/* Device-side parameter commit: giga_ctx_set_param* + giga_ctx_commit_params for tensors that already live on the device.  `values[i]`
+ * = device pointer (fp32, 16-byte aligned, the reference's state-dict layout) of tensor `names[i]`; every operand layout of the
+ * inference kernels (fp32 blobs, fp16 hi/lo splits of the tensor-core convolutions and decoder, head constants) is written by kernels
+ * on `stream` -- bit-identical to the host packer -- and only conv_in's 3.6 KB of taps (kernel parameters of its kernel) are read back.
+ * GIGA-family models only (all encoder tensors + whole heads).  Synchronises the device (the blobs may be in use) and `stream`. */
+int giga_ctx_commit_device(giga_ctx *ctx, int n, const char *const *names, const float *const *values, void *stream);
+/* debug: copy a packed operand blob to the host (0 = encoder blob, 1 = fp32 head blob, 2 = head constants, 3..7 = streamed decoder
+ * weights per job type); returns the byte count (0 = not present) or a negative error */
+long giga_debug_blob(giga_ctx *ctx, int which, void *dst, long capacity);
+
 /* Native training step ---------------------------------------------------------------------------
  * Replaces the autograd graph of `_update` in scripts/train_giga.py:199-211 (net(x, pos, p_tsdf=pos_occ) ... loss.backward()): the
  * differentiable forward of conv_onet/models/__init__.py:42-67 and its backward (ATen/cuDNN conv3d / conv2d / conv_transpose2d

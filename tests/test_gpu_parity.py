@@ -600,3 +600,47 @@ def test_decoder_head_combinations(net, oracle_sd):
                     assert (out[i] - full[i]).abs().max().item() <= 2e-6, (mask, i)   # same arithmetic per chain (3-chain item vs single-chain job)
                 else:
                     assert out[i] is None
+
+
+@pytest.mark.parametrize("name", ["giga", "giga_aff", "giga_geo"])
+def test_device_side_commit_is_bit_identical_to_the_host_packer(oracle_sd, name):
+    """giga_ctx_commit_device (kernels pack every operand layout from the live device tensors) against giga_ctx_commit_params (host
+    packer): the packed blobs -- fp32 operands, fp16 hi/lo splits of the tensor-core convs and decoder, head constants, per-head scales --
+    and therefore the outputs are the same bits; a parameter update is picked up through the device path."""
+    import numpy as np
+    from giga_b200._lib import lib
+
+    def blobs(net):
+        eng = net._engine()
+        out = []
+        for which in range(8):
+            buf = np.zeros(8 << 20, np.uint8)
+            nb = lib.giga_debug_blob(eng.h, which, C.c_void_p(buf.ctypes.data), buf.nbytes)
+            assert nb >= 0
+            out.append(buf[:nb].copy())
+        return out
+
+    host = make_net(name, oracle_sd)
+    host._engine_raw().commit_mode = "host"
+    dev = make_net(name, oracle_sd)
+    bh, bd = blobs(host), blobs(dev)
+    assert host._engine_raw().commit_mode == "host" and dev._engine_raw().commit_mode == "auto"
+    for which, (a, b) in enumerate(zip(bh, bd)):
+        assert a.shape == b.shape and np.array_equal(a, b), f"blob {which} differs"
+    assert sum(len(a) for a in bh) > 4_000_000
+    x, p, pt = O.seeded_inputs(3, 130, seed=5)
+    with torch.no_grad():
+        args = (x.to(DEV), pt.to(DEV), pt.to(DEV)) if name == "giga_geo" else (x.to(DEV), p.to(DEV))
+        oh, od = host(*args), dev(*args)
+        oh, od = (oh,) if torch.is_tensor(oh) else oh, (od,) if torch.is_tensor(od) else od
+        for a, b in zip(oh, od):
+            assert torch.equal(a, b)
+        first = next(dev.parameters())
+        first.mul_(1.5)                                   # version bump -> re-commit through the device path
+        o2 = dev(*args)
+        o2 = (o2,) if torch.is_tensor(o2) else o2
+        assert not torch.equal(o2[0], od[0])
+        sd2 = {k: v.detach().cpu() for k, v in dev.state_dict().items()}
+        ref = (O.infer_geo(sd2, x, pt),) if name == "giga_geo" else O.forward(sd2, x, p)
+        for a, b in zip(o2, ref):
+            _close(a, b, name="device commit after update")
