@@ -231,6 +231,7 @@ struct giga_ctx {
     const float* val[kSlots] = {};
     float* grad[kSlots] = {};
     bool bound = false, table_dirty = true;
+    int fwd_impl = 1;             // training forward: 1 = tcgen05 encoder + decoder on device-packed operands (default), 0 = fp32 FMA pipe
     unsigned heads = 0;
     PackEntry* d_tab = nullptr;
     int n_tab = 0;
@@ -582,6 +583,50 @@ bool get(const giga_ctx* ctx, const std::string& name, long numel, const float**
   if (it == ctx->raw.end() || (long)it->second.size() != numel) return false;
   *out = it->second.data();
   return true;
+}
+
+// tensor-core U-Net on TALL pre-split activations (unet_tall.cuh), persistent kernels: d_tall[0] (pre) -> planes (conv_final fused into the
+// last layer), or -> d_tall["u1c2"] when keep_u1c2
+void unet_tall_forward(giga_ctx* ctx, int n_img, float* planes, bool keep_u1c2, cudaStream_t st) {
+    auto tb = [&](const char* nm) {
+      TallBuf t;
+      if (!strcmp(nm, "pre")) { t.p = ctx->d_tall[0]; t.ps = ctx->tall_ps[0]; return t; }
+      for (int i = 0; i < kNumActs; ++i)
+        if (!strcmp(kActs[i].name, nm)) { t.p = ctx->d_tall[1 + i]; t.ps = ctx->tall_ps[1 + i]; }
+      return t;
+    };
+    const TallBuf none;
+    const float* E = ctx->d_enc;
+    const EncLayout& L = ctx->el;
+    {
+      // tile-level dependency edges (dep_out -> dep_in): d0c1->d0c2, d1c1->d1c2, d2c1->d2c2->u0up->u0c1->u0c2->u1up->u1c1->u1c2;
+      // the edges through the max-pools are whole-grid waits
+      launch_persist<P_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st, 0, -1);
+      launch_persist<P_c40, P_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st, -1, 0, 0);
+      {
+        LaunchScope ls(ctx, "maxpool:p0", st);
+        launch_k(ctx, pool_tall_kernel<20, 4>, dim3(ceil_div(n_img * 4 * 400, 256)), dim3(256), 0, st, (const float*)tb("d0c2").p, tb("d0c2").ps,
+                 tb("p0").p, tb("p0").ps, n_img);
+      }
+      launch_persist<P_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st, 1, -1);
+      launch_persist<P_c20, P_d1c1>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st, -1, 1, 0);
+      {
+        LaunchScope ls(ctx, "maxpool:p1", st);
+        launch_k(ctx, pool_tall_kernel<10, 8>, dim3(ceil_div(n_img * 8 * 100, 256)), dim3(256), 0, st, (const float*)tb("d1c2").p, tb("d1c2").ps,
+                 tb("p1").p, tb("p1").ps, n_img);
+      }
+      launch_persist<P_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st, 2, -1);
+      launch_persist<P_d2c2, P_d2c1>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st, 3, 2, 0);
+      launch_persist<P_u0up, P_d2c2>(ctx, "convT:u0", n_img, tb("d2c2"), none, E + L.tc_up[0], E + L.up_b[0], tb("u0"), nullptr, st, 7, 3, 0);
+      launch_persist<P_u0c1, P_u0up>(ctx, "conv3x3:u0c1", n_img, tb("u0"), tb("d1c2"), E + L.tc_conv[6], E + L.bias[6], tb("u0c1"), nullptr, st, 4, 7);
+      launch_persist<P_c20, P_u0c1>(ctx, "conv3x3:u0c2", n_img, tb("u0c1"), none, E + L.tc_conv[7], E + L.bias[7], tb("u0c2"), nullptr, st, 5, 4, 0);
+      launch_persist<P_u1up, P_c20>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st, 8, 5, 0);
+      launch_persist<P_u1c1, P_u1up>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st, 6, 8);
+      if (keep_u1c2)   // the training step needs u1c2 itself (ReLU mask, conv_final's filter gradient): plain layer, conv_final runs separately
+        launch_persist<P_c40, P_u1c1>(ctx, "conv3x3:u1c2", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], tb("u1c2"), nullptr, st, -1, 6, 0);
+      else
+        launch_persist<P_u1c2, P_u1c1>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st, -1, 6, 0);
+    }
 }
 
 }  // namespace
@@ -1015,43 +1060,7 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
         *u0 = act(ctx, "u0"), *u0c1 = act(ctx, "u0c1"), *u0c2 = act(ctx, "u0c2"), *u1 = act(ctx, "u1"),
         *u1c1 = act(ctx, "u1c1"), *u1c2 = act(ctx, "u1c2");
   if (ctx->encoder_impl >= 1) {
-    // tensor-core U-Net on TALL pre-split activations (unet_tall.cuh), persistent kernels
-    auto tb = [&](const char* nm) {
-      TallBuf t;
-      if (!strcmp(nm, "pre")) { t.p = ctx->d_tall[0]; t.ps = ctx->tall_ps[0]; return t; }
-      for (int i = 0; i < kNumActs; ++i)
-        if (!strcmp(kActs[i].name, nm)) { t.p = ctx->d_tall[1 + i]; t.ps = ctx->tall_ps[1 + i]; }
-      return t;
-    };
-    const TallBuf none;
-    const float* E = ctx->d_enc;
-    const EncLayout& L = ctx->el;
-    {
-      // tile-level dependency edges (dep_out -> dep_in): d0c1->d0c2, d1c1->d1c2, d2c1->d2c2->u0up->u0c1->u0c2->u1up->u1c1->u1c2;
-      // the edges through the max-pools are whole-grid waits
-      launch_persist<P_c40>(ctx, "conv3x3:d0c1", n_img, tb("pre"), none, E + L.tc_conv[0], E + L.bias[0], tb("d0c1"), nullptr, st, 0, -1);
-      launch_persist<P_c40, P_c40>(ctx, "conv3x3:d0c2", n_img, tb("d0c1"), none, E + L.tc_conv[1], E + L.bias[1], tb("d0c2"), nullptr, st, -1, 0, 0);
-      {
-        LaunchScope ls(ctx, "maxpool:p0", st);
-        launch_k(ctx, pool_tall_kernel<20, 4>, dim3(ceil_div(n_img * 4 * 400, 256)), dim3(256), 0, st, (const float*)tb("d0c2").p, tb("d0c2").ps,
-                 tb("p0").p, tb("p0").ps, n_img);
-      }
-      launch_persist<P_d1c1>(ctx, "conv3x3:d1c1", n_img, tb("p0"), none, E + L.tc_conv[2], E + L.bias[2], tb("d1c1"), nullptr, st, 1, -1);
-      launch_persist<P_c20, P_d1c1>(ctx, "conv3x3:d1c2", n_img, tb("d1c1"), none, E + L.tc_conv[3], E + L.bias[3], tb("d1c2"), nullptr, st, -1, 1, 0);
-      {
-        LaunchScope ls(ctx, "maxpool:p1", st);
-        launch_k(ctx, pool_tall_kernel<10, 8>, dim3(ceil_div(n_img * 8 * 100, 256)), dim3(256), 0, st, (const float*)tb("d1c2").p, tb("d1c2").ps,
-                 tb("p1").p, tb("p1").ps, n_img);
-      }
-      launch_persist<P_d2c1>(ctx, "conv3x3:d2c1", n_img, tb("p1"), none, E + L.tc_conv[4], E + L.bias[4], tb("d2c1"), nullptr, st, 2, -1);
-      launch_persist<P_d2c2, P_d2c1>(ctx, "conv3x3:d2c2", n_img, tb("d2c1"), none, E + L.tc_conv[5], E + L.bias[5], tb("d2c2"), nullptr, st, 3, 2, 0);
-      launch_persist<P_u0up, P_d2c2>(ctx, "convT:u0", n_img, tb("d2c2"), none, E + L.tc_up[0], E + L.up_b[0], tb("u0"), nullptr, st, 7, 3, 0);
-      launch_persist<P_u0c1, P_u0up>(ctx, "conv3x3:u0c1", n_img, tb("u0"), tb("d1c2"), E + L.tc_conv[6], E + L.bias[6], tb("u0c1"), nullptr, st, 4, 7);
-      launch_persist<P_c20, P_u0c1>(ctx, "conv3x3:u0c2", n_img, tb("u0c1"), none, E + L.tc_conv[7], E + L.bias[7], tb("u0c2"), nullptr, st, 5, 4, 0);
-      launch_persist<P_u1up, P_c20>(ctx, "convT:u1", n_img, tb("u0c2"), none, E + L.tc_up[1], E + L.up_b[1], tb("u1"), nullptr, st, 8, 5, 0);
-      launch_persist<P_u1c1, P_u1up>(ctx, "conv3x3:u1c1", n_img, tb("u1"), tb("d0c2"), E + L.tc_conv[8], E + L.bias[8], tb("u1c1"), nullptr, st, 6, 8);
-      launch_persist<P_u1c2, P_u1c1>(ctx, "conv3x3:u1c2+final", n_img, tb("u1c1"), none, E + L.tc_conv[9], E + L.bias[9], none, planes, st, -1, 6, 0);
-    }
+    unet_tall_forward(ctx, n_img, planes, /*keep_u1c2=*/false, st);
     ctx->last_B = B;
     ctx->last_impl = ctx->encoder_impl;
     CU_TRY(cudaGetLastError());
@@ -1886,6 +1895,11 @@ int giga_ctx_set_option(giga_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "pdl")) {
     if (value != 0 && value != 1) return fail(GIGA_EINVAL, "pdl must be 0 or 1");
     ctx->pdl = value;
+    return GIGA_OK;
+  }
+  if (!strcmp(key, "train_forward_impl")) {
+    if (value < 0 || value > 1) return fail(GIGA_EINVAL, "train_forward_impl must be 0 (fp32 FMA pipe) or 1 (tcgen05 kernels on device-packed operands)");
+    ctx->tr.fwd_impl = value;
     return GIGA_OK;
   }
   if (!strcmp(key, "encoder_impl")) {

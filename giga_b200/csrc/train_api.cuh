@@ -224,31 +224,9 @@ TcPackEntry tc_entry(const float* src, float* dst_words) {
   return e;
 }
 
-}  // namespace
-
-extern "C" {
-
-int giga_ctx_commit_device(giga_ctx* ctx, int n, const char* const* names, const float* const* values, void* stream) {
-  if (!ctx || n <= 0 || !names || !values) return fail(GIGA_EINVAL, "giga_ctx_commit_device: bad argument");
-  if (int r = set_device(ctx)) return r;
+// blobs + tables of the device-side packer (pack_dev.cuh) for the bound tensors
+int ensure_tc_tables(giga_ctx* ctx) {
   auto& T = ctx->tr;
-  const float* val[giga_ctx::Train::kSlots] = {};
-  unsigned heads = 0;
-  if (int r = map_param_slots("giga_ctx_commit_device", n, names, values, nullptr, val, nullptr, &heads)) return r;
-  bool same = T.bound && heads == T.heads;
-  for (int s = 0; same && s < giga_ctx::Train::kSlots; ++s) same = val[s] == T.val[s];
-  if (!same) {
-    memcpy(T.val, val, sizeof val);
-    memset(T.grad, 0, sizeof T.grad);   // gradient buffers belong to a giga_train_bind of the same tensors
-    T.heads = heads;
-    T.bound = true;
-    T.table_dirty = T.tc_table_dirty = true;
-  }
-  if (int r = ensure_attrs(ctx)) return r;
-  // the packed blobs may still be read by kernels of this ctx on other streams (torch side streams, the pipelined host path)
-  CU_TRY(cudaDeviceSynchronize());
-  if (T.table_dirty)
-    if (int r = train_build_table(ctx)) return r;
   const EncLayout& L = ctx->el;
   float* E = ctx->d_enc;
   if (!ctx->d_hc) {
@@ -262,8 +240,8 @@ int giga_ctx_commit_device(giga_ctx* ctx, int n, const char* const* names, const
   for (int type = 0; type < 5; ++type) {
     const int nh = type == 0 ? 3 : 1;
     const unsigned need = type == 0 ? 7u : (1u << (type - 1));
-    if ((heads & need) != need) {
-      if (ctx->d_wblob[type]) { cudaFree(ctx->d_wblob[type]); ctx->d_wblob[type] = nullptr; }
+    if ((T.heads & need) != need) {
+      if (ctx->d_wblob[type]) { CU_TRY(cudaDeviceSynchronize()); cudaFree(ctx->d_wblob[type]); ctx->d_wblob[type] = nullptr; }
     } else if (!ctx->d_wblob[type]) {
       CU_TRY(cudaMalloc(&ctx->d_wblob[type], (size_t)5 * wd_block_bytes(nh)));
       CU_TRY(cudaMemset(ctx->d_wblob[type], 0, (size_t)5 * wd_block_bytes(nh)));
@@ -290,14 +268,20 @@ int giga_ctx_commit_device(giga_ctx* ctx, int n, const char* const* names, const
     tab.push_back(tc_entry<T_u1up>(T.val[24], E + L.tc_up[1]));
     TcPackEntry fin = {T.val[26], reinterpret_cast<uint16_t*>(E + L.tc_fin), 0, 0, 0, 0, 0, 0, 2, 0};
     tab.push_back(fin);
+    CU_TRY(cudaDeviceSynchronize());   // a packing kernel of an earlier commit may still read the table
     CU_TRY(cudaMemcpy(T.d_tctab, tab.data(), sizeof(TcPackEntry) * tab.size(), cudaMemcpyHostToDevice));
     T.n_tctab = (int)tab.size();
     T.tc_table_dirty = false;
   }
+  return GIGA_OK;
+}
+
+DecPackArgs make_dec_pack_args(giga_ctx* ctx) {
+  auto& T = ctx->tr;
   DecPackArgs A = {};
-  A.heads = heads;
+  A.heads = T.heads;
   for (int h = 0; h < 4; ++h) {
-    if (!(heads & (1u << h))) continue;
+    if (!(T.heads & (1u << h))) continue;
     const float* const* v = T.val + TS_HEAD0 + TS_HEAD * h;
     for (int i = 0; i < 5; ++i) {
       A.head[h].fcc_w[i] = v[2 + 6 * i]; A.head[h].fcc_b[i] = v[3 + 6 * i];
@@ -309,23 +293,59 @@ int giga_ctx_commit_device(giga_ctx* ctx, int n, const char* const* names, const
   A.hc = ctx->d_hc;
   A.dheads = ctx->d_heads;
   A.scale = T.d_hscale;
-  cudaStream_t st = (cudaStream_t)stream;
+  return A;
+}
+
+// all operand layouts from the live tensors: fp32 blobs (+ data-gradient weights, conv_in staging), tensor-core convs, decoder
+void launch_device_pack(giga_ctx* ctx, const DecPackArgs& A, cudaStream_t st) {
+  auto& T = ctx->tr;
   {
-    LaunchScope ls(ctx, "commit:pack_fp32", st);
+    LaunchScope ls(ctx, "pack:fp32", st);
     train_pack_kernel<<<dim3(T.n_tab, 4), 256, 0, st>>>(T.d_tab);
   }
   {
-    LaunchScope ls(ctx, "commit:pack_tc", st);
+    LaunchScope ls(ctx, "pack:tc_conv", st);
     pack_conv_tc_kernel<<<dim3(T.n_tctab, 8), 256, 0, st>>>(T.d_tctab);
   }
   {
-    LaunchScope ls(ctx, "commit:head_scale", st);
+    LaunchScope ls(ctx, "pack:head_scale", st);
     head_scale_kernel<<<4, 256, 0, st>>>(A);
   }
   {
-    LaunchScope ls(ctx, "commit:pack_decoder", st);
+    LaunchScope ls(ctx, "pack:decoder", st);
     pack_decoder_ws_kernel<<<dim3(5, 5), 256, 0, st>>>(A);
   }
+}
+
+}  // namespace
+
+extern "C" {
+
+int giga_ctx_commit_device(giga_ctx* ctx, int n, const char* const* names, const float* const* values, void* stream) {
+  if (!ctx || n <= 0 || !names || !values) return fail(GIGA_EINVAL, "giga_ctx_commit_device: bad argument");
+  if (int r = set_device(ctx)) return r;
+  auto& T = ctx->tr;
+  const float* val[giga_ctx::Train::kSlots] = {};
+  unsigned heads = 0;
+  if (int r = map_param_slots("giga_ctx_commit_device", n, names, values, nullptr, val, nullptr, &heads)) return r;
+  bool same = T.bound && heads == T.heads;
+  for (int s = 0; same && s < giga_ctx::Train::kSlots; ++s) same = val[s] == T.val[s];
+  if (!same) {
+    memcpy(T.val, val, sizeof val);
+    memset(T.grad, 0, sizeof T.grad);   // gradient buffers belong to a giga_train_bind of the same tensors
+    T.heads = heads;
+    T.bound = true;
+    T.table_dirty = T.tc_table_dirty = true;
+  }
+  if (int r = ensure_attrs(ctx)) return r;
+  // the packed blobs may still be read by kernels of this ctx on other streams (torch side streams, the pipelined host path)
+  CU_TRY(cudaDeviceSynchronize());
+  if (T.table_dirty)
+    if (int r = train_build_table(ctx)) return r;
+  if (int r = ensure_tc_tables(ctx)) return r;
+  DecPackArgs A = make_dec_pack_args(ctx);
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_device_pack(ctx, A, st);
   // conv_in's 27 x 32 taps are kernel parameters of the inference kernel (constant bank): 3.6 KB come back to the host
   {
     float cin[28 * 32];
@@ -399,7 +419,11 @@ int giga_train_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, 
   OrderScope order(ctx, st);
   T.fwd_valid = false;
   // ---- operands from the live parameters (device to device; nothing crosses the host) ----
-  {
+  const bool tc = T.fwd_impl == 1;
+  if (tc) {
+    if (int r = ensure_tc_tables(ctx)) return r;
+    launch_device_pack(ctx, make_dec_pack_args(ctx), st);
+  } else {
     LaunchScope ls(ctx, "train:pack", st);
     train_pack_kernel<<<dim3(T.n_tab, 4), 256, 0, st>>>(T.d_tab);
   }
@@ -426,9 +450,46 @@ int giga_train_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, 
     else
       xz_finish_tall_kernel<G><<<blocks, 256, 0, st>>>((const float*)ctx->d_xzpart, tall_pre, ps_pre, B, ctx->d_flags, (int)(9 * ctx->flags_stride + 16));
   }
+  ctx->work_slot = 0;
   {
     LaunchScope ls(ctx, "train:tall_to_nchw", st);
     tall_to_nchw_kernel<40, 4><<<ceil_div(n_img * 4 * G2, 256), 256, 0, st>>>(tall_pre, ctx->d_pre, ps_pre, n_img);
+  }
+  if (tc) {
+    // ---- tcgen05 U-Net (the inference kernels; the last layer unfused so that u1c2 exists), then every activation expanded to the NCHW fp32
+    //      form the backward kernels read (hi + lo * 2^-11 carries 22 significant bits), conv_final on the expanded u1c2 ----
+    unet_tall_forward(ctx, n_img, nullptr, /*keep_u1c2=*/true, st);
+    for (int i = 0; i < kNumActs; ++i) {
+      const int hw = kActs[i].hw, c8 = kActs[i].ch / 8;
+      const float* tsrc = ctx->d_tall[1 + i];
+      const long ps = ctx->tall_ps[1 + i];
+      const int blocks = ceil_div(n_img * c8 * hw * hw, 256);
+      LaunchScope ls(ctx, "train:tall_to_nchw", st);
+      if (hw == 40 && c8 == 4) tall_to_nchw_kernel<40, 4><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
+      else if (hw == 20 && c8 == 4) tall_to_nchw_kernel<20, 4><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
+      else if (hw == 20 && c8 == 8) tall_to_nchw_kernel<20, 8><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
+      else if (hw == 10 && c8 == 8) tall_to_nchw_kernel<10, 8><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
+      else tall_to_nchw_kernel<10, 16><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
+    }
+    {
+      LaunchScope ls(ctx, "train:conv_final", st);
+      conv1x1_nhwc_kernel<<<dim3(G2 / F_PIX, n_img), 256, 0, st>>>(act(ctx, "u1c2"), ctx->d_enc + ctx->el.fin_w, ctx->d_enc + ctx->el.fin_b, T.d_planes);
+    }
+    ctx->last_B = B;
+    ctx->last_impl = 0;   // d_act holds every activation in NCHW fp32 (giga_debug_copy reads them there)
+    // ---- heads: the warp-specialised tcgen05 decoder on the device-packed blobs, both point sets in one launch ----
+    if (grasp && geo) {
+      if (int r = launch_decode(ctx, T.d_planes, B, p, Ng, 7u, p_tsdf, No, 8u, qual, rot, width, occ, st)) return r;
+    } else if (grasp) {
+      if (int r = launch_decode(ctx, T.d_planes, B, p, Ng, 7u, nullptr, 0, 0u, qual, rot, width, nullptr, st)) return r;
+    } else {
+      if (int r = launch_decode(ctx, T.d_planes, B, p_tsdf, No, 8u, nullptr, 0, 0u, nullptr, nullptr, nullptr, occ, st)) return r;
+    }
+    CU_TRY(cudaGetLastError());
+    T.x = tsdf; T.p = grasp ? p : nullptr; T.pt = geo ? p_tsdf : nullptr;
+    T.B = B; T.Ng = grasp ? Ng : 0; T.No = geo ? No : 0; T.detach = detach_tsdf ? 1 : 0;
+    T.fwd_valid = true;
+    return GIGA_OK;
   }
   float *d0c1 = act(ctx, "d0c1"), *d0c2 = act(ctx, "d0c2"), *p0 = act(ctx, "p0"), *d1c1 = act(ctx, "d1c1"), *d1c2 = act(ctx, "d1c2"),
         *p1 = act(ctx, "p1"), *d2c1 = act(ctx, "d2c1"), *d2c2 = act(ctx, "d2c2"), *u0 = act(ctx, "u0"), *u0c1 = act(ctx, "u0c1"),

@@ -74,10 +74,12 @@ def _gpu_autograd_reference(sd, x, p, pt, y, name="giga"):
     return {k: v.grad.detach().cpu() for k, v in net2.named_parameters()}
 
 
-@pytest.mark.parametrize("B,No", [(4, 128), (9, 300)])
-def test_native_forward_and_every_parameter_gradient(oracle_sd, B, No):
-    """B = 4 runs conv_in's fine tiling, B = 9 the 5-row tiling; No = 300 has a ragged last point tile"""
+@pytest.mark.parametrize("B,No,fwd_impl", [(4, 128, 1), (9, 300, 1), (4, 128, 0), (9, 300, 0)])
+def test_native_forward_and_every_parameter_gradient(oracle_sd, B, No, fwd_impl):
+    """B = 4 runs conv_in's fine tiling, B = 9 the 5-row tiling; No = 300 has a ragged last point tile; fwd_impl: the training forward on
+    the tcgen05 kernels (device-packed operands, default) or on the fp32 FMA-pipe kernels"""
     net = make_net("giga", oracle_sd, frozen=False)
+    net._engine_raw().set_option("train_forward_impl", fwd_impl)
     x, p, pt, y = _batch(B, No, seed=50 + B)
     out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
     assert all(o.requires_grad for o in out)                    # an ordinary differentiable module: no opt-in
