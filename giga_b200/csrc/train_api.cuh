@@ -542,12 +542,13 @@ int giga_train_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, 
   return GIGA_OK;
 }
 
-int giga_train_backward(giga_ctx* ctx, const float* g_qual, const float* g_rot, const float* g_width, const float* g_occ, void* stream) {
+int giga_train_backward(giga_ctx* ctx, const float* g_qual, const float* g_rot, const float* g_width, const float* g_occ, float* g_p, void* stream) {
   if (!ctx) return fail(GIGA_EINVAL, "giga_train_backward: ctx is null");
   auto& T = ctx->tr;
   if (!T.fwd_valid) return fail(GIGA_ESTATE, "giga_train_backward: no forward to differentiate (giga_train_forward must precede; one backward per forward)");
   if ((g_qual || g_rot || g_width) && !T.p) return fail(GIGA_EINVAL, "giga_train_backward: grasp-head gradients without grasp points in the forward");
   if (g_occ && !T.pt) return fail(GIGA_EINVAL, "giga_train_backward: TSDF-head gradient without p_tsdf in the forward");
+  if (g_p && !T.p) return fail(GIGA_EINVAL, "giga_train_backward: position gradient without grasp points in the forward");
   if (g_rot && (reinterpret_cast<uintptr_t>(g_rot) & 15)) return fail(GIGA_EINVAL, "giga_train_backward: g_rot must be 16-byte aligned");
   for (int s = 0; s < giga_ctx::Train::kSlots; ++s)
     if (T.val[s] && !T.grad[s]) return fail(GIGA_ESTATE, "giga_train_backward: '" + train_slot_name(s) + "' has no gradient buffer bound");
@@ -560,15 +561,24 @@ int giga_train_backward(giga_ctx* ctx, const float* g_qual, const float* g_rot, 
   bool enc_grad = false;
   for (int h = 0; h < 4; ++h) enc_grad |= gouts[h] && !(h == 3 && T.detach);
   if (enc_grad) CU_TRY(cudaMemsetAsync(T.d_gplanes, 0, sizeof(float) * 3 * (size_t)B * C * G2, st));
-  // ---- heads: one launch per point set (the grasp heads with a gradient share a launch, blockIdx.z = head) ----
-  for (int set = 0; set < 2; ++set) {
+  // ---- heads: ONE launch, blockIdx.z = (head with a gradient), each at its own point set ----
+  {
     DecBwdArgs A = {};
-    int nj = 0;
-    for (int h = set == 0 ? 0 : 3; h < (set == 0 ? 3 : 4); ++h) {
+    int nj = 0, max_tiles = 0;
+    size_t need = 0;
+    for (int h = 0; h < 4; ++h) {
       if (!gouts[h]) continue;
       DecBwdJob& J = A.job[nj++];
       J.head = h;
+      J.pts = h == 3 ? T.pt : T.p;
+      J.N = h == 3 ? T.No : T.Ng;
+      J.tiles = ceil_div(J.N, DB_PTS);
       J.gout = gouts[h];
+      J.gplanes = (h == 3 && T.detach) ? nullptr : T.d_gplanes;
+      J.gpts = h == 3 ? nullptr : g_p;
+      J.save_off = (long)need;
+      need += (size_t)B * J.tiles * DB_SAVE;
+      max_tiles = std::max(max_tiles, J.tiles);
       float* const* g = T.grad + TS_HEAD0 + TS_HEAD * h;
       J.GR.fcp_w = g[0]; J.GR.fcp_b = g[1];
       for (int i = 0; i < 5; ++i) {
@@ -578,22 +588,18 @@ int giga_train_backward(giga_ctx* ctx, const float* g_qual, const float* g_rot, 
       }
       J.GR.out_w = g[32]; J.GR.out_b = g[33];
     }
-    if (!nj) continue;
-    const float* pts = set ? T.pt : T.p;
-    const int N = set ? T.No : T.Ng;
-    const int tiles = ceil_div(N, DB_PTS);
-    const size_t need = (size_t)nj * B * tiles * DB_SAVE;
-    if (need > T.save_cap) {
-      CU_TRY(cudaStreamSynchronize(st));
-      if (T.d_save) cudaFree(T.d_save);
-      T.d_save = nullptr;
-      T.save_cap = 0;
-      CU_TRY(cudaMalloc(&T.d_save, sizeof(float) * need));
-      T.save_cap = need;
+    if (nj) {
+      if (need > T.save_cap) {
+        CU_TRY(cudaStreamSynchronize(st));
+        if (T.d_save) cudaFree(T.d_save);
+        T.d_save = nullptr;
+        T.save_cap = 0;
+        CU_TRY(cudaMalloc(&T.d_save, sizeof(float) * need));
+        T.save_cap = need;
+      }
+      LaunchScope ls(ctx, "train:decode_bwd", st);
+      decode_points_bwd_kernel<<<dim3(max_tiles, B, nj), DB_PTS, DB_SMEM_BYTES, st>>>(T.d_planes, T.d_heads, B, A, T.d_save);
     }
-    LaunchScope ls(ctx, set ? "train:decode_bwd:tsdf" : "train:decode_bwd:grasp", st);
-    decode_points_bwd_kernel<<<dim3(tiles, B, nj), DB_PTS, DB_SMEM_BYTES, st>>>(T.d_planes, pts, T.d_heads, B, N, A, T.d_save,
-                                                                               (set && T.detach) ? nullptr : T.d_gplanes);
   }
   CU_TRY(cudaGetLastError());
   if (!enc_grad) return GIGA_OK;

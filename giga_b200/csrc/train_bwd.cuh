@@ -196,21 +196,28 @@ __device__ __forceinline__ void warp_gather_skew(const float* __restrict__ plane
 }
 
 struct DecBwdJob {
-  int head;
+  int head, N, tiles;
+  const float* pts;    // [B][N][3]
   const float* gout;   // gradient of the loss w.r.t. this head's output: [B][N] or [B][N][4] (rot)
+  float* gplanes;      // [3][B][40][40][32] (+=), or null (detached features)
+  float* gpts;         // [B][N][3] (+=) gradient w.r.t. the query positions (grad_refine), or null
+  long save_off;       // this job's scratch: [B * tiles][DB_SAVE]
   HeadGrads GR;
 };
-struct DecBwdArgs { DecBwdJob job[3]; };   // the heads evaluated at one point set: blockIdx.z picks the job
+struct DecBwdArgs { DecBwdJob job[4]; };   // every head with a gradient, at its own point set: blockIdx.z picks the job (one launch: the
+                                           // latency-bound single-point grasp tiles run beside the TSDF head's thousands of tiles)
 
+// grid (max tiles, B, jobs), block 128
 __global__ void __launch_bounds__(DB_PTS, 2)
 decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][32]
-                         const float* __restrict__ pts,      // [B][N][3]
                          const float* __restrict__ hw,       // [4][DW_HEAD] packed head parameters (input-major)
-                         int B, int N, const __grid_constant__ DecBwdArgs A,
-                         float* __restrict__ save,           // [jobs][B * tiles][DB_SAVE]
-                         float* __restrict__ gplanes) {      // [3][B][40][40][32] (+=), or null (detached features)
-  const int head = A.job[blockIdx.z].head;
+                         int B, const __grid_constant__ DecBwdArgs A, float* __restrict__ save) {
+  if ((int)blockIdx.x >= A.job[blockIdx.z].tiles) return;
+  const int head = A.job[blockIdx.z].head, N = A.job[blockIdx.z].N;
+  const float* __restrict__ pts = A.job[blockIdx.z].pts;
   const float* __restrict__ gout = A.job[blockIdx.z].gout;
+  float* __restrict__ gplanes = A.job[blockIdx.z].gplanes;
+  float* __restrict__ gpts = A.job[blockIdx.z].gpts;
   const HeadGrads& GR = A.job[blockIdx.z].GR;
   extern __shared__ __align__(16) float smem[];
   float* feat = smem;                     // [96][DB_ST]
@@ -228,7 +235,7 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
   const float* pp = pts + ((size_t)b * N + nc) * 3;
   const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
   const float* W = hw + (size_t)head * DW_HEAD;
-  float* sv = save + (((size_t)blockIdx.z * B + b) * gridDim.x + blockIdx.x) * DB_SAVE + tid;   // [6][32][128], this thread's column
+  float* sv = save + A.job[blockIdx.z].save_off + ((size_t)b * A.job[blockIdx.z].tiles + blockIdx.x) * DB_SAVE + tid;   // [6][32][128], this thread's column
 
   // ---- forward recompute (decode_points_kernel's arithmetic), keeping the hidden state that enters each ResNet block ----
   float h[32];
@@ -396,7 +403,16 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
     if (c < 3) red_add(GR.fcp_w + j * 3 + c, acc);
     else red_add(GR.fcp_b + j, acc);
   }
-  if (!gplanes) return;
+  float dp[3] = {0.f, 0.f, 0.f};
+  if (gpts) {   // d h0 / d p = Wp (decoder.py:163, fc_p)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      dp[0] = fmaf(__ldg(W + DW_FCP + j), g[j], dp[0]);
+      dp[1] = fmaf(__ldg(W + DW_FCP + 32 + j), g[j], dp[1]);
+      dp[2] = fmaf(__ldg(W + DW_FCP + 64 + j), g[j], dp[2]);
+    }
+  }
+  if (!gplanes && !gpts) return;
 
   // ---- feature gradient: d feat[k] = sum_blk sum_j Wc_blk[j][k] g_blk[j], scattered bilinearly into the plane gradients ----
   float gf[96];
@@ -420,6 +436,51 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
     }
   }
   if (!valid) return;
+  if (gpts) {
+    // grid_sampler_2d_backward w.r.t. the grid (bilinear, border, align_corners = True) chained through decoder.py:119-121 (g = 2 t - 1) and
+    // normalize_coordinate (common.py:253-260: the one-sided clamps are constants).  Plane axes: xz (u = x, v = z), xy (x, y), yz (y, z).
+    const float pv[3] = {px, py, pz};
+    const int au[3] = {0, 0, 1}, av[3] = {2, 1, 2};
+    float pix[3], dpix[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float t = __fdiv_rn(pv[a], 1.00001f) + 0.5f, dt = 1.f / 1.00001f;
+      if (t >= 1.f) { t = 0.99999f; dt = 0.f; }
+      if (t < 0.f) { t = 0.f; dt = 0.f; }
+      float ix = ((2.0f * t - 1.0f) + 1.f) * 19.5f, d = 39.f * dt;
+      if (ix <= 0.f) { ix = 0.f; d = 0.f; } else if (ix >= 39.f) { ix = 39.f; d = 0.f; }   // clip_coordinates_set_grad
+      pix[a] = ix; dpix[a] = d;
+    }
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const float ix = pix[au[pl]], iy = pix[av[pl]];
+      const float x0f = floorf(ix), y0f = floorf(iy);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const float tx = ix - x0f, ty = iy - y0f, sx = 1.f - tx, sy = 1.f - ty;
+      const bool xin = x0 + 1 < G, yin = y0 + 1 < G;            // out-of-range corners read as zero (ATen safe_get)
+      const float* pb = planes + ((size_t)pl * B + b) * (G2 * C);
+      const float* nw = pb + (y0 * G + x0) * C;
+      float gix = 0.f, giy = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 tnw = __ldg(reinterpret_cast<const float4*>(nw) + c4);
+        const float4 tne = xin ? __ldg(reinterpret_cast<const float4*>(nw + C) + c4) : z4;
+        const float4 tsw = yin ? __ldg(reinterpret_cast<const float4*>(nw + G * C) + c4) : z4;
+        const float4 tse = (xin && yin) ? __ldg(reinterpret_cast<const float4*>(nw + G * C + C) + c4) : z4;
+        const float* gq = gf + pl * 32 + 4 * c4;
+        gix += gq[0] * ((tne.x - tnw.x) * sy + (tse.x - tsw.x) * ty) + gq[1] * ((tne.y - tnw.y) * sy + (tse.y - tsw.y) * ty) +
+               gq[2] * ((tne.z - tnw.z) * sy + (tse.z - tsw.z) * ty) + gq[3] * ((tne.w - tnw.w) * sy + (tse.w - tsw.w) * ty);
+        giy += gq[0] * ((tsw.x - tnw.x) * sx + (tse.x - tne.x) * tx) + gq[1] * ((tsw.y - tnw.y) * sx + (tse.y - tne.y) * tx) +
+               gq[2] * ((tsw.z - tnw.z) * sx + (tse.z - tne.z) * tx) + gq[3] * ((tsw.w - tnw.w) * sx + (tse.w - tne.w) * tx);
+      }
+      dp[au[pl]] = fmaf(gix, dpix[au[pl]], dp[au[pl]]);
+      dp[av[pl]] = fmaf(giy, dpix[av[pl]], dp[av[pl]]);
+    }
+    float* gp = gpts + ((size_t)b * N + n) * 3;
+    red_add(gp, dp[0]); red_add(gp + 1, dp[1]); red_add(gp + 2, dp[2]);
+  }
+  if (!gplanes) return;
   TexInfo ti;
   point_taps(pp, ti);
 #pragma unroll

@@ -272,12 +272,11 @@ class _GigaBase(nn.Module):
         return eng
 
     def _train_active(self, *inputs) -> bool:
-        """autograd semantics of an ordinary nn.Module: with gradient mode on and parameters that require gradients the outputs are
-        differentiable -- through the native training step (csrc/train_bwd.cuh).  Query positions that require a gradient
-        (grad_refine) go through the bridge."""
-        if not torch.is_grad_enabled() or any(t is not None and t.requires_grad for t in inputs):
+        """autograd semantics of an ordinary nn.Module: with gradient mode on and parameters (or query positions) that require
+        gradients the outputs are differentiable -- through the native training step (csrc/train_bwd.cuh)."""
+        if not torch.is_grad_enabled():
             return False
-        return any(p.requires_grad for p in self.parameters())
+        return any(t is not None and t.requires_grad for t in inputs) or any(p.requires_grad for p in self.parameters())
 
     def to(self, device):
         """models/__init__.py:126-134"""
@@ -312,19 +311,6 @@ class _GigaBase(nn.Module):
     def __setstate__(self, state):
         super().__setstate__(state)
         self._bind_heads()
-
-    # -- training bridge (opt-in; see giga_b200/training.py) --------------------------------
-    def enable_training_bridge(self, enabled: bool = True):
-        """Make `forward()` differentiable w.r.t. the parameters: forward values still come from the CUDA
-        library, gradients from a PyTorch-autograd recompute on the GPU (library kernels) until the native
-        backward kernels exist.  Off by default: without it outputs carry no graph and backward() raises."""
-        self.__dict__["_train_bridge"] = bool(enabled)
-        return self
-
-    def _bridge_active(self, *inputs) -> bool:
-        if not (bool(self.__dict__.get("_train_bridge")) and torch.is_grad_enabled()):
-            return False
-        return any(p.requires_grad for p in self.parameters()) or any(t is not None and t.requires_grad for t in inputs)
 
     @property
     def gpu_launches(self) -> int:
@@ -556,11 +542,6 @@ class ConvolutionalOccupancyNetwork(_GigaBase):
 
     def forward(self, inputs, p, p_tsdf=None, sample=True, **kwargs):
         """models/__init__.py:42-67"""
-        if self._bridge_active(p):
-            from .training import bridged_forward
-            eng = self._engine()
-            return bridged_forward(self, _prep(inputs, eng.device), _prep(p, eng.device),
-                                   _prep(p_tsdf, eng.device) if p_tsdf is not None else None)
         if self._train_active(p, p_tsdf):
             from .training import native_forward
             return native_forward(self, inputs, p, p_tsdf)
@@ -583,32 +564,26 @@ class ConvolutionalOccupancyNetwork(_GigaBase):
                            "same failure as the reference for GIGA configs")
 
     def grad_refine(self, x, pos, bound_value=0.0125, lr=1e-6, num_step=1):
-        """models/__init__.py:136-164: SGD on the query positions to raise the predicted quality (not called by any
-        shipped script).  Forward values come from the CUDA library; d(qual)/d(pos) comes from the training bridge's
-        PyTorch recompute on the GPU (giga_b200/training.py) until the native backward kernels exist."""
-        was = bool(self.__dict__.get("_train_bridge"))
-        self.enable_training_bridge(True)
-        try:
-            pos_tmp = pos.clone()
-            l_bound = pos - bound_value
-            u_bound = pos + bound_value
-            pos_tmp.requires_grad = True
-            optimizer = torch.optim.SGD([pos_tmp], lr=lr)
-            self.eval()
-            with torch.enable_grad():
-                for _ in range(num_step):
-                    optimizer.zero_grad()
-                    qual_out, _, _ = self.forward(x, pos_tmp)
-                    loss = -qual_out.sum()
-                    loss.backward()
-                    optimizer.step()
-            for prm in self.parameters():   # the reference leaves parameter gradients behind as well; drop ours
-                prm.grad = None
-            with torch.no_grad():
-                pos_tmp = torch.maximum(torch.minimum(pos_tmp, u_bound), l_bound)
-                qual_out, rot_out, width_out = self.forward(x, pos_tmp)
-        finally:
-            self.enable_training_bridge(was)
+        """models/__init__.py:136-164: SGD on the query positions to raise the predicted quality (not called by any shipped script).
+        d(qual)/d(pos) comes from the native backward kernels (fc_p and grid_sampler's grid gradient, csrc/train_bwd.cuh)."""
+        pos_tmp = pos.clone()
+        l_bound = pos - bound_value
+        u_bound = pos + bound_value
+        pos_tmp.requires_grad = True
+        optimizer = torch.optim.SGD([pos_tmp], lr=lr)
+        self.eval()
+        with torch.enable_grad():
+            for _ in range(num_step):
+                optimizer.zero_grad()
+                qual_out, _, _ = self.forward(x, pos_tmp)
+                loss = -qual_out.sum()
+                loss.backward()
+                optimizer.step()
+        for prm in self.parameters():   # the reference leaves parameter gradients behind as well; drop ours
+            prm.grad = None
+        with torch.no_grad():
+            pos_tmp = torch.maximum(torch.minimum(pos_tmp, u_bound), l_bound)
+            qual_out, rot_out, width_out = self.forward(x, pos_tmp)
         return qual_out, pos_tmp, rot_out, width_out
 
 
@@ -629,11 +604,6 @@ class ConvolutionalOccupancyNetworkGeometry(_GigaBase):
 
     def forward(self, inputs, p, p_tsdf, sample=True, **kwargs):
         """models/__init__.py:179-195"""
-        if self._bridge_active():
-            from .training import bridged_forward
-            eng = self._engine()
-            pt = _prep(p_tsdf, eng.device)
-            return bridged_forward(self, _prep(inputs, eng.device), pt, pt)[0]
         if self._train_active(p_tsdf):
             from .training import native_forward
             return native_forward(self, inputs, None, p_tsdf)[0]

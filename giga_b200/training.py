@@ -1,5 +1,4 @@
-"""Training on the library's own kernels: the native training step, the fused loss / flat Adam tail, the gradient exchange -- and the
-round-1 recompute bridge, kept only for gradients with respect to query positions.
+"""Training on the library's own kernels: the native training step, the fused loss / flat Adam tail, the gradient exchange.
 
   * `native_forward` / `_NativeStep` (csrc/train_bwd.cuh, giga_train_forward / giga_train_backward): what `net(...)` runs when gradient
     mode is on and parameters require gradients -- replaces the autograd graph of scripts/train_giga.py:199-211 (`_update`).  Forward on
@@ -10,9 +9,8 @@ round-1 recompute bridge, kept only for gradients with respect to query position
     constructor for the arguments train_giga.py uses (:67): parameters, gradients and moments in four flat buffers, ONE launch per step
     (giga_adam_step); `Adam.allreduce_gradients()` = one in-place NCCL all-reduce of the flat 581,863-element gradient buffer
     (SURVEY.md section 8e), `allreduce_gradients(params)` the same for a plain torch optimizer.
-  * `bridged_forward` / `_Bridge` (opt-in, `net.enable_training_bridge()`): forward by the CUDA library, backward = PyTorch autograd
-    recompute on the GPU.  Used by `grad_refine` (gradients w.r.t. the query positions) and by the tests as a second
-    gradient reference; never on the training path, never on the CPU.
+  * gradients with respect to the grasp query positions (`grad_refine`, models/__init__.py:136-164) come from the same backward kernels
+    (fc_p plus grid_sampler's grid gradient).  There is no PyTorch / ATen compute anywhere in this package.
 """
 from __future__ import annotations
 
@@ -21,128 +19,9 @@ from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 from . import _lib
 from ._lib import check, lib
-
-PLANES = ("xz", "xy", "yz")
-_AX = {"xz": (0, 2), "xy": (0, 1), "yz": (1, 2)}
-
-
-# ------------------------------------------------------------------------------------------------------
-# the model function in differentiable PyTorch ops (GPU), parameterised by a name -> tensor mapping
-# ------------------------------------------------------------------------------------------------------
-def _unet(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
-    g = lambda n: sd["encoder.unet." + n]
-    enc = []
-    for i in range(3):
-        x = F.relu(F.conv2d(x, g(f"down_convs.{i}.conv1.weight"), g(f"down_convs.{i}.conv1.bias"), padding=1))
-        x = F.relu(F.conv2d(x, g(f"down_convs.{i}.conv2.weight"), g(f"down_convs.{i}.conv2.bias"), padding=1))
-        enc.append(x)
-        if i < 2:
-            x = F.max_pool2d(x, 2, 2)
-    for i in range(2):
-        up = F.conv_transpose2d(x, g(f"up_convs.{i}.upconv.weight"), g(f"up_convs.{i}.upconv.bias"), stride=2)
-        x = torch.cat((up, enc[-(i + 2)]), 1)
-        x = F.relu(F.conv2d(x, g(f"up_convs.{i}.conv1.weight"), g(f"up_convs.{i}.conv1.bias"), padding=1))
-        x = F.relu(F.conv2d(x, g(f"up_convs.{i}.conv2.weight"), g(f"up_convs.{i}.conv2.bias"), padding=1))
-    return F.conv2d(x, g("conv_final.weight"), g("conv_final.bias"))
-
-
-def _conv_in(x, w, b):
-    """Conv3d(1, 32, 3, padding=1) as 27 shifted views x one matmul.  Same arithmetic as F.conv3d; cuDNN's weight-gradient kernel for a
-    single input channel (wgrad2d_grouped_direct) took 37 ms per step at batch 64 -- 58 % of the whole training step -- while this
-    form differentiates into a [32 x 27] <- [32 x B*64000] x [B*64000 x 27] matmul."""
-    B = x.shape[0]
-    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
-    cols = torch.stack([xp[:, dx:dx + 40, dy:dy + 40, dz:dz + 40] for dx in range(3) for dy in range(3) for dz in range(3)], 1)   # [B,27,40,40,40]
-    f = torch.matmul(w.reshape(32, 27), cols.reshape(B, 27, -1)) + b.view(1, 32, 1)
-    return f.view(B, 32, 40, 40, 40)
-
-
-def _encode(sd, x):
-    f = F.relu(_conv_in(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"]))  # [b,c,ix,iy,iz]
-    # 40^3 voxels onto 40^2 cells: the scatter_mean is the mean along the perpendicular axis (SURVEY.md 8a-a4)
-    pre = {"xz": f.mean(3).transpose(2, 3), "xy": f.mean(4).transpose(2, 3), "yz": f.mean(2).transpose(2, 3)}
-    return {k: _unet(sd, v) for k, v in pre.items()}
-
-
-def _norm_axis(v):
-    t = v / 1.00001 + 0.5
-    t = torch.where(t >= 1, torch.full_like(t, 1 - 10e-6), t)
-    return torch.where(t < 0, torch.zeros_like(t), t)
-
-
-def _features(p, planes):
-    out = []
-    for k in PLANES:
-        a0, a1 = _AX[k]
-        uv = torch.stack((_norm_axis(p[..., a0]), _norm_axis(p[..., a1])), -1)
-        grid = (2.0 * uv - 1.0)[:, :, None]
-        out.append(F.grid_sample(planes[k], grid, padding_mode="border", align_corners=True, mode="bilinear").squeeze(-1))
-    return torch.cat(out, 1).transpose(1, 2)
-
-
-def _head(sd, name, p, c):
-    pre = f"decoder_{name}."
-    net = F.linear(p, sd[pre + "fc_p.weight"], sd[pre + "fc_p.bias"])
-    for i in range(5):
-        net = net + F.linear(c, sd[pre + f"fc_c.{i}.weight"], sd[pre + f"fc_c.{i}.bias"])
-        h = F.linear(F.relu(net), sd[pre + f"blocks.{i}.fc_0.weight"], sd[pre + f"blocks.{i}.fc_0.bias"])
-        net = net + F.linear(F.relu(h), sd[pre + f"blocks.{i}.fc_1.weight"], sd[pre + f"blocks.{i}.fc_1.bias"])
-    return F.linear(F.relu(net), sd[pre + "fc_out.weight"], sd[pre + "fc_out.bias"]).squeeze(-1)
-
-
-def _forward_torch(sd, x, p, p_tsdf, detach_tsdf: bool, has_grasp: bool):
-    planes = _encode(sd, x)
-    outs = []
-    if has_grasp:
-        c = _features(p, planes)
-        outs += [torch.sigmoid(_head(sd, "qual", p, c)), F.normalize(_head(sd, "rot", p, c), dim=2), _head(sd, "width", p, c)]
-    if p_tsdf is not None:
-        pl = {k: v.detach() for k, v in planes.items()} if detach_tsdf else planes
-        outs.append(_head(sd, "tsdf", p_tsdf, _features(p_tsdf, pl)))
-    return tuple(outs)
-
-
-class _Bridge(torch.autograd.Function):
-    """forward: native CUDA kernels; backward: autograd through `_forward_torch` (recompute)."""
-
-    @staticmethod
-    def forward(ctx, net, x, p, p_tsdf, names, *params):
-        with torch.no_grad():
-            outs = net._forward_native(x, p, p_tsdf)
-        ctx.net, ctx.names, ctx.has_tsdf = net, names, p_tsdf is not None
-        ctx.p_grad = bool(p.requires_grad)
-        ctx.save_for_backward(x, p, p_tsdf if p_tsdf is not None else x.new_empty(0), *params)
-        return tuple(outs)
-
-    @staticmethod
-    def backward(ctx, *grads):
-        x, p, pt, *params = ctx.saved_tensors
-        leaves = [t.detach().requires_grad_(True) for t in params]
-        sd = dict(zip(ctx.names, leaves))
-        # the recompute runs under the caller's torch.backends flags, exactly like the reference's own training step would
-        # (PyTorch's default lets cuDNN use TF32 for convolutions; set torch.backends.cudnn.allow_tf32 = False for fp32 gradients)
-        return _Bridge._backward_impl(ctx, leaves, sd, x, p, pt, grads)
-
-    @staticmethod
-    def _backward_impl(ctx, leaves, sd, x, p, pt, grads):
-        with torch.enable_grad():
-            p_leaf = p.detach().requires_grad_(True) if ctx.p_grad else p      # grad_refine differentiates w.r.t. the query positions
-            outs = _forward_torch(sd, x, p_leaf, pt if ctx.has_tsdf else None, getattr(ctx.net, "detach_tsdf", False), hasattr(ctx.net, "decoder_qual"))
-            pairs = [(o, g) for o, g in zip(outs, grads) if g is not None]
-            wrt = list(leaves) + ([p_leaf] if ctx.p_grad else [])
-            gp = torch.autograd.grad([o for o, _ in pairs], wrt, [g for _, g in pairs], allow_unused=True)
-        gpos = gp[-1] if ctx.p_grad else None
-        return (None, None, gpos, None, None) + tuple(gp[:len(leaves)])
-
-
-def bridged_forward(net, x, p, p_tsdf):
-    named = [(k, v) for k, v in net.named_parameters()]
-    return _Bridge.apply(net, x, p, p_tsdf, [k for k, _ in named], *[v for _, v in named])
-
 
 # ------------------------------------------------------------------------------------------------------
 # the native training step (csrc/train_bwd.cuh): differentiable forward + hand-written backward kernels
@@ -171,6 +50,9 @@ class _NativeStep(torch.autograd.Function):
                 raise _lib.GigaError(f"{what} must be (B,N,3) with B={B}, got {tuple(t.shape)}")
             return t, t.shape[1]
 
+        ctx.p_grad = bool(p is not None and p.requires_grad)
+        if p_tsdf is not None and p_tsdf.requires_grad:
+            raise _lib.GigaError("gradients with respect to p_tsdf are not provided (no caller of the reference asks for them)")
         p, Ng = pts(p, "points")
         p_tsdf, No = pts(p_tsdf, "p_tsdf")
         if p_tsdf is not None and not hasattr(net, "decoder_tsdf"):
@@ -230,11 +112,13 @@ class _NativeStep(torch.autograd.Function):
             g = next(it) if present else None
             gs.append(g.to(device=dev, dtype=torch.float32).contiguous() if g is not None else None)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        check(lib.giga_train_backward(eng.h, _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), st), "giga_train_backward")
+        gp = torch.zeros_like(ctx.keep[1]) if ctx.p_grad else None
+        check(lib.giga_train_backward(eng.h, _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), _ptr(gp), st), "giga_train_backward")
         eng.__dict__["_train_token"] += 1      # consumed
+        head = (None, None, gp, None, None)
         if ctx.direct:
-            return (None,) * 5 + (None,) * len(ctx.grads)
-        return (None,) * 5 + tuple(g if rg else None for g, rg in zip(ctx.grads, ctx.params_rg))
+            return head + (None,) * len(ctx.grads)
+        return head + tuple(g if rg else None for g, rg in zip(ctx.grads, ctx.params_rg))
 
 
 def native_forward(net, x, p, p_tsdf):

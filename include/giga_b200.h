@@ -229,12 +229,14 @@ long giga_debug_blob(giga_ctx *ctx, int which, void *dst, long capacity);
  *   the `giga_detach` variant (models/__init__.py:61-62: the TSDF head's features carry no gradient to the encoder).
  * giga_train_backward: g_* = gradients of the loss w.r.t. the four outputs of the LAST giga_train_forward ([B][Ng], [B][Ng][4],
  *   [B][Ng], [B][No]; NULL = that output does not contribute); adds the parameter gradients into the bound buffers.  tsdf / p /
- *   p_tsdf of the forward must still be alive.  One backward per forward.  Weight-gradient sums use floating-point atomics (run-to-run
+ *   p_tsdf of the forward must still be alive.  One backward per forward.  g_p (optional, [B][Ng][3], accumulated +=) receives the
+ *   gradient w.r.t. the grasp query positions (`grad_refine`, models/__init__.py:136-164: fc_p plus grid_sampler's grid gradient).  Weight-gradient sums use floating-point atomics (run-to-run
  *   differences at the 1e-6 relative level, as PyTorch's default cuDNN algorithms). */
 int giga_train_bind(giga_ctx *ctx, int n, const char *const *names, const float *const *values, float *const *grads);
 int giga_train_forward(giga_ctx *ctx, const float *tsdf, int B, const float *p, int Ng, const float *p_tsdf, int No, int detach_tsdf,
                        float *qual, float *rot, float *width, float *occ, void *stream);
-int giga_train_backward(giga_ctx *ctx, const float *g_qual, const float *g_rot, const float *g_width, const float *g_occ, void *stream);
+int giga_train_backward(giga_ctx *ctx, const float *g_qual, const float *g_rot, const float *g_width, const float *g_occ, float *g_p,
+                        void *stream);
 
 /* TSDF integration / read-out -------------------------------------------------
  * Replaces `TSDFVolume.integrate` / `get_grid` of vgn/perception.py:79-115, i.e. open3d.pipelines.integration.UniformTSDFVolume

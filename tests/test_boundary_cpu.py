@@ -134,5 +134,5 @@ def test_training_and_perception_host_surface():
         with pytest.raises(giga_b200.GigaError):
             perception.TSDFVolume(0.3, 40)
         assert lib.giga_train_forward(None, None, 1, None, 0, None, 0, 0, None, None, None, None, None) == -1
-        assert lib.giga_train_backward(None, None, None, None, None, None) == -1
+        assert lib.giga_train_backward(None, None, None, None, None, None, None) == -1
         assert lib.giga_tsdf_grid(None, None, None, 40, None, None) == -1

@@ -66,11 +66,12 @@ def _compare_grads(net, ref_leaves, second=None):
 
 
 def _gpu_autograd_reference(sd, x, p, pt, y, name="giga"):
-    """the same loss differentiated by PyTorch's own GPU kernels (fp32, TF32 off) through the opt-in bridge"""
+    """the same loss differentiated by PyTorch's own GPU kernels (fp32, TF32 off) through tests/torch_bridge.py"""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    net2 = make_net(name, sd, frozen=False).enable_training_bridge()
-    _loss(net2(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV)), y, DEV).backward()
+    from tests.torch_bridge import bridged_forward
+    net2 = make_net(name, sd, frozen=False)
+    _loss(bridged_forward(net2, x.to(DEV), p.to(DEV), pt.to(DEV)), y, DEV).backward()
     return {k: v.grad.detach().cpu() for k, v in net2.named_parameters()}
 
 
@@ -132,6 +133,25 @@ def test_model_variants(oracle_sd, name):
     lf(out, DEV).backward()
     lf(ref, "cpu").backward()
     _compare_grads(net, ref_leaves)
+
+
+def test_position_gradients_match_autograd(oracle_sd):
+    """d(outputs)/d(p) from the backward kernels (fc_p + grid_sampler's grid gradient, one-sided clamps, border clip) against CPU autograd
+    through the oracle, together with the parameter gradients of the same backward; points on / beyond the cube faces included"""
+    net = make_net("giga", oracle_sd, frozen=False)
+    x, p, _ = O.seeded_inputs(3, 200, seed=17)          # edge cases on: points outside [-0.5, 0.5] and exactly on +-0.5
+    pd = p.to(DEV).requires_grad_(True)
+    q, r, w = net(x.to(DEV), pd)
+    wts = torch.linspace(0.5, 1.5, 200)
+    (q * wts.to(DEV)).sum().backward(retain_graph=False)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in oracle_sd.items()}
+    pr = p.clone().requires_grad_(True)
+    qr, rr, wr = O.forward(leaves, x, pr)
+    (qr * wts).sum().backward()
+    scale = float(pr.grad.abs().max())
+    assert scale > 0
+    assert float((pd.grad.cpu() - pr.grad).abs().max()) <= 2e-4 * scale
+    _compare_grads(net, {k: v for k, v in leaves.items()})
 
 
 def test_one_forward_at_a_time(oracle_sd):

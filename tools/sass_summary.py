@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "giga_b200", "libgiga_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-OPS = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "FFMA2", "FFMA", "HMMA", "LDG", "STG", "LDS", "STS", "SHFL", "BAR"]
+OPS = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "FFMA2", "FFMA", "HMMA", "REDG", "LDG", "STG", "LDS", "STS", "SHFL", "BAR"]
 fn, counts, total = None, collections.OrderedDict(), collections.Counter()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -24,7 +24,7 @@ for line in out.splitlines():
     if m and fn:
         op = m.group(1)
         for o in OPS:
-            if op == o or (o in ("LDG", "STG", "LDS", "STS", "BAR", "SYNCS", "SHFL") and op.startswith(o)):
+            if op == o or (o in ("LDG", "STG", "LDS", "STS", "BAR", "SYNCS", "SHFL", "REDG") and op.startswith(o)):
                 counts[fn][o] += 1
                 total[o] += 1
                 break

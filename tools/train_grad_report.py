@@ -31,8 +31,9 @@ if os.environ.get("BRIDGE"):
     # differ on this batch (ReLU / max-pool decisions at near-ties are discontinuities of the gradient)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    net2 = make_net("giga", sd, frozen=False).enable_training_bridge()
-    out2 = net2(x.cuda(), p.cuda(), p_tsdf=pt.cuda())
+    from tests.torch_bridge import bridged_forward
+    net2 = make_net("giga", sd, frozen=False)
+    out2 = bridged_forward(net2, x.cuda(), p.cuda(), pt.cuda())
     _loss(out2, y, "cuda").backward()
     torch.cuda.synchronize()
     print("---- bridge (ATen/cuDNN on the GPU) vs CPU oracle, and native vs bridge ----")

@@ -2,7 +2,7 @@
 """BASELINE.json configs[3]: a scripts/train_giga.py-style step (forward + loss + backward + Adam, batch 64, one grasp point + 2048
 occupancy points per sample) on ONE GPU.  Three arms, same data:
   native   giga_train_forward / giga_train_backward (csrc/train_bwd.cuh) + fused loss + flat Adam (csrc/train.cuh): this library only
-  bridge   the round-1 opt-in bridge (forward by the library, backward = PyTorch recompute on ATen/cuDNN) + torch ops for loss/Adam
+  bridge   round 1's path, now test infrastructure (tests/torch_bridge.py: forward by the library, backward = PyTorch recompute on ATen/cuDNN) + torch ops for loss/Adam
 Prints ms/step, samples/s and the per-kernel device times of one native step."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -26,7 +26,7 @@ y = (label, rot_t, width_t, occ_t)
 
 def make(bridge):
     net = giga_b200.get_network("giga"); net.load_state_dict(O.seeded_state_dict(seed=1)); net = net.to(dev)
-    return net.enable_training_bridge() if bridge else net
+    return net
 
 
 def timed(fn, K=10, W=3):
@@ -72,11 +72,12 @@ print(f"  inference forward (tcgen05 path, re-commit once): {d:.2f} ms")
 del net, opt
 # ---- bridge (round-1 path) ----
 if not os.environ.get("TRAIN_NO_BRIDGE"):
+    from tests.torch_bridge import bridged_forward
     net = make(True)
     topt = torch.optim.Adam(net.parameters(), lr=2e-4)
     def bridge_step():
         topt.zero_grad(set_to_none=True)
-        qual, rot, width, occ = net(x, pos, p_tsdf=pos_occ)
+        qual, rot, width, occ = bridged_forward(net, x, pos, pos_occ)
         qual, rot, width = qual.squeeze(-1), rot.squeeze(1), width.squeeze(-1)
         l_qual = F.binary_cross_entropy(qual, label, reduction="none")
         l_rot = torch.min(1.0 - (rot * rot_t[:, 0]).sum(1).abs(), 1.0 - (rot * rot_t[:, 1]).sum(1).abs())
