@@ -34,6 +34,18 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void red_add(float* p, float a) { atomicAdd(p, a); }
+// (d0, d1) += (a0, a1) * (b0, b1) as ONE packed FFMA2
+__device__ __forceinline__ void fma2p(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n .reg .b64 d, a, b;\n mov.b64 d, {%0, %1};\n mov.b64 a, {%2, %3};\n mov.b64 b, {%4, %5};\n fma.rn.f32x2 d, a, b, d;\n mov.b64 {%0, %1}, d;\n}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// (d0, d1) += (a0, a1) * s as ONE packed FFMA2 on two scalar registers (the allocator pairs them)
+__device__ __forceinline__ void fma2s(float& d0, float& d1, float a0, float a1, float s) {
+  asm("{\n .reg .b64 d, a, b;\n mov.b64 d, {%0, %1};\n mov.b64 a, {%2, %3};\n mov.b64 b, {%4, %4};\n fma.rn.f32x2 d, a, b, d;\n mov.b64 {%0, %1}, d;\n}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(s));
+}
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // conv_in forward for training: the inference kernel body with its 27x32 weights in __constant__ memory, refreshed device-to-device
@@ -104,9 +116,9 @@ constexpr int DB_SAVE = 6 * 32 * DB_PTS;            // floats of scratch per til
 // dW[j][k0 + 8 kg + i] += sum_pt sG[j][pt] * sA[8 kg + i][pt]   (thread = (j, kg)); bias: db[j] += sum_pt sG[j][pt]
 __device__ __forceinline__ void wgrad_tile32(const float* sA, const float* sG, float* dW, int ldw, float* db, int tid) {
   const int j = tid >> 2, kg = tid & 3;
-  float acc[8];
+  float acc[8], acb[8];   // even / odd points: packed FFMA2 over point pairs, summed at the end
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 8; ++i) acc[i] = acb[i] = 0.f;
   float bs = 0.f;
   const float* gr = sG + db_row(j);
   const float* ar = sA + db_row(8 * kg);      // rows 8 kg .. 8 kg + 7 share one skew
@@ -117,10 +129,12 @@ __device__ __forceinline__ void wgrad_tile32(const float* sA, const float* sG, f
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 a = ld4(ar + i * DB_ST + p);
-      acc[i] = fmaf(g.x, a.x, acc[i]); acc[i] = fmaf(g.y, a.y, acc[i]);
-      acc[i] = fmaf(g.z, a.z, acc[i]); acc[i] = fmaf(g.w, a.w, acc[i]);
+      fma2p(acc[i], acb[i], g.x, g.y, a.x, a.y);
+      fma2p(acc[i], acb[i], g.z, g.w, a.z, a.w);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] += acb[i];
   float* d = dW + (size_t)j * ldw + 8 * kg;
   red_add4(d, acc[0], acc[1], acc[2], acc[3]);
   red_add4(d + 4, acc[4], acc[5], acc[6], acc[7]);
@@ -152,8 +166,8 @@ __device__ __forceinline__ void matvec32(const float* Wt, const float* x, float*
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
       const float4 w = wr[j4];
-      h[4 * j4 + 0] = fmaf(w.x, r, h[4 * j4 + 0]); h[4 * j4 + 1] = fmaf(w.y, r, h[4 * j4 + 1]);
-      h[4 * j4 + 2] = fmaf(w.z, r, h[4 * j4 + 2]); h[4 * j4 + 3] = fmaf(w.w, r, h[4 * j4 + 3]);
+      fma2s(h[4 * j4 + 0], h[4 * j4 + 1], w.x, w.y, r);
+      fma2s(h[4 * j4 + 2], h[4 * j4 + 3], w.z, w.w, r);
     }
   }
 }
@@ -257,8 +271,8 @@ decode_points_bwd_kernel(const float* __restrict__ planes,   // [3][B][40][40][3
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
         const float4 w = wr[j4];
-        h[4 * j4 + 0] = fmaf(w.x, f, h[4 * j4 + 0]); h[4 * j4 + 1] = fmaf(w.y, f, h[4 * j4 + 1]);
-        h[4 * j4 + 2] = fmaf(w.z, f, h[4 * j4 + 2]); h[4 * j4 + 3] = fmaf(w.w, f, h[4 * j4 + 3]);
+        fma2s(h[4 * j4 + 0], h[4 * j4 + 1], w.x, w.y, f);
+        fma2s(h[4 * j4 + 2], h[4 * j4 + 3], w.z, w.w, f);
       }
     }
 #pragma unroll
@@ -839,7 +853,7 @@ pool_bwd_kernel(const float* __restrict__ full, const float* __restrict__ gpool,
 constexpr int CB_THREADS = 320;
 constexpr int CB_XR = 43;                   // x-slab row stride ([iz + 1][iy + 1], iy fastest)
 constexpr int CB_XS = 42 * CB_XR;           // one ix plane of the staged volume
-constexpr int CB_GF = 321;                  // d f row stride (odd: conflict-free lane = channel reads)
+constexpr int CB_GF = 324;                  // d f row stride: 16-byte aligned rows, an odd number of 16-byte units (conflict-free lane = channel float4 reads)
 constexpr int CB_XTOT = round_up(3 * CB_XS, 4);   // the weight rows behind the slabs are read as float4
 constexpr int CB_SMEM_FLOATS = CB_XTOT + 28 * 32 + 2 * 32 * 40 + 32 * CB_GF;
 constexpr int CB_SMEM_BYTES = CB_SMEM_FLOATS * 4;
@@ -882,11 +896,12 @@ conv_in_bwd_kernel(const float* __restrict__ x,       // [B][40 ix][40 iy][40 iz
       __syncthreads();   // staging complete / previous sub-tile's phase 2 done
       {   // phase 1: voxel (iy = tid % 40, iz = 8 zt + tid / 40)
         const int iy = tid % G, izl = tid / G, iz = 8 * zt + izl;
-        float z[32], gy[32];
+        float2 z2[16];   // channel pairs: FFMA2 (each component the forward's own fma sequence: the ReLU mask is the forward's, bit for bit)
+        float gy[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) gy[c] = __ldg(gyz + (size_t)c * G2 + iz * G + iy);   // in flight during the 864 FMAs below
+        for (int c = 0; c < 32; ++c) gy[c] = __ldg(gyz + (size_t)c * G2 + iz * G + iy);   // in flight during the FMAs below
 #pragma unroll
-        for (int c = 0; c < 32; ++c) z[c] = ws[27 * 32 + c];
+        for (int c = 0; c < 16; ++c) z2[c] = make_float2(ws[27 * 32 + 2 * c], ws[27 * 32 + 2 * c + 1]);
 #pragma unroll
         for (int d = 0; d < 3; ++d)
 #pragma unroll
@@ -898,14 +913,14 @@ conv_in_bwd_kernel(const float* __restrict__ x,       // [B][40 ix][40 iy][40 iz
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
                 const float4 wv = wr[c4];
-                z[4 * c4 + 0] = fmaf(wv.x, xv, z[4 * c4 + 0]); z[4 * c4 + 1] = fmaf(wv.y, xv, z[4 * c4 + 1]);
-                z[4 * c4 + 2] = fmaf(wv.z, xv, z[4 * c4 + 2]); z[4 * c4 + 3] = fmaf(wv.w, xv, z[4 * c4 + 3]);
+                fma2(z2[2 * c4], make_float2(wv.x, wv.y), xv);
+                fma2(z2[2 * c4 + 1], make_float2(wv.z, wv.w), xv);
               }
             }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float gsum = (gxz[c * 40 + iz] + gxy[c * 40 + iy]) + gy[c];
-          gfs[c * CB_GF + tid] = z[c] > 0.f ? gsum / 40.0f : 0.f;
+          gfs[c * CB_GF + tid] = ((c & 1) ? z2[c >> 1].y : z2[c >> 1].x) > 0.f ? gsum / 40.0f : 0.f;
         }
       }
       __syncthreads();
@@ -913,15 +928,22 @@ conv_in_bwd_kernel(const float* __restrict__ x,       // [B][40 ix][40 iy][40 iz
         const float* gl = gfs + lane * CB_GF;
         const float* xb = xs + tdx * CB_XS + tdy;
 #pragma unroll 1
-        for (int iy = 0; iy < G; ++iy) {
-          // voxel (iy, iz = 8 zt + k): x(ix + dx - 1, iy + dy - 1, iz + dz - 1) = xs[dx][iz + dz][iy + dy]
-          float xw[10];
+        for (int iy = 0; iy < G; iy += 4) {
+          // voxels (iy .. iy + 3, iz = 8 zt + k): x(ix + dx - 1, iy + dy - 1, iz + dz - 1) = xs[dx][iz + dz][iy + dy]; four iy per 128-bit
+          // load of d f (the loop is shared-memory-issue bound)
+          float xw[10][4];
 #pragma unroll
-          for (int k = 0; k < 10; ++k) xw[k] = xb[(8 * zt + k) * CB_XR + iy];
+          for (int k = 0; k < 10; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xw[k][j] = xb[(8 * zt + k) * CB_XR + iy + j];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const float gv = gl[k * G + iy];
-            acc[0] = fmaf(gv, xw[k], acc[0]); acc[1] = fmaf(gv, xw[k + 1], acc[1]); acc[2] = fmaf(gv, xw[k + 2], acc[2]);
+            const float4 gv = ld4(gl + k * G + iy);
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz) {
+              acc[dz] = fmaf(gv.x, xw[k + dz][0], acc[dz]); acc[dz] = fmaf(gv.y, xw[k + dz][1], acc[dz]);
+              acc[dz] = fmaf(gv.z, xw[k + dz][2], acc[dz]); acc[dz] = fmaf(gv.w, xw[k + dz][3], acc[dz]);
+            }
           }
         }
       } else {
