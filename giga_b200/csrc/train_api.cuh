@@ -459,17 +459,16 @@ int giga_train_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, 
     // ---- tcgen05 U-Net (the inference kernels; the last layer unfused so that u1c2 exists), then every activation expanded to the NCHW fp32
     //      form the backward kernels read (hi + lo * 2^-11 carries 22 significant bits), conv_final on the expanded u1c2 ----
     unet_tall_forward(ctx, n_img, nullptr, /*keep_u1c2=*/true, st);
-    for (int i = 0; i < kNumActs; ++i) {
-      const int hw = kActs[i].hw, c8 = kActs[i].ch / 8;
-      const float* tsrc = ctx->d_tall[1 + i];
-      const long ps = ctx->tall_ps[1 + i];
-      const int blocks = ceil_div(n_img * c8 * hw * hw, 256);
-      LaunchScope ls(ctx, "train:tall_to_nchw", st);
-      if (hw == 40 && c8 == 4) tall_to_nchw_kernel<40, 4><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
-      else if (hw == 20 && c8 == 4) tall_to_nchw_kernel<20, 4><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
-      else if (hw == 20 && c8 == 8) tall_to_nchw_kernel<20, 8><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
-      else if (hw == 10 && c8 == 8) tall_to_nchw_kernel<10, 8><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
-      else tall_to_nchw_kernel<10, 16><<<blocks, 256, 0, st>>>(tsrc, ctx->d_act[i], ps, n_img);
+    {
+      ExpandArgs X = {};
+      X.n_img = n_img;
+      int max_blocks = 0;
+      for (int i = 0; i < kNumActs; ++i) {
+        X.e[i] = {ctx->d_tall[1 + i], ctx->d_act[i], ctx->tall_ps[1 + i], kActs[i].hw, kActs[i].ch / 8};
+        max_blocks = std::max(max_blocks, ceil_div(n_img * (kActs[i].ch / 8) * kActs[i].hw * kActs[i].hw, 256));
+      }
+      LaunchScope ls(ctx, "train:expand_activations", st);
+      tall_expand_all_kernel<<<dim3(max_blocks, kNumActs), 256, 0, st>>>(X);
     }
     {
       LaunchScope ls(ctx, "train:conv_final", st);

@@ -25,6 +25,7 @@
 #include "conv_in.cuh"
 #include "decoder.cuh"
 #include "unet.cuh"
+#include "unet_tall.cuh"
 
 namespace giga {
 
@@ -67,6 +68,28 @@ conv_in_planes_train_kernel(const __grid_constant__ CUtensorMap tmap, float* __r
       default: conv_in_body<CI_TY, 4, 3>(&tmap, tall, ps, xz_part, B, c_conv_in_train, smem_ci); break;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Every TALL pre-split activation of the tensor-core forward -> the NCHW fp32 form the backward kernels read, in ONE launch
+// (tall_to_nchw_kernel per layer took 15 launches): blockIdx.y = layer, blocks past a layer's size exit.
+struct ExpandEntry { const float* src; float* dst; long ps; int hw, c8; };
+struct ExpandArgs { ExpandEntry e[16]; int n_img; };
+
+__global__ void __launch_bounds__(256) tall_expand_all_kernel(const __grid_constant__ ExpandArgs A) {
+  const ExpandEntry& E = A.e[blockIdx.y];
+  const int hw2 = E.hw * E.hw;
+  const long t = (long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long)A.n_img * E.c8 * hw2) return;
+  const int pix = (int)(t % hw2);
+  const int kc = (int)((t / hw2) % E.c8);
+  const int img = (int)(t / ((long)hw2 * E.c8));
+  const long pos = TALL_MARGIN + tall_pos(E.hw, img, pix / E.hw, pix % E.hw);
+  float v[8];
+  join8(ldu4(E.src + ((size_t)kc * E.ps + pos) * 4), ldu4(E.src + ((size_t)(E.c8 + kc) * E.ps + pos) * 4), v);
+  float* p = E.dst + ((size_t)img * (8 * E.c8) + 8 * kc) * hw2 + pix;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[(size_t)j * hw2] = v[j];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
