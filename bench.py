@@ -482,7 +482,7 @@ def main():
             # fwd+bwd ~ 3x the forward's FLOPs: 3.72 GFLOP per sample
             tps = 64 * args.steps / (train_ms * 1e-3)
             out["train"] = {"workload": f"configs[3]: train_giga.py step, global batch 64 ({64 // world}/GPU x {world}), 1 grasp pt + 2048 occupancy pts per sample, "
-                                        "native forward + fused loss + native backward + flat all-reduce + flat Adam, fp32 (FMA pipe)",
+                                        "forward on the tcgen05 kernels (device-packed operands) + fused loss + native backward (fp32 FMA pipe) + flat all-reduce + flat Adam",
                             "value": tps, "unit": "samples/s", "ms_per_step": train_ms / args.steps, "scaling": "strong",
                             "tflops_fp32": round(3.72e9 * tps / 1e12, 2), **train_info}
         print(json.dumps(out))
