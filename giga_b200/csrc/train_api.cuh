@@ -428,7 +428,8 @@ int giga_train_forward(giga_ctx* ctx, const float* tsdf, int B, const float* p, 
     train_pack_kernel<<<dim3(T.n_tab, 4), 256, 0, st>>>(T.d_tab);
   }
   CU_TRY(cudaMemcpyToSymbolAsync(c_conv_in_train, T.d_cin, sizeof(ConvInParams), 0, cudaMemcpyDeviceToDevice, st));
-  // ---- encoder: the inference conv_in body (weights from constant memory) + the fp32 FMA-pipe U-Net, every activation kept ----
+  // ---- encoder: the inference conv_in body (weights from constant memory), then the U-Net on the tcgen05 kernels (default) or on the fp32
+  //      FMA-pipe kernels; every activation is kept (NCHW fp32) for the backward ----
   const int n_img = 3 * B;
   float* tall_pre = ctx->d_tall[0];
   const long ps_pre = ctx->tall_ps[0];
