@@ -96,6 +96,30 @@ def test_native_forward_and_every_parameter_gradient(oracle_sd, B, No, fwd_impl)
     _compare_grads(net, ref_leaves, second=_gpu_autograd_reference(oracle_sd, x, p, pt, y))
 
 
+@pytest.mark.parametrize("B,Ng,No", [(2, 130, 64), (1, 257, 1)])
+def test_many_grasp_points_per_scene(oracle_sd, B, Ng, No):
+    """grasp heads differentiated at more than one 128-point tile per scene (ragged last tile), a single scene, a single occupancy point"""
+    net = make_net("giga", oracle_sd, frozen=False)
+    x, p, _ = O.seeded_inputs(B, Ng, seed=61)
+    _, _, pt = O.seeded_inputs(B, No, seed=62)
+    g = torch.Generator().manual_seed(5)
+    wq, wr, ww, wo = torch.randn(B, Ng, generator=g), torch.randn(B, Ng, 4, generator=g), torch.randn(B, Ng, generator=g), torch.randn(B, No, generator=g)
+    lf = lambda o, dev: (o[0] * wq.to(dev)).sum() + (o[1] * wr.to(dev)).sum() + (o[2] * ww.to(dev)).sum() + (o[3] * wo.to(dev)).sum()
+    out = net(x.to(DEV), p.to(DEV), p_tsdf=pt.to(DEV))
+    leaves = {k: v.clone().requires_grad_(True) for k, v in oracle_sd.items()}
+    ref = O.forward(leaves, x, p, pt)
+    for a, b in zip(out, ref):
+        assert (a.detach().cpu() - b.detach()).abs().max().item() <= 1e-4
+    lf(out, DEV).backward()
+    lf(ref, "cpu").backward()
+    from tests.torch_bridge import bridged_forward
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net2 = make_net("giga", oracle_sd, frozen=False)
+    lf(bridged_forward(net2, x.to(DEV), p.to(DEV), pt.to(DEV)), DEV).backward()
+    _compare_grads(net, leaves, second={k: v.grad.detach().cpu() for k, v in net2.named_parameters()})
+
+
 def test_gradients_accumulate_and_upstream_scale(oracle_sd):
     """a second backward adds to .grad (autograd semantics); gradients are linear in the upstream gradient"""
     net = make_net("giga", oracle_sd, frozen=False)

@@ -28,6 +28,28 @@ def test_integration_and_grid_bit_exact(seed, R, n_views):
     assert ref.weight.max() == n_views
 
 
+def test_other_camera_and_volume_geometry():
+    """a non-square image with an off-centre principal point, a larger volume, views from below the table plane (many voxels behind or
+    outside the frustum), and a depth image with holes (zeros) and far readings (>= depth_trunc)"""
+    rng = np.random.default_rng(3)
+    intr = TO.Intrinsic(200, 150, 180.0, 175.0, 90.5, 80.25)
+    boxes = [((0.1, 0.1, 0.05), (0.2, 0.25, 0.3)), ((0.3, 0.3, 0.05), (0.38, 0.36, 0.12))]
+    Ts, imgs = [], []
+    for k, eye in enumerate([(0.9, 0.2, 0.6), (-0.4, 0.25, 0.5), (0.25, 0.25, 1.2), (0.25, -0.6, -0.1)]):
+        T = TO.look_at(eye, (0.25, 0.25, 0.1))
+        d = TO.render_depth(intr, T, boxes, noise=0.001, rng=rng)
+        d[rng.random(d.shape) < 0.05] = 0.0           # holes
+        d[:10] = 2.5                                    # beyond depth_trunc: dropped at RGBD creation
+        Ts.append(T); imgs.append(d)
+    imgs, Ts = np.stack(imgs), np.stack(Ts)
+    for R in (40, 64):
+        ref = TO.create_tsdf(0.5, R, imgs, intr, Ts)
+        vol = perception.create_tsdf(0.5, R, imgs, _intr(intr), Ts)
+        assert np.array_equal(vol._weight.cpu().numpy(), ref.weight) and np.array_equal(vol._tsdf.cpu().numpy(), ref.tsdf)
+        assert np.array_equal(vol.get_grid(), ref.get_grid())
+        assert 0 < (ref.weight > 0).mean() < 1
+
+
 def test_incremental_integrate_equals_batched_and_order_matters():
     imgs, intr, Ts = TO.seeded_scene(7, n_views=5)
     a = perception.TSDFVolume(0.3, 40)
