@@ -415,6 +415,7 @@ int ensure_tsdf_maps(giga_ctx* ctx, const float* tsdf, int B) {
 int ensure_workspace(giga_ctx* ctx, int B) {
   if (B <= ctx->cap_B) return GIGA_OK;
   ctx->graph_epoch++;
+  ctx->tr.fwd_valid = false;   // the kept activations of a training forward are about to be freed
   CU_TRY(cudaDeviceSynchronize());
   if (ctx->d_pre) cudaFree(ctx->d_pre);
   if (ctx->d_xzpart) cudaFree(ctx->d_xzpart);
@@ -1067,6 +1068,7 @@ int giga_encode(giga_ctx* ctx, const float* tsdf, int B, float* planes, void* st
     return GIGA_OK;
   }
   ctx->last_impl = 0;
+  ctx->tr.fwd_valid = false;   // this path overwrites the NCHW activations a pending giga_train_backward would read
   {   // the fp32 FMA-pipe U-Net reads NCHW fp32 planes: expand the pre-split planes (hi + lo * 2^-11 carries 22 significant bits)
     LaunchScope ls(ctx, "tall_to_nchw:pre", st);
     tall_to_nchw_kernel<40, 4><<<ceil_div(n_img * 4 * G2, 256), 256, 0, st>>>(tall_pre, ctx->d_pre, ps_pre, n_img);
