@@ -250,6 +250,8 @@ struct giga_ctx {
     float* d_gplanes = nullptr;   // [3][B][1600][32]
     float* d_planes = nullptr;    // forward plane features
     float* d_save = nullptr;      // decoder backward scratch
+    unsigned* d_wg_counters = nullptr;   // [16 launches][16 (co, ci) tiles] dynamic tile counters of the filter-gradient kernels
+    int wg_slot = 0;
     size_t save_cap = 0;
     // the forward this backward belongs to
     const float *x = nullptr, *p = nullptr, *pt = nullptr;
@@ -695,7 +697,7 @@ void giga_ctx_destroy(giga_ctx* ctx) {
   }
   {
     auto& T = ctx->tr;   // (d_blob / d_heads alias ctx->d_enc / ctx->d_heads)
-    void* tp[] = {T.d_tab, T.d_cin, T.d_tctab, T.d_hscale, T.d_gpre, T.d_gplanes, T.d_planes, T.d_save};
+    void* tp[] = {T.d_tab, T.d_cin, T.d_tctab, T.d_hscale, T.d_gpre, T.d_gplanes, T.d_planes, T.d_save, T.d_wg_counters};
     for (void* q : tp)
       if (q) cudaFree(q);
     for (float* q : T.d_g)

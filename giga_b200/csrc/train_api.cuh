@@ -170,8 +170,9 @@ void launch_wgrad(giga_ctx* ctx, const char* name, int n_img, const float* gz, c
                   float* db, cudaStream_t st) {
   const int n_cc = (cout / 32) * (cin_src / 32), n_tiles = n_img * K::NB;
   const int P = std::max(1, std::min(n_tiles, (3 * ctx->num_sms + n_cc - 1) / n_cc));
+  unsigned* counters = ctx->tr.d_wg_counters + 16 * (ctx->tr.wg_slot++ % 16);   // zeroed at the start of the backward
   LaunchScope ls(ctx, name, st);
-  conv3x3_wgrad_kernel<K><<<dim3(n_cc, P), 256, K::SMEM_BYTES, st>>>(gz, in, n_img, cout, cin_src, dW, cin_total, db);
+  conv3x3_wgrad_kernel<K><<<dim3(n_cc, P), 256, K::SMEM_BYTES, st>>>(gz, in, n_img, cout, cin_src, dW, cin_total, db, counters);
 }
 
 template <class K>
@@ -561,6 +562,9 @@ int giga_train_backward(giga_ctx* ctx, const float* g_qual, const float* g_rot, 
   bool enc_grad = false;
   for (int h = 0; h < 4; ++h) enc_grad |= gouts[h] && !(h == 3 && T.detach);
   if (enc_grad) CU_TRY(cudaMemsetAsync(T.d_gplanes, 0, sizeof(float) * 3 * (size_t)B * C * G2, st));
+  if (!T.d_wg_counters) CU_TRY(cudaMalloc(&T.d_wg_counters, sizeof(unsigned) * 256));
+  CU_TRY(cudaMemsetAsync(T.d_wg_counters, 0, sizeof(unsigned) * 256, st));   // work counters of the 14 filter-gradient launches
+  T.wg_slot = 0;
   // ---- heads: ONE launch, blockIdx.z = (head with a gradient), each at its own point set ----
   {
     DecBwdArgs A = {};

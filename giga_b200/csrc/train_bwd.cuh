@@ -618,7 +618,8 @@ conv3x3_wgrad_kernel(const float* __restrict__ gz,    // [n_img][COUT][HW][HW]  
                      const float* __restrict__ in,    // [n_img][CIN_SRC][HW][HW]
                      int n_img, int COUT, int CIN_SRC,
                      float* __restrict__ dW,          // [COUT][CIN_TOTAL][3][3], already offset to this source's first input channel
-                     int CIN_TOTAL, float* __restrict__ db) {   // db: null for the second source of a concat
+                     int CIN_TOTAL, float* __restrict__ db,     // db: null for the second source of a concat
+                     unsigned* __restrict__ next_tile) {        // [co tiles * ci tiles] zeroed work counters: tiles are handed out dynamically
   constexpr int HW = K::HW, R = K::R, GPR = K::GPR, GW = K::GW, CS = K::CS, PSX = K::PSX, GST = K::GST;
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;                 // [32 ci][R + 2][CS]
@@ -634,10 +635,15 @@ conv3x3_wgrad_kernel(const float* __restrict__ gz,    // [n_img][COUT][HW][HW]  
     for (int t = 0; t < 9; ++t) acc[k][t] = make_float2(0.f, 0.f);
   float2 bacc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   const int n_tiles = n_img * K::NB;
+  __shared__ int s_tile;
 #pragma unroll 1
-  for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
-    const int img = tile / K::NB, y0 = (tile % K::NB) * R;
+  for (;;) {
+    __syncthreads();   // the previous tile's reads of xs / gs (and of s_tile) are done
+    if (tid == 0) s_tile = (int)atomicAdd(next_tile + blockIdx.x, 1u);   // (a static stride leaves the SMs 4 or 5 tiles each: 14 % tail)
     __syncthreads();
+    const int tile = s_tile;
+    if (tile >= n_tiles) break;
+    const int img = tile / K::NB, y0 = (tile % K::NB) * R;
     for (int e = tid; e < 32 * (R + 2) * CS; e += 256) {
       const int c = e / ((R + 2) * CS), rem = e % ((R + 2) * CS), r = rem / CS, col = rem % CS;
       const int y = y0 + r - 1, xx = col - 4;
